@@ -1,0 +1,184 @@
+/* libvcb200 -- C ABI of the B200-native detect + ReID hot path for kaylode/vehicle-counting.
+ *
+ * The reference has no FFI: its boundary is the Python call surface
+ *   networks/yolo.py:68-99            YoloBackbone.detect      (detector forward + NMS)
+ *   networks/detector.py:36-38        Detector.inference_step
+ *   networks/deepsort/deep/feature_extractor.py:26-47   Extractor._preprocess / __call__
+ *   networks/deepsort/deep_sort.py:119-129              DeepSort._get_features (ROI crops)
+ * Every numeric library call those functions make (cuDNN conv via torch, ATen pointwise,
+ * torchvision.ops.nms, cv2.resize) is replaced by one entry point below.  The Python mirror of the
+ * reference classes (vehicle_counting_b200/networks/...) binds them with ctypes; INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; all pointers are DEVICE pointers owned by the caller
+ * unless a parameter is documented as host memory; work is enqueued on the caller's stream, no hidden
+ * synchronisation; return 0 on success, a negative VCB_ERR_* otherwise (vcb_last_error_string() has
+ * the detail); nothing throws across the ABI; sm_100 only -- any other device is VCB_ERR_ARCH (there
+ * is no fallback path).  Activations are NHWC fp16 with an explicit channel pitch so that several
+ * producers can write disjoint channel slices of one buffer (concat-free).
+ */
+#ifndef VCB200_H_
+#define VCB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vcb_stream_t; /* cudaStream_t */
+
+enum {
+  VCB_OK = 0,
+  VCB_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  VCB_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
+  VCB_ERR_ARCH = -3,        /* device is not sm_100 */
+  VCB_ERR_FAULT = -4        /* a kernel recorded a pipeline fault (see vcb_last_fault) */
+};
+
+enum { VCB_ACT_NONE = 0, VCB_ACT_SILU = 1, VCB_ACT_RELU = 2 };
+enum { VCB_RES_NONE = 0, VCB_RES_AFTER_ACT = 1, VCB_RES_BEFORE_ACT = 2 };
+enum { VCB_F16 = 0, VCB_F32 = 1 };
+enum { VCB_A_AUTO = 0, VCB_A_IM2COL_TMA = 1, VCB_A_GATHER = 2, VCB_A_C4 = 3 };
+
+/* ---- library state ------------------------------------------------------------------------ */
+int vcb_init(int device);                 /* selects device, checks sm_100, resolves driver entry points */
+const char* vcb_last_error_string(void);  /* thread-local, never NULL */
+int vcb_last_fault(int32_t out4[4]);      /* host: {code, block, info0, info1} of the last kernel fault */
+int vcb_version(void);
+
+/* ---- K1: implicit-GEMM convolution on tcgen05 (replaces torch Conv2d+BN+SiLU / ReLU, reference
+ *      call sites networks/yolo.py:70 [upstream DetectionModel] and deepsort/deep/model.py:83-95) --- */
+typedef struct VcbConvDesc {
+  int32_t n, h, w;            /* input batch, height, width */
+  int32_t cin, cin_pitch;     /* logical input channels; channel pitch of x in elements */
+  int32_t cout, cout_pitch;   /* logical output channels; channel pitch of y in elements */
+  int32_t kh, kw, stride, pad;
+  int32_t act;                /* VCB_ACT_* applied after bias */
+  int32_t res_mode;           /* VCB_RES_*: residual tensor has the output's shape */
+  int32_t res_pitch;          /* channel pitch of the residual (elements) */
+  int32_t out_dtype;          /* VCB_F16 or VCB_F32 */
+  int32_t a_mode;             /* VCB_A_*: how the im2col operand reaches shared memory */
+  int32_t block_n;            /* 0 = auto; N tile (multiple of 16, <= 256) */
+  int32_t stages;             /* 0 = auto; smem pipeline depth */
+  int32_t reserved[4];
+} VcbConvDesc;
+
+/* element counts of the packed fp16 weight blob and the padded fp32 bias for this descriptor */
+int vcb_conv_packed_sizes(const VcbConvDesc* d, int64_t* weight_halfs, int64_t* bias_floats);
+/* w_oihw: fp32 [cout][cin][kh][kw] with BN already folded; bias may be NULL (zeros) */
+int vcb_conv_pack_weights(const VcbConvDesc* d, const float* w_oihw, const float* bias, void* w_packed,
+                          float* bias_packed, vcb_stream_t stream);
+int vcb_conv2d_fwd(const VcbConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
+                   const void* residual, void* y, vcb_stream_t stream);
+/* output spatial size for a descriptor */
+int vcb_conv_out_hw(const VcbConvDesc* d, int32_t* ho, int32_t* wo);
+
+/* ---- K2: data-movement / pooling kernels (upstream Upsample, SPPF max-pools, ReID MaxPool2d) --- */
+/* uint8 RGB/BGR HWC frames -> fp16 NHWC4 (4th channel zero), value/255 (AutoShape: x/255) */
+int vcb_frames_to_f16c4(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t stream);
+/* nearest x2 upsample of a channel slice into a channel slice (nn.Upsample(None, 2, 'nearest')) */
+int vcb_upsample2x(const void* src, int32_t src_pitch, void* dst, int32_t dst_pitch, int32_t n, int32_t h,
+                   int32_t w, int32_t c, vcb_stream_t stream);
+/* SPPF: buf holds x in channels [0,c) of pitch `pitch`; writes mp5(x), mp5^2(x), mp5^3(x) into
+ * channels [c,2c), [2c,3c), [3c,4c) (stride 1, pad 2, -inf padding) */
+int vcb_sppf_pool(void* buf, int32_t pitch, int32_t n, int32_t h, int32_t w, int32_t c, vcb_stream_t stream);
+/* MaxPool2d(k, s, p) NHWC fp16 */
+int vcb_maxpool(const void* src, int32_t src_pitch, void* dst, int32_t dst_pitch, int32_t n, int32_t h, int32_t w,
+                int32_t c, int32_t k, int32_t s, int32_t p, vcb_stream_t stream);
+
+/* ---- K3: Detect decode + confidence filter + best class (upstream Detect.forward inference branch and
+ *      the filtering half of non_max_suppression) ---------------------------------------------- */
+typedef struct VcbDetectLevel {
+  const void* logits;      /* fp16 or fp32 [n][ny][nx][pitch], channel = anchor*no + field */
+  int32_t pitch;
+  int32_t ny, nx;
+  float stride;
+  float anchor_w[3], anchor_h[3];   /* pixels */
+} VcbDetectLevel;
+
+typedef struct VcbDetectDesc {
+  int32_t n;               /* frames */
+  int32_t nc;              /* classes (no = nc + 5) */
+  int32_t num_levels;      /* <= 4 */
+  int32_t logits_dtype;    /* VCB_F16 / VCB_F32 */
+  float conf_thres;
+  int32_t max_candidates;  /* capacity per frame of the candidate arrays */
+  VcbDetectLevel level[4];
+} VcbDetectDesc;
+
+/* cand_box: float [n][max_candidates][4] xyxy (inference-image pixels); cand_score: float; cand_cls: int32;
+ * cand_index: int32 global prediction index (level order, then anchor, y, x); cand_count: int32 [n]
+ * (zeroed by this call).  Candidate order within a frame is unspecified; vcb_nms sorts. */
+int vcb_detect_decode(const VcbDetectDesc* d, float* cand_box, float* cand_score, int32_t* cand_cls,
+                      int32_t* cand_index, int32_t* cand_count, vcb_stream_t stream);
+
+/* ---- K4: class-aware greedy NMS (upstream non_max_suppression tail + torchvision.ops.nms) ------ */
+typedef struct VcbNmsDesc {
+  int32_t n;               /* frames */
+  int32_t max_candidates;  /* stride of the candidate arrays */
+  int32_t max_det;         /* 300 */
+  float iou_thres;         /* suppress iff IoU > thr */
+  float max_wh;            /* class offset (4096 in v6.0) */
+  int32_t max_nms;         /* 30000: keep only the top-scoring max_nms candidates */
+  /* scale_coords: (x - pad_x) / gain, clip to [0, w0] x [0, h0]; per frame arrays of length n, may be NULL */
+  const float* gain;
+  const float* pad_x;
+  const float* pad_y;
+  const float* w0;
+  const float* h0;
+} VcbNmsDesc;
+
+/* bytes of the sort workspace vcb_nms needs for n frames of max_candidates slots */
+int64_t vcb_nms_workspace_bytes(int32_t n, int32_t max_candidates);
+/* sort_ws: workspace of vcb_nms_workspace_bytes() bytes (only touched when a frame has more than 8192
+ * candidates; smaller frames sort in shared memory).  det: float [n][max_det][6] = x1,y1,x2,y2,conf,cls
+ * sorted by descending score (ties: lower prediction index first); det_count: int32 [n]. */
+int vcb_nms(const VcbNmsDesc* d, const float* cand_box, const float* cand_score, const int32_t* cand_cls,
+            const int32_t* cand_index, const int32_t* cand_count, uint64_t* sort_ws, float* det,
+            int32_t* det_count, vcb_stream_t stream);
+
+/* ---- K5: ROI crop + bilinear resize + normalise (deep_sort.py:119-129 + feature_extractor.py:26-39) --- */
+typedef struct VcbRoiDesc {
+  int32_t num_rois;
+  int32_t out_size;        /* 50 */
+  float mean[3], inv_std[3];   /* applied to channel 0,1,2 of the stored frame order */
+} VcbRoiDesc;
+/* frames: uint8 [*][fh][fw][3]; rois: int32 [num_rois][5] = frame, x1, y1, x2, y2 (already int-truncated and
+ * clipped, end exclusive); out: fp16 [num_rois][out][out][4] (4th channel zero) */
+int vcb_roi_resize_norm(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, int32_t fw, const int32_t* rois,
+                        void* out, vcb_stream_t stream);
+/* float64 xyxy boxes -> the reference's integer crop rectangle (deep_sort.py:78-95), on device.
+ * boxes: double [num][4]; frame_of: int32 [num]; rois out: int32 [num][5] */
+int vcb_boxes_to_rois(const double* boxes_xyxy, const int32_t* frame_of, int32_t num, int32_t fw, int32_t fh,
+                      int32_t* rois, vcb_stream_t stream);
+
+/* ---- K6/K7: ReID tails (model.py:71, :93-95) and train-mode BatchNorm (feature_extractor.py:10-22) ---- */
+/* x: fp16 [n][hw][pitch] -> out fp32 [n][c]: mean over hw positions then L2 normalise */
+int vcb_avgpool_l2norm(const void* x, int32_t pitch, int32_t n, int32_t hw, int32_t c, float* out,
+                       vcb_stream_t stream);
+/* per-(segment, channel) batch statistics of fp32 x [rows][c]; seg_row_start: int32 [num_seg+1] row
+ * offsets (rows = crops*hw).  Writes scale/shift fp32 [num_seg][c] so that y = x*scale + shift equals
+ * BatchNorm2d in training mode (biased variance, eps) with affine gamma/beta. */
+int vcb_bn_train_stats(const float* x, int32_t c, const int32_t* seg_row_start, int32_t num_seg,
+                       const float* gamma, const float* beta, float eps, float* scale, float* shift,
+                       vcb_stream_t stream);
+/* y(fp16, pitch) = act(x*scale[seg]+shift[seg] (+ residual)), x fp32 [rows][c]; row_seg: int32 [rows] */
+int vcb_bn_apply(const float* x, int32_t c, int32_t rows, const int32_t* row_seg, const float* scale,
+                 const float* shift, const void* residual, int32_t res_pitch, int32_t act, void* y,
+                 int32_t y_pitch, vcb_stream_t stream);
+
+/* ---- whole-path executor: the calls above, issued once on a capturing stream, become one CUDA
+ *      graph that is replayed per batch (tensor maps and shapes are baked in as kernel parameters) --- */
+typedef struct VcbGraph VcbGraph;
+int vcb_graph_begin(vcb_stream_t stream);                 /* cudaStreamBeginCapture (stream must not be 0) */
+int vcb_graph_end(vcb_stream_t stream, VcbGraph** out);   /* end capture + instantiate */
+int vcb_graph_launch(VcbGraph* g, vcb_stream_t stream);
+int vcb_graph_num_kernels(const VcbGraph* g);             /* kernel nodes in the captured graph */
+int vcb_graph_destroy(VcbGraph* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCB200_H_ */

@@ -1,0 +1,162 @@
+"""GPU bring-up matrix for the tcgen05 conv kernel (not a pytest file; run under gpurun).
+
+Each case runs in its own subprocess so that a trapped kernel (bounded mbarrier wait) cannot poison
+the CUDA context of the others.  The checker is torch's fp32 conv2d on the same fp16-rounded
+operands (test infrastructure only).  Usage:
+    python tests/bringup_conv.py            # whole matrix
+    python tests/bringup_conv.py --case 3   # one case, in-process
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+# (name, dict)
+CASES = []
+
+
+def case(name, **kw):
+    base = dict(n=1, h=16, w=16, cin=64, cout=64, k=1, s=1, p=0, act="none", res="none", out="f16", mode="tma",
+                cin_pitch=None, cout_pitch=None, block_n=0, stages=0)
+    base.update(kw)
+    CASES.append((name, base))
+
+
+for mode in ("gather", "tma"):
+    case(f"{mode}-1x1-k64", mode=mode)
+    case(f"{mode}-1x1-k128-n128", mode=mode, cin=128, cout=128)
+    case(f"{mode}-3x3-s1", mode=mode, n=2, h=20, w=20, k=3, p=1)
+    case(f"{mode}-3x3-s2-odd", mode=mode, n=3, h=25, w=25, k=3, s=2, p=1, cin=64, cout=128, act="relu")
+    case(f"{mode}-1x1-s2-odd", mode=mode, n=3, h=13, w=13, k=1, s=2, p=0, cin=128, cout=256)
+    case(f"{mode}-cin48-cout48", mode=mode, n=2, h=40, w=40, k=3, p=1, cin=48, cout=48, act="silu")
+    case(f"{mode}-cin96-cout192-res", mode=mode, n=2, h=40, w=40, k=3, p=1, cin=96, cout=192, act="silu", res="after")
+    case(f"{mode}-cout255-f32", mode=mode, n=2, h=20, w=20, cin=128, cout=255, cout_pitch=256, out="f32")
+    case(f"{mode}-cout384-2tiles", mode=mode, n=2, h=20, w=20, k=3, p=1, cin=192, cout=384, act="silu")
+    case(f"{mode}-pitch-slices", mode=mode, n=2, h=20, w=20, k=1, cin=64, cout=64, cin_pitch=128, cout_pitch=192, act="silu")
+    case(f"{mode}-resbefore-relu", mode=mode, n=4, h=13, w=13, k=3, p=1, cin=128, cout=128, act="relu", res="before")
+    case(f"{mode}-big-persistent", mode=mode, n=8, h=80, w=80, k=3, p=1, cin=128, cout=256, act="silu")
+    case(f"{mode}-blockn64-stages3", mode=mode, n=2, h=40, w=40, k=3, p=1, cin=64, cout=128, block_n=64, stages=4)
+case("c4-yolo-stem", mode="c4", n=2, h=64, w=64, cin=3, cin_pitch=4, cout=32, k=6, s=2, p=2, act="silu")
+case("c4-reid-stem", mode="c4", n=5, h=50, w=50, cin=3, cin_pitch=4, cout=64, k=3, s=1, p=1, act="relu")
+case("c4-yolo-stem-big", mode="c4", n=4, h=640, w=640, cin=3, cin_pitch=4, cout=48, k=6, s=2, p=2, act="silu")
+
+
+def run_case(idx: int) -> dict:
+    import torch
+    import torch.nn.functional as F
+    from vehicle_counting_b200 import _lib as L, ops
+
+    name, c = CASES[idx]
+    L.init(0)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1234 + idx)
+    n, h, w, cin, cout, k, s, p = (c[x] for x in ("n", "h", "w", "cin", "cout", "k", "s", "p"))
+    cin_pitch = c["cin_pitch"] or cin
+    mode = {"tma": L.A_IM2COL_TMA, "gather": L.A_GATHER, "c4": L.A_C4}[c["mode"]]
+    act = {"none": L.ACT_NONE, "silu": L.ACT_SILU, "relu": L.ACT_RELU}[c["act"]]
+    res_mode = {"none": L.RES_NONE, "after": L.RES_AFTER_ACT, "before": L.RES_BEFORE_ACT}[c["res"]]
+    cout_store = (cout + 7) // 8 * 8
+    cout_pitch = c["cout_pitch"] or cout_store
+
+    x_full = (torch.randn(n, h, w, cin_pitch, generator=g) * 1.0).half()
+    if c["mode"] == "c4":
+        x_full[..., 3] = 0
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).half().float()
+    bias = torch.randn(cout, generator=g) * 0.5
+    d = ops.make_conv_desc(n, h, w, cin, cout, k, s, p, cin_pitch=cin_pitch, cout_pitch=cout_pitch, act=act,
+                           res_mode=res_mode, res_pitch=cout_pitch if res_mode else 0,
+                           out_dtype=L.F32 if c["out"] == "f32" else L.F16, a_mode=mode, block_n=c["block_n"], stages=c["stages"])
+    ho, wo = ops.conv_out_hw(d)
+    res_full = (torch.randn(n, ho, wo, cout_pitch, generator=g)).half() if res_mode else None
+
+    # reference (fp32 math on the fp16-rounded operands)
+    xr = x_full[..., :cin].float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xr, wt, bias, s, p)
+    if res_mode == L.RES_BEFORE_ACT:
+        ref = ref + res_full[..., :cout].float().permute(0, 3, 1, 2)
+    if act == L.ACT_SILU:
+        ref = F.silu(ref)
+    elif act == L.ACT_RELU:
+        ref = F.relu(ref)
+    if res_mode == L.RES_AFTER_ACT:
+        ref = ref + res_full[..., :cout].float().permute(0, 3, 1, 2)
+    ref = ref.permute(0, 2, 3, 1).contiguous()                    # NHWC
+
+    xd = x_full.to(dev)
+    wp, bp = ops.pack_conv_weights(d, wt.to(dev), bias.to(dev))
+    out_dtype = torch.float32 if c["out"] == "f32" else torch.float16
+    y = torch.full((n, ho, wo, cout_pitch), 777.0, dtype=out_dtype, device=dev)
+    resd = res_full.to(dev) if res_full is not None else None
+    torch.cuda.synchronize()
+    t0 = time.time()
+    ops.conv2d(d, xd, wp, bp, y, residual=resd)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    got = y.float().cpu()
+    err = (got[..., :cout] - ref).abs()
+    scale = ref.abs().max().item()
+    out = {"case": name, "idx": idx, "max_abs_err": err.max().item(), "ref_max": scale,
+           "rel": err.max().item() / max(scale, 1e-9), "ms_first_call": dt * 1e3}
+    # untouched padding channels must keep the sentinel (beyond cout_store) -- checks slice writes
+    if cout_pitch > cout_store:
+        out["pad_untouched"] = bool((got[..., cout_store:] == 777.0).all().item())
+    if out["rel"] > 5e-3:
+        e2 = err.reshape(-1, cout)
+        rows_bad = (e2.max(1).values > 5e-3 * scale)
+        cols_bad = (e2.max(0).values > 5e-3 * scale)
+        out["bad_rows"] = int(rows_bad.sum()); out["n_rows"] = e2.shape[0]
+        out["bad_cols"] = int(cols_bad.sum())
+        out["first_bad_rows"] = torch.nonzero(rows_bad).flatten()[:16].tolist()
+        out["first_bad_cols"] = torch.nonzero(cols_bad).flatten()[:16].tolist()
+        out["bad_row_mod128_hist"] = torch.bincount(torch.nonzero(rows_bad).flatten() % 128, minlength=128).tolist()
+        r0 = out["first_bad_rows"][0] if out["first_bad_rows"] else 0
+        out["sample_got"] = got.reshape(-1, cout_pitch)[r0, :8].tolist()
+        out["sample_ref"] = ref.reshape(-1, cout)[r0, :8].tolist()
+    out["fault"] = list(L.last_fault())
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", type=int, default=None)
+    ap.add_argument("--only", type=str, default=None, help="substring filter")
+    ap.add_argument("--out", type=str, default=os.path.join(ROOT, "gpurun_out", "bringup_conv.jsonl"))
+    a = ap.parse_args()
+    if a.case is not None:
+        print("RESULT " + json.dumps(run_case(a.case)))
+        return
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    n_ok = n_bad = 0
+    with open(a.out, "w") as fo:
+        for i, (name, _) in enumerate(CASES):
+            if a.only and a.only not in name:
+                continue
+            try:
+                pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", str(i)], capture_output=True,
+                                    text=True, timeout=120)
+                line = [l for l in pr.stdout.splitlines() if l.startswith("RESULT ")]
+                if line:
+                    r = json.loads(line[-1][7:])
+                else:
+                    r = {"case": name, "idx": i, "crash": True, "rc": pr.returncode, "stderr": pr.stderr[-1500:]}
+            except subprocess.TimeoutExpired:
+                r = {"case": name, "idx": i, "timeout": True}
+            ok = (not r.get("crash")) and (not r.get("timeout")) and r.get("rel", 1) <= 5e-3 and r.get("pad_untouched", True)
+            n_ok += ok
+            n_bad += (not ok)
+            r["ok"] = bool(ok)
+            fo.write(json.dumps(r) + "\n")
+            fo.flush()
+            print(("PASS " if ok else "FAIL ") + json.dumps(r)[:600], flush=True)
+    print(f"bringup_conv: {n_ok} passed, {n_bad} failed")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,244 @@
+"""GPU parity tests of the HBM-bound kernels (K2-K7) against the CPU oracle / torch fp32 references."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def test_frames_to_f16c4(lib):
+    from vehicle_counting_b200 import ops
+    rng = np.random.default_rng(0)
+    for shape in [(2, 64, 48), (1, 7, 9), (3, 640, 640)]:
+        fr = torch.from_numpy(rng.integers(0, 256, shape + (3,), dtype=np.uint8))
+        out = torch.full(shape + (4,), 5.0, dtype=torch.float16, device=DEV)
+        ops.frames_to_f16c4(fr.to(DEV), out)
+        ref = (fr.float() / 255.0).half()
+        got = out.cpu()
+        assert torch.equal(got[..., :3], ref)          # bit-exact: same fp32 divide, same rounding
+        assert (got[..., 3] == 0).all()
+
+
+def test_upsample2x_into_slice(lib):
+    from vehicle_counting_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    n, h, w, c = 2, 5, 7, 16
+    src = torch.randn(n, h, w, 24, generator=g).half()
+    dst = torch.full((n, 2 * h, 2 * w, 40), 9.0, dtype=torch.float16)
+    sd, dd = src.to(DEV), dst.to(DEV)
+    ops.upsample2x(sd[..., 8:], 24, dd[..., 16:], 40, n, h, w, c)
+    ref = F.interpolate(src[..., 8:24].permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest").permute(0, 2, 3, 1).half()
+    got = dd.cpu()
+    assert torch.equal(got[..., 16:32], ref)
+    assert (got[..., :16] == 9.0).all() and (got[..., 32:] == 9.0).all()
+
+
+@pytest.mark.parametrize("h,w", [(20, 20), (12, 23), (40, 40)])
+def test_sppf_pool(lib, h, w):
+    from vehicle_counting_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    n, c = 3, 32
+    buf = torch.zeros(n, h, w, 4 * c, dtype=torch.float16)
+    buf[..., :c] = torch.randn(n, h, w, c, generator=g).half()
+    bd = buf.to(DEV)
+    ops.sppf_pool(bd, 4 * c, n, h, w, c)
+    x = buf[..., :c].permute(0, 3, 1, 2).float()
+    y1 = F.max_pool2d(x, 5, 1, 2); y2 = F.max_pool2d(y1, 5, 1, 2); y3 = F.max_pool2d(y2, 5, 1, 2)
+    ref = torch.cat([x, y1, y2, y3], 1).permute(0, 2, 3, 1).half()
+    assert torch.equal(bd.cpu(), ref)
+
+
+def test_maxpool_reid_stem(lib):
+    from vehicle_counting_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    n, h, w, c = 4, 50, 50, 64
+    x = torch.randn(n, h, w, c, generator=g).half()
+    out = torch.empty(n, 25, 25, c, dtype=torch.float16, device=DEV)
+    ops.maxpool(x.to(DEV), c, out, c, n, h, w, c, 3, 2, 1)
+    ref = F.max_pool2d(x.permute(0, 3, 1, 2).float(), 3, 2, 1).permute(0, 2, 3, 1).half()
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_avgpool_l2norm(lib):
+    from vehicle_counting_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    n, hw, c = 9, 16, 512
+    x = torch.randn(n, hw, c, generator=g).abs().half()
+    out = torch.empty(n, c, dtype=torch.float32, device=DEV)
+    ops.avgpool_l2norm(x.to(DEV), c, n, hw, c, out)
+    m = x.float().mean(1)
+    ref = m / m.norm(p=2, dim=1, keepdim=True)
+    assert (out.cpu() - ref).abs().max().item() < 2e-6
+
+
+def test_bn_train_stats_and_apply(lib):
+    from vehicle_counting_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(4)
+    c, hw = 64, 25
+    crops = [3, 1, 5]
+    rows = sum(crops) * hw
+    x = torch.randn(rows, c, generator=g) * 2 + 0.5
+    gamma = torch.rand(c, generator=g) + 0.5
+    beta = torch.randn(c, generator=g)
+    seg_start = torch.tensor(np.cumsum([0] + [k * hw for k in crops]), dtype=torch.int32)
+    row_seg = torch.repeat_interleave(torch.arange(3, dtype=torch.int32), torch.tensor([k * hw for k in crops]))
+    res = torch.randn(rows, c, generator=g).half()
+    xd = x.to(DEV)
+    scale = torch.empty(3, c, device=DEV); shift = torch.empty(3, c, device=DEV)
+    ops.bn_train_stats(xd, c, seg_start.to(DEV), 3, gamma.to(DEV), beta.to(DEV), 1e-5, scale, shift)
+    y = torch.empty(rows, c, dtype=torch.float16, device=DEV)
+    ops.bn_apply(xd, c, rows, row_seg.to(DEV), scale, shift, res.to(DEV), c, L.ACT_RELU, y, c)
+    refs = []
+    for s in range(3):
+        xs = x[seg_start[s]:seg_start[s + 1]]
+        # [rows, c] -> BatchNorm over rows == BatchNorm2d over (N,H,W) in train mode
+        refs.append(F.batch_norm(xs.t().unsqueeze(0), None, None, gamma, beta, True, 0.0, 1e-5).squeeze(0).t())
+    ref = F.relu(torch.cat(refs, 0) + res.float())
+    assert (y.float().cpu() - ref).abs().max().item() < 4e-3 * ref.abs().max().item()
+
+
+def _decode_inputs(n, levels, nc, seed, dtype):
+    g = torch.Generator().manual_seed(seed)
+    no = nc + 5
+    logits = []
+    for (ny, nx) in levels:
+        t = torch.randn(n, ny, nx, 256 if 3 * no <= 256 else 3 * no, generator=g) * 2.0
+        t[..., 4::no][..., :3] -= 1.0
+        logits.append(t.to(dtype))
+    return logits
+
+
+def _oracle_pred(logits, levels, nc):
+    """[n, P, no] decoded predictions exactly like oracle.yolov5.Detect.forward (fp32 CPU)."""
+    from oracle import yolov5 as Y
+    no = nc + 5
+    z = []
+    for i, (ny, nx) in enumerate(levels):
+        x = logits[i].float()[..., :3 * no]
+        n = x.shape[0]
+        x = x.view(n, ny, nx, 3, no).permute(0, 3, 1, 2, 4)          # [n, a, y, x, no]
+        yv, xv = torch.meshgrid(torch.arange(ny), torch.arange(nx), indexing="ij")
+        grid = torch.stack((xv, yv), 2).view(1, 1, ny, nx, 2).float()
+        anchor = torch.tensor(Y.ANCHORS_PX[i], dtype=torch.float32).view(1, 3, 1, 1, 2)
+        y = x.sigmoid()
+        xy = (y[..., 0:2] * 2.0 - 0.5 + grid) * Y.STRIDES[i]
+        wh = (y[..., 2:4] * 2.0) ** 2 * anchor
+        z.append(torch.cat((xy, wh, y[..., 4:]), -1).reshape(n, -1, no))
+    return torch.cat(z, 1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_detect_decode_and_nms_match_oracle(lib, dtype):
+    from oracle import yolov5 as Y
+    from vehicle_counting_b200 import ops, _lib as L
+    n, nc = 3, 80
+    levels = [(16, 20), (8, 10), (4, 5)]
+    logits = _decode_inputs(n, levels, nc, 7, dtype)
+    pred = _oracle_pred(logits, levels, nc)
+    P = pred.shape[1]
+    dd = L.DetectDesc()
+    dd.n, dd.nc, dd.num_levels = n, nc, 3
+    dd.logits_dtype = L.F32 if dtype == torch.float32 else L.F16
+    dd.conf_thres, dd.max_candidates = 0.25, P
+    dl = [t.to(DEV) for t in logits]
+    for i, (ny, nx) in enumerate(levels):
+        lv = dd.level[i]
+        lv.logits, lv.pitch, lv.ny, lv.nx, lv.stride = dl[i].data_ptr(), dl[i].shape[-1], ny, nx, float(Y.STRIDES[i])
+        for a in range(3):
+            lv.anchor_w[a] = float(Y.ANCHORS_PX[i][2 * a]); lv.anchor_h[a] = float(Y.ANCHORS_PX[i][2 * a + 1])
+    cb = torch.zeros(n, P, 4, device=DEV); cs = torch.zeros(n, P, device=DEV)
+    cc = torch.zeros(n, P, dtype=torch.int32, device=DEV); ci = torch.zeros(n, P, dtype=torch.int32, device=DEV)
+    cnt = torch.zeros(n, dtype=torch.int32, device=DEV)
+    ops.detect_decode(dd, cb, cs, cc, ci, cnt)
+    nd = L.NmsDesc()
+    nd.n, nd.max_candidates, nd.max_det, nd.iou_thres, nd.max_wh, nd.max_nms = n, P, 300, 0.45, 4096.0, 30000
+    ws = torch.zeros(ops.nms_workspace_bytes(n, P) // 8, dtype=torch.int64, device=DEV)
+    det = torch.zeros(n, 300, 6, device=DEV); dc = torch.zeros(n, dtype=torch.int32, device=DEV)
+    ops.nms(nd, cb, cs, cc, ci, cnt, ws, det, dc)
+    torch.cuda.synchronize()
+    ref = Y.non_max_suppression(pred, 0.25, 0.45, None, 300, 4096)
+    cnt_h, dc_h, det_h = cnt.cpu(), dc.cpu(), det.cpu()
+    for b in range(n):
+        # candidate set: same prediction indices as the oracle's filter (threshold band excluded)
+        x = pred[b]
+        conf = (x[:, 5:] * x[:, 4:5]).max(1).values
+        keep = (x[:, 4] > 0.25) & (conf > 0.25)
+        band = ((x[:, 4] - 0.25).abs() < 1e-4) | ((conf - 0.25).abs() < 1e-4)
+        got_idx = set(ci[b, :cnt_h[b]].cpu().tolist())
+        want = set(torch.nonzero(keep & ~band).flatten().tolist())
+        maybe = set(torch.nonzero(band).flatten().tolist())
+        assert want <= got_idx <= (want | maybe)
+        r = ref[b]
+        assert dc_h[b].item() == r.shape[0], (b, dc_h[b].item(), r.shape[0])
+        got = det_h[b, :r.shape[0]]
+        assert torch.equal(got[:, 5], r[:, 5])
+        assert (got[:, :4] - r[:, :4]).abs().max().item() < 1e-2
+        assert (got[:, 4] - r[:, 4]).abs().max().item() < 1e-5
+        assert (got[1:, 4] <= got[:-1, 4]).all()
+
+
+def test_nms_bit_exact_on_given_candidates(lib):
+    """Integer/index work is bit-exact: same candidates in -> same kept indices, order and count out."""
+    from oracle import yolov5 as Y
+    from vehicle_counting_b200 import ops, _lib as L
+    rng = np.random.default_rng(5)
+    n = 4
+    counts = [0, 1, 700, 9000]            # empty, single, typical, > smem sort capacity (global path)
+    P = 9000
+    cb = np.zeros((n, P, 4), np.float32); cs = np.zeros((n, P), np.float32)
+    cc = np.zeros((n, P), np.int32); ci = np.zeros((n, P), np.int32)
+    for b, c in enumerate(counts):
+        ctr = rng.uniform(0, 640, (c, 2)).astype(np.float32)
+        wh = rng.uniform(8, 120, (c, 2)).astype(np.float32)
+        cb[b, :c, :2] = ctr - wh / 2; cb[b, :c, 2:] = ctr + wh / 2
+        s = rng.uniform(0.25, 1.0, c).astype(np.float32)
+        s[: c // 3] = np.round(s[: c // 3], 2)          # force score ties
+        cs[b, :c] = s
+        cc[b, :c] = rng.integers(0, 4, c)
+        ci[b, :c] = rng.permutation(c * 3)[:c]          # unique, unordered prediction indices
+    nd = L.NmsDesc()
+    nd.n, nd.max_candidates, nd.max_det, nd.iou_thres, nd.max_wh, nd.max_nms = n, P, 300, 0.45, 4096.0, 30000
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    ws = torch.zeros(ops.nms_workspace_bytes(n, P) // 8, dtype=torch.int64, device=DEV)
+    det = torch.zeros(n, 300, 6, device=DEV); dc = torch.zeros(n, dtype=torch.int32, device=DEV)
+    ops.nms(nd, t(cb), t(cs), t(cc), t(ci), t(np.asarray(counts, np.int32)), ws, det, dc)
+    torch.cuda.synchronize()
+    det_h, dc_h = det.cpu().numpy(), dc.cpu().numpy()
+    for b, c in enumerate(counts):
+        order = np.lexsort((ci[b, :c], -cs[b, :c]))      # score desc, prediction index asc
+        boxes = cb[b, :c][order] + (cc[b, :c][order].astype(np.float32) * np.float32(4096.0))[:, None]
+        keep = Y.greedy_nms(boxes, np.arange(c, 0, -1, dtype=np.float32), 0.45)[:300]
+        sel = order[keep]
+        assert dc_h[b] == len(sel)
+        np.testing.assert_array_equal(det_h[b, :len(sel), :4], cb[b, sel])
+        np.testing.assert_array_equal(det_h[b, :len(sel), 4], cs[b, sel])
+        np.testing.assert_array_equal(det_h[b, :len(sel), 5], cc[b, sel].astype(np.float32))
+
+
+def test_roi_resize_norm_matches_oracle(lib):
+    from oracle import reid as R
+    from vehicle_counting_b200 import ops, _lib as L
+    rng = np.random.default_rng(11)
+    fh, fw = 360, 480
+    frames = rng.integers(0, 256, (2, fh, fw, 3), dtype=np.uint8)
+    boxes = np.array([[10.2, 20.7, 90.9, 200.1], [-5.0, -3.0, 40.0, 50.0], [400.5, 300.2, 600.0, 400.0],
+                      [100.0, 100.0, 150.0, 150.0], [30.3, 40.4, 33.9, 45.1], [0.0, 0.0, 479.9, 359.9]], np.float64)
+    frame_of = np.array([0, 1, 0, 1, 0, 1], np.int32)
+    rois = torch.zeros(len(boxes), 5, dtype=torch.int32, device=DEV)
+    ops.boxes_to_rois(torch.from_numpy(boxes).to(DEV), torch.from_numpy(frame_of).to(DEV), len(boxes), fw, fh, rois)
+    want = np.array([(f,) + R.crop_box(b, fw, fh) for f, b in zip(frame_of, boxes)], np.int32)
+    np.testing.assert_array_equal(rois.cpu().numpy(), want)          # integer crop rule: bit-exact
+    rd = L.RoiDesc()
+    rd.num_rois, rd.out_size = len(boxes), 50
+    for c in range(3):
+        rd.mean[c] = R.NORM_MEAN[c]; rd.inv_std[c] = 1.0 / R.NORM_STD[c]
+    out = torch.zeros(len(boxes), 50, 50, 4, dtype=torch.float16, device=DEV)
+    ops.roi_resize_norm(rd, torch.from_numpy(frames).to(DEV), fh, fw, rois, out)
+    crops = [frames[f][y1:y2, x1:x2] for f, x1, y1, x2, y2 in want]
+    ref = R.preprocess(crops).permute(0, 2, 3, 1)                   # NHWC fp32
+    got = out.float().cpu()
+    assert (got[..., 3] == 0).all()
+    assert (got[..., :3] - ref).abs().max().item() < 2.5e-3        # fp16 storage of values up to ~2.7

@@ -1,0 +1,214 @@
+// extern "C" surface of libvcb200.so (declared in include/vcb200.h) + library state + CUDA-graph capture.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <vector>
+
+#include "vcb_internal.h"
+
+namespace vcb {
+
+// other translation units
+int frames_to_f16c4(const uint8_t*, void*, int, int, int, cudaStream_t);
+int upsample2x(const void*, int, void*, int, int, int, int, int, cudaStream_t);
+int sppf_pool(void*, int, int, int, int, int, cudaStream_t);
+int maxpool(const void*, int, void*, int, int, int, int, int, int, int, int, cudaStream_t);
+int avgpool_l2norm(const void*, int, int, int, int, float*, cudaStream_t);
+int bn_train_stats(const float*, int, const int*, int, const float*, const float*, float, float*, float*, cudaStream_t);
+int bn_apply(const float*, int, int, const int*, const float*, const float*, const void*, int, int, void*, int, cudaStream_t);
+int detect_decode(const VcbDetectDesc&, float*, float*, int*, int*, int*, cudaStream_t);
+int nms(const VcbNmsDesc&, const float*, const float*, const int*, const int*, const int*, unsigned long long*, float*, int*,
+        cudaStream_t);
+long long nms_workspace_bytes(int n, int max_candidates);
+int roi_resize_norm(const VcbRoiDesc&, const uint8_t*, int, int, const int*, void*, cudaStream_t);
+int boxes_to_rois(const double*, const int*, int, int, int, int*, cudaStream_t);
+
+static thread_local char g_err[512] = "";
+
+State& state() {
+  static State s;
+  return s;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return VCB_OK;
+  return set_error(VCB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int require_init() {
+  if (!state().initialised) return set_error(VCB_ERR_INVALID, "vcb_init() has not been called");
+  return VCB_OK;
+}
+
+}  // namespace vcb
+
+using namespace vcb;
+
+struct VcbGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int num_kernels = 0;
+};
+
+extern "C" {
+
+int vcb_version(void) { return 100; }
+
+const char* vcb_last_error_string(void) { return g_err; }
+
+int vcb_init(int device) {
+  State& s = state();
+  if (s.initialised && s.device == device) return VCB_OK;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return check_cuda(e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return check_cuda(e, "cudaGetDeviceProperties");
+  if (prop.major != 10) return set_error(VCB_ERR_ARCH, "device %d is sm_%d%d; libvcb200 runs on sm_100 only (no fallback path)", device, prop.major, prop.minor);
+  s.num_sms = prop.multiProcessorCount;
+  cudaDriverGetVersion(&s.driver_version);
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  s.encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeIm2col entry point not found");
+  s.encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  if (s.fault_host == nullptr) {
+    e = cudaHostAlloc(reinterpret_cast<void**>(&s.fault_host), sizeof(KernelFault), cudaHostAllocMapped);
+    if (e != cudaSuccess) return check_cuda(e, "cudaHostAlloc(fault record)");
+    memset(s.fault_host, 0, sizeof(KernelFault));
+    e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&s.fault_dev), s.fault_host, 0);
+    if (e != cudaSuccess) return check_cuda(e, "cudaHostGetDevicePointer");
+  }
+  s.device = device;
+  s.initialised = true;
+  return VCB_OK;
+}
+
+int vcb_last_fault(int32_t out4[4]) {
+  State& s = state();
+  if (!out4) return set_error(VCB_ERR_INVALID, "null output");
+  if (!s.fault_host) { out4[0] = out4[1] = out4[2] = out4[3] = 0; return VCB_OK; }
+  out4[0] = s.fault_host->code; out4[1] = s.fault_host->block; out4[2] = s.fault_host->info0; out4[3] = s.fault_host->info1;
+  return VCB_OK;
+}
+
+#define VCB_GUARD(d) do { if ((d) == nullptr) return set_error(VCB_ERR_INVALID, "null descriptor"); const int rc_ = require_init(); if (rc_ != VCB_OK) return rc_; } while (0)
+
+int vcb_conv_packed_sizes(const VcbConvDesc* d, int64_t* weight_halfs, int64_t* bias_floats) {
+  if (!d) return set_error(VCB_ERR_INVALID, "null descriptor");
+  return conv_packed_sizes(*d, weight_halfs, bias_floats);
+}
+int vcb_conv_out_hw(const VcbConvDesc* d, int32_t* ho, int32_t* wo) {
+  if (!d) return set_error(VCB_ERR_INVALID, "null descriptor");
+  return conv_out_hw(*d, ho, wo);
+}
+int vcb_conv_pack_weights(const VcbConvDesc* d, const float* w, const float* bias, void* wp, float* bp, vcb_stream_t st) {
+  VCB_GUARD(d);
+  if (!w || !wp || !bp) return set_error(VCB_ERR_INVALID, "conv_pack_weights: null pointer");
+  return conv_pack_weights(*d, w, bias, wp, bp, (cudaStream_t)st);
+}
+int vcb_conv2d_fwd(const VcbConvDesc* d, const void* x, const void* wp, const float* bp, const void* res, void* y, vcb_stream_t st) {
+  VCB_GUARD(d);
+  return conv2d_fwd(*d, x, wp, bp, res, y, (cudaStream_t)st);
+}
+int vcb_frames_to_f16c4(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return frames_to_f16c4(frames, out, n, h, w, (cudaStream_t)st);
+}
+int vcb_upsample2x(const void* src, int32_t sp, void* dst, int32_t dp, int32_t n, int32_t h, int32_t w, int32_t c, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return upsample2x(src, sp, dst, dp, n, h, w, c, (cudaStream_t)st);
+}
+int vcb_sppf_pool(void* buf, int32_t pitch, int32_t n, int32_t h, int32_t w, int32_t c, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return sppf_pool(buf, pitch, n, h, w, c, (cudaStream_t)st);
+}
+int vcb_maxpool(const void* src, int32_t sp, void* dst, int32_t dp, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, int32_t s,
+                int32_t p, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return maxpool(src, sp, dst, dp, n, h, w, c, k, s, p, (cudaStream_t)st);
+}
+int vcb_detect_decode(const VcbDetectDesc* d, float* cb, float* cs, int32_t* cc, int32_t* ci, int32_t* cnt, vcb_stream_t st) {
+  VCB_GUARD(d);
+  return detect_decode(*d, cb, cs, cc, ci, cnt, (cudaStream_t)st);
+}
+int64_t vcb_nms_workspace_bytes(int32_t n, int32_t max_candidates) { return nms_workspace_bytes(n, max_candidates); }
+int vcb_nms(const VcbNmsDesc* d, const float* cb, const float* cs, const int32_t* cc, const int32_t* ci, const int32_t* cnt,
+            uint64_t* ws, float* det, int32_t* det_count, vcb_stream_t st) {
+  VCB_GUARD(d);
+  return nms(*d, cb, cs, cc, ci, cnt, reinterpret_cast<unsigned long long*>(ws), det, det_count, (cudaStream_t)st);
+}
+int vcb_roi_resize_norm(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, int32_t fw, const int32_t* rois, void* out,
+                        vcb_stream_t st) {
+  VCB_GUARD(d);
+  return roi_resize_norm(*d, frames, fh, fw, rois, out, (cudaStream_t)st);
+}
+int vcb_boxes_to_rois(const double* boxes, const int32_t* frame_of, int32_t num, int32_t fw, int32_t fh, int32_t* rois, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return boxes_to_rois(boxes, frame_of, num, fw, fh, rois, (cudaStream_t)st);
+}
+int vcb_avgpool_l2norm(const void* x, int32_t pitch, int32_t n, int32_t hw, int32_t c, float* out, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return avgpool_l2norm(x, pitch, n, hw, c, out, (cudaStream_t)st);
+}
+int vcb_bn_train_stats(const float* x, int32_t c, const int32_t* seg, int32_t num_seg, const float* gamma, const float* beta, float eps,
+                       float* scale, float* shift, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return bn_train_stats(x, c, seg, num_seg, gamma, beta, eps, scale, shift, (cudaStream_t)st);
+}
+int vcb_bn_apply(const float* x, int32_t c, int32_t rows, const int32_t* row_seg, const float* scale, const float* shift,
+                 const void* residual, int32_t res_pitch, int32_t act, void* y, int32_t y_pitch, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return bn_apply(x, c, rows, row_seg, scale, shift, residual, res_pitch, act, y, y_pitch, (cudaStream_t)st);
+}
+
+// ---- CUDA graph capture ------------------------------------------------------------------------
+int vcb_graph_begin(vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  if (st == nullptr) return set_error(VCB_ERR_INVALID, "graph capture needs a non-default stream");
+  return check_cuda(cudaStreamBeginCapture((cudaStream_t)st, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+}
+int vcb_graph_end(vcb_stream_t st, VcbGraph** out) {
+  if (!out) return set_error(VCB_ERR_INVALID, "null output");
+  VcbGraph* g = new VcbGraph();
+  cudaError_t e = cudaStreamEndCapture((cudaStream_t)st, &g->graph);
+  if (e != cudaSuccess || g->graph == nullptr) { delete g; return check_cuda(e != cudaSuccess ? e : cudaErrorUnknown, "cudaStreamEndCapture"); }
+  size_t n = 0;
+  cudaGraphGetNodes(g->graph, nullptr, &n);
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (n) cudaGraphGetNodes(g->graph, nodes.data(), &n);
+  for (size_t i = 0; i < n; ++i) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++g->num_kernels;
+  }
+  e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess) { cudaGraphDestroy(g->graph); delete g; return check_cuda(e, "cudaGraphInstantiate"); }
+  *out = g;
+  return VCB_OK;
+}
+int vcb_graph_launch(VcbGraph* g, vcb_stream_t st) {
+  if (!g || !g->exec) return set_error(VCB_ERR_INVALID, "null graph");
+  return check_cuda(cudaGraphLaunch(g->exec, (cudaStream_t)st), "cudaGraphLaunch");
+}
+int vcb_graph_num_kernels(const VcbGraph* g) { return g ? g->num_kernels : 0; }
+int vcb_graph_destroy(VcbGraph* g) {
+  if (!g) return VCB_OK;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+  return VCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,538 @@
+// K1 -- implicit-GEMM convolution on the sm_100a tensor cores (tcgen05.mma, fp16 in / fp32 TMEM
+// accumulate) with bias + SiLU/ReLU + residual fused into the epilogue.
+//
+// Replaces the cuDNN convolutions the reference reaches through torch.nn.Conv2d:
+//   YOLOv5 Conv = Conv2d + BatchNorm2d(folded) + SiLU   (/root/reference/networks/yolo.py:70 ->
+//                 [upstream models/common.py Conv])
+//   ReID  conv/BN/ReLU/residual blocks                  (/root/reference/networks/deepsort/deep/model.py:5-37)
+//
+// GEMM view: D[M = n*ho*wo, N = cout] = A[M, K = kh*kw*cin] * B[N, K]^T.  A is never materialised:
+// one K-step is one filter tap (r, s) x 64 input channels, i.e. a 128-pixel x 128-byte tile that is
+// fetched straight from the NHWC activation tensor.  Three A producers share the rest of the kernel:
+//   A_TMA    one im2col-mode TMA per K-step (cp.async.bulk.tensor.4d...im2col), zero fill by the TMA unit
+//   A_GATHER 128 producer threads issue 16-byte cp.async with zero-fill predicates (any geometry with
+//            cin % 8 == 0; also the bring-up / cross-check path for A_TMA)
+//   A_C4     same, 8-byte granules over a 4-channel (RGBx) input: the 6x6/s2 YOLO stem and the 3x3 ReID
+//            stem, where one K-step is 16 taps x 4 channels
+// B (weights, packed [cout_pad][K_pad] fp16, K-major) always arrives by tiled TMA.  Both operands land
+// in the 128-byte-swizzled K-major layout the UMMA shared-memory descriptor expects.
+//
+// CTA = warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer, warp 5 MMA issuer
+// (+ TMEM allocator), warps 6-9 gather producers (A_GATHER / A_C4 only).  Persistent: each CTA walks
+// tiles blockIdx.x, +gridDim.x, ...; the fp32 accumulator is double-buffered in TMEM so the epilogue of
+// tile i overlaps the main loop of tile i+1.
+#include "vcb_internal.h"
+#include "vcb_ptx.cuh"
+
+namespace vcb {
+
+enum { A_TMA = 0, A_GATHER = 1, A_C4 = 2 };
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // fp16 elements = 128 bytes = one swizzle row
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kMaxStages = 8;
+constexpr int kGatherLag = 2;                     // cp.async groups in flight per gather thread
+constexpr int kNumEpilogueThreads = 128;
+constexpr int kGatherThreads = 128;
+
+struct ConvParams {
+  // geometry
+  int N, H, W, Cin, cin_pitch;
+  int P, Q, PQ, M;
+  int kh, kw, stride, pad;
+  int Cout;            // logical output channels
+  int cout_store;      // channels actually written (Cout rounded up to 8, <= out_pitch)
+  int out_pitch;
+  int chunks_per_tap;  // ceil(Cin / 64)           (A_TMA, A_GATHER)
+  int num_k_iters;
+  int block_n, n_tiles, m_tiles, num_tiles;
+  int num_stages, acc_stages, tmem_cols;
+  int act, res_mode, res_pitch, out_fp32;
+  const __half* x;
+  const float* bias;
+  const __half* residual;
+  void* out;
+  KernelFault* fault;
+};
+
+struct RowInfo {     // one output pixel of the current M tile (gather modes)
+  int img_base;      // n * H * W
+  short h0, w0;      // top-left input coordinate of the receptive field (may be negative)
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == VCB_ACT_SILU) return v / (1.0f + __expf(-v));
+  if (act == VCB_ACT_RELU) return fmaxf(v, 0.0f);
+  return v;
+}
+
+template <int A_MODE>
+__global__ void __launch_bounds__(A_MODE == A_TMA ? 192 : 320, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
+  const uint32_t bars = smem_base + (uint32_t)p.num_stages * stage_bytes;   // 8-byte aligned
+  auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(kMaxStages + s); };
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
+  const uint32_t row_table = tmem_slot + 16u;   // 128 x RowInfo (8 B)
+  // generic pointers to the same locations (for plain loads/stores)
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (size_t)p.num_stages * stage_bytes + 8 * (2 * kMaxStages + 4));
+  RowInfo* rows = reinterpret_cast<RowInfo*>(smem_gen + (size_t)p.num_stages * stage_bytes + 8 * (2 * kMaxStages + 4) + 16);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    const uint32_t full_count = (A_MODE == A_TMA) ? 1u : (1u + kGatherThreads);
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(full_bar(s), full_count);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), kNumEpilogueThreads);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) {
+    if (A_MODE == A_TMA) tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 4) {
+    // ======================= TMA producer (one thread) =======================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        int cw = 0, ch = 0, cn = 0;
+        if (A_MODE == A_TMA) {
+          const int m0 = m_tile * kBlockM;
+          cn = m0 / p.PQ;
+          const int rem = m0 - cn * p.PQ;
+          const int p0 = rem / p.Q, q0 = rem - p0 * p.Q;
+          cw = q0 * p.stride - p.pad;
+          ch = p0 * p.stride - p.pad;
+        }
+        int r = 0, s = 0, c = 0;
+        for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
+          const int st = it % p.num_stages;
+          const uint32_t ph = (it / p.num_stages) & 1u;
+          mbar_wait(empty_bar(st), ph ^ 1u, p.fault, FAULT_EMPTY_WAIT, st);
+          const uint32_t a_dst = smem_base + (uint32_t)st * stage_bytes;
+          const uint32_t b_dst = a_dst + kATileBytes;
+          if (A_MODE == A_TMA) {
+            mbar_arrive_expect_tx(full_bar(st), kATileBytes + b_tile_bytes);
+            tma_load_im2col_4d(&tmap_a, full_bar(st), a_dst, c * kBlockK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+            if (++c == p.chunks_per_tap) { c = 0; if (++s == p.kw) { s = 0; ++r; } }
+          } else {
+            mbar_arrive_expect_tx(full_bar(st), b_tile_bytes);
+          }
+          tma_load_2d(&tmap_b, full_bar(st), b_dst, kit * kBlockK, n_tile * p.block_n);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ======================= MMA issuer (one thread) =======================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16((uint32_t)p.block_n);
+      uint32_t it = 0, tile_iter = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
+        const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
+        const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
+        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u, p.fault, FAULT_TMEM_EMPTY_WAIT, (int)acc);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.block_n;
+        for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
+          const int st = it % p.num_stages;
+          const uint32_t ph = (it / p.num_stages) & 1u;
+          mbar_wait(full_bar(st), ph, p.fault, FAULT_FULL_WAIT, st);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base + (uint32_t)st * stage_bytes;
+          const uint64_t a_desc = umma_desc_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + kATileBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +32 bytes per UMMA_K step inside the swizzle row: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kit | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(st));
+          if (kit == p.num_k_iters - 1) umma_commit(tmem_full_bar(acc));
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ======================= epilogue: TMEM -> registers -> global =======================
+    uint32_t tile_iter = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
+      const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
+      mbar_wait(tmem_full_bar(acc), acc_ph, p.fault, FAULT_TMEM_FULL_WAIT, (int)acc);
+      tcgen05_fence_after();
+      const int row = m_tile * kBlockM + warp * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + acc * (uint32_t)p.block_n + ((uint32_t)(warp * 32) << 16);
+      const size_t out_row = (size_t)row * (size_t)p.out_pitch;
+      const size_t res_row = (size_t)row * (size_t)p.res_pitch;
+      for (int col0 = 0; col0 < p.block_n; col0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(t_row + (uint32_t)col0, v);
+        tmem_ld_wait();
+        const int n0 = n_tile * p.block_n + col0;
+#pragma unroll
+        for (int half8 = 0; half8 < 2; ++half8) {
+          const int nn = n0 + half8 * 8;
+          if (!row_ok || nn >= p.cout_store) continue;
+          float f[8];
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nn));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nn + 4));
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[half8 * 8 + i]) + bb[i];
+          if (p.res_mode != VCB_RES_NONE) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + res_row + nn));
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+            float rr[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 t = __half22float2(rh[i]);
+              rr[2 * i] = t.x;
+              rr[2 * i + 1] = t.y;
+            }
+            if (p.res_mode == VCB_RES_BEFORE_ACT) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i] + rr[i], p.act);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act) + rr[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
+          }
+          if (p.out_fp32) {
+            float* o = reinterpret_cast<float*>(p.out) + out_row + nn;
+            *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          } else {
+            __half2 h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+            __half* o = reinterpret_cast<__half*>(p.out) + out_row + nn;
+            *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tmem_empty_bar(acc));
+    }
+  } else if (A_MODE != A_TMA) {
+    // ======================= gather producers (warps 6-9) =======================
+    const int gtid = threadIdx.x - 192;
+    uint32_t it = 0;          // K-steps issued by this thread (same sequence in every gather thread)
+    uint32_t arrived = 0;     // K-steps already signalled on their full barrier
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // everyone is done reading the previous table
+      {
+        const int m = m_tile * kBlockM + gtid;
+        RowInfo ri;
+        if (m < p.M) {
+          const int n = m / p.PQ;
+          const int rem = m - n * p.PQ;
+          const int pp = rem / p.Q, qq = rem - pp * p.Q;
+          ri.img_base = n * p.H * p.W;
+          ri.h0 = (short)(pp * p.stride - p.pad);
+          ri.w0 = (short)(qq * p.stride - p.pad);
+        } else {
+          ri.img_base = 0;
+          ri.h0 = (short)-16384;      // every tap fails the bounds test -> zero fill
+          ri.w0 = (short)-16384;
+        }
+        rows[gtid] = ri;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      int r = 0, s = 0, c = 0;
+      for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
+        const int st = it % p.num_stages;
+        const uint32_t ph = (it / p.num_stages) & 1u;
+        mbar_wait(empty_bar(st), ph ^ 1u, p.fault, FAULT_EMPTY_WAIT, 100 + st);
+        const uint32_t a_dst = smem_base + (uint32_t)st * stage_bytes;
+        if (A_MODE == A_GATHER) {
+          const int j = gtid & 7;                         // 16-byte chunk inside the 128-byte row
+          const int cbase = c * kBlockK + j * 8;
+          const bool c_ok = cbase < p.Cin;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (gtid >> 3) + 16 * i;
+            const RowInfo ri = rows[rr];
+            const int h = ri.h0 + r, w = ri.w0 + s;
+            const bool ok = c_ok && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+            const __half* src = ok ? p.x + (size_t)(ri.img_base + h * p.W + w) * (size_t)p.cin_pitch + cbase : p.x;
+            cp_async_16(a_dst + (uint32_t)rr * 128u + (uint32_t)((j ^ (rr & 7)) << 4), src, ok);
+          }
+          if (++c == p.chunks_per_tap) { c = 0; if (++s == p.kw) { s = 0; ++r; } }
+        } else {   // A_C4: 16 taps x 4 channels per K-step, 8-byte granules
+          const int u = gtid & 15;
+          const int t = kit * 16 + u;
+          const int tr = t / p.kw, ts = t - tr * p.kw;
+          const bool t_ok = t < p.kh * p.kw;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int rr = (gtid >> 4) + 8 * i;
+            const RowInfo ri = rows[rr];
+            const int h = ri.h0 + tr, w = ri.w0 + ts;
+            const bool ok = t_ok && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+            const __half* src = ok ? p.x + (size_t)(ri.img_base + h * p.W + w) * 4 : p.x;
+            cp_async_8(a_dst + (uint32_t)rr * 128u + (uint32_t)(((u >> 1) ^ (rr & 7)) << 4) + (uint32_t)((u & 1) << 3),
+                       src, ok);
+          }
+        }
+        cp_async_commit();
+        if (it + 1 - arrived > (uint32_t)kGatherLag) {     // oldest outstanding group is complete
+          cp_async_wait<kGatherLag>();
+          fence_proxy_async_smem();
+          mbar_arrive(full_bar(arrived % p.num_stages));
+          ++arrived;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (; arrived < it; ++arrived) mbar_arrive(full_bar(arrived % p.num_stages));
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: OIHW fp32 (BN folded) -> [cout_pad][K_pad] fp16, K index = (tap * cin_pad + c) for
+// the 64-channel-chunk modes and (tap * 4 + c) for A_C4
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias, __half* __restrict__ wp,
+                                    float* __restrict__ bp, int cout, int cin, int kh, int kw, int cout_pad, int k_pad,
+                                    int cin_pad, int c4) {
+  const long long total = (long long)cout_pad * k_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i / k_pad), k = (int)(i - (long long)o * k_pad);
+    int tap, c;
+    if (c4) { tap = k >> 2; c = k & 3; } else { tap = k / cin_pad; c = k - tap * cin_pad; }
+    float v = 0.0f;
+    if (o < cout && c < cin && tap < kh * kw) {
+      const int r = tap / kw, s = tap - r * kw;
+      v = w[(((size_t)o * cin + c) * kh + r) * kw + s];
+    }
+    wp[i] = __float2half_rn(v);
+  }
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < cout_pad; o += gridDim.x * blockDim.x)
+    bp[o] = (bias != nullptr && o < cout) ? bias[o] : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct ConvGeom {
+  int a_mode;   // A_TMA / A_GATHER / A_C4
+  int P, Q, M;
+  int cin_pad, k_pad, num_k_iters, chunks_per_tap;
+  int block_n, n_tiles, cout_pad, m_tiles;
+  int stages, acc_stages, tmem_cols;
+  size_t smem_bytes;
+};
+
+static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
+  if (d.n <= 0 || d.h <= 0 || d.w <= 0 || d.cin <= 0 || d.cout <= 0 || d.kh <= 0 || d.kw <= 0 || d.stride <= 0 ||
+      d.pad < 0)
+    return set_error(VCB_ERR_INVALID, "conv: non-positive dimension");
+  g.P = (d.h + 2 * d.pad - d.kh) / d.stride + 1;
+  g.Q = (d.w + 2 * d.pad - d.kw) / d.stride + 1;
+  if (g.P <= 0 || g.Q <= 0) return set_error(VCB_ERR_INVALID, "conv: empty output");
+  const long long M = (long long)d.n * g.P * g.Q;
+  if (M > 0x7fffff00LL || (long long)d.n * d.h * d.w > 0x7fffff00LL) return set_error(VCB_ERR_INVALID, "conv: too many pixels");
+  g.M = (int)M;
+  int mode = d.a_mode;
+  if (mode == VCB_A_AUTO) mode = (d.cin_pitch == 4 && d.cin <= 4) ? VCB_A_C4 : VCB_A_IM2COL_TMA;
+  if (mode == VCB_A_C4) {
+    if (d.cin_pitch != 4 || d.cin > 4) return set_error(VCB_ERR_INVALID, "conv: A_C4 needs cin<=4 and cin_pitch==4");
+    g.a_mode = A_C4;
+    g.cin_pad = 4;
+    g.chunks_per_tap = 0;
+    g.num_k_iters = (d.kh * d.kw + 15) / 16;
+  } else {
+    if (d.cin % 8 != 0 || d.cin_pitch % 8 != 0 || d.cin_pitch < d.cin)
+      return set_error(VCB_ERR_INVALID, "conv: cin and cin_pitch must be multiples of 8 (cin_pitch >= cin)");
+    g.a_mode = (mode == VCB_A_GATHER) ? A_GATHER : A_TMA;
+    g.chunks_per_tap = (d.cin + kBlockK - 1) / kBlockK;
+    g.cin_pad = g.chunks_per_tap * kBlockK;
+    g.num_k_iters = d.kh * d.kw * g.chunks_per_tap;
+    if (g.a_mode == A_TMA && (d.pad > 127 || d.kh > 128 || d.kw > 128 || d.stride > 8))
+      return set_error(VCB_ERR_INVALID, "conv: geometry outside the im2col TMA limits");
+  }
+  if (d.h > 16000 || d.w > 16000) return set_error(VCB_ERR_INVALID, "conv: image too large");
+  g.k_pad = g.num_k_iters * kBlockK;
+  const int cout16 = (d.cout + 15) / 16 * 16;
+  if (d.block_n != 0) {
+    if (d.block_n % 16 != 0 || d.block_n < 16 || d.block_n > 256) return set_error(VCB_ERR_INVALID, "conv: bad block_n");
+    g.block_n = d.block_n;
+    g.n_tiles = (cout16 + g.block_n - 1) / g.block_n;
+  } else {
+    g.n_tiles = (cout16 + 255) / 256;
+    g.block_n = ((cout16 + g.n_tiles - 1) / g.n_tiles + 15) / 16 * 16;
+  }
+  g.cout_pad = g.n_tiles * g.block_n;
+  g.m_tiles = (g.M + kBlockM - 1) / kBlockM;
+  const int cout_store = (d.cout + 7) / 8 * 8;
+  if (d.cout_pitch < cout_store || d.cout_pitch % 8 != 0)
+    return set_error(VCB_ERR_INVALID, "conv: cout_pitch must be a multiple of 8 and >= round_up(cout, 8)");
+  if (d.res_mode != VCB_RES_NONE && (d.res_pitch % 8 != 0 || d.res_pitch < cout_store))
+    return set_error(VCB_ERR_INVALID, "conv: bad residual pitch");
+  g.acc_stages = (2 * g.block_n <= 512) ? 2 : 1;
+  int cols = g.acc_stages * g.block_n, pow2 = 32;
+  while (pow2 < cols) pow2 <<= 1;
+  g.tmem_cols = pow2;
+  const size_t stage_bytes = (size_t)kATileBytes + (size_t)g.block_n * 128;
+  const size_t fixed = 1024 /*align slack*/ + 8 * (2 * kMaxStages + 4) + 16 + kBlockM * sizeof(RowInfo) + 64;
+  int stages = (int)((size_t)(227 * 1024 - fixed) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (d.stages != 0) stages = d.stages < stages ? d.stages : stages;
+  const int min_stages = (g.a_mode == A_TMA) ? 2 : kGatherLag + 2;
+  if (stages < min_stages) return set_error(VCB_ERR_INVALID, "conv: not enough shared memory for the pipeline");
+  g.stages = stages;
+  g.smem_bytes = fixed + (size_t)stages * stage_bytes;
+  return VCB_OK;
+}
+
+int conv_packed_sizes(const VcbConvDesc& d, int64_t* weight_halfs, int64_t* bias_floats) {
+  ConvGeom g;
+  const int rc = conv_geometry(d, g);
+  if (rc != VCB_OK) return rc;
+  if (weight_halfs) *weight_halfs = (int64_t)g.cout_pad * g.k_pad;
+  if (bias_floats) *bias_floats = g.cout_pad;
+  return VCB_OK;
+}
+
+int conv_out_hw(const VcbConvDesc& d, int32_t* ho, int32_t* wo) {
+  ConvGeom g;
+  const int rc = conv_geometry(d, g);
+  if (rc != VCB_OK) return rc;
+  if (ho) *ho = g.P;
+  if (wo) *wo = g.Q;
+  return VCB_OK;
+}
+
+int conv_pack_weights(const VcbConvDesc& d, const float* w, const float* bias, void* wp, float* bp, cudaStream_t st) {
+  ConvGeom g;
+  const int rc = conv_geometry(d, g);
+  if (rc != VCB_OK) return rc;
+  const long long total = (long long)g.cout_pad * g.k_pad;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  pack_weights_kernel<<<blocks, 256, 0, st>>>(w, bias, reinterpret_cast<__half*>(wp), bp, d.cout, d.cin, d.kh, d.kw,
+                                              g.cout_pad, g.k_pad, g.cin_pad, g.a_mode == A_C4 ? 1 : 0);
+  return check_cuda(cudaGetLastError(), "pack_weights launch");
+}
+
+template <int A_MODE>
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, const ConvGeom& g, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<A_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv)");
+    attr_set = true;
+  }
+  const int grid = p.num_tiles < state().num_sms ? p.num_tiles : state().num_sms;
+  conv_umma_kernel<A_MODE><<<grid, A_MODE == A_TMA ? 192 : 320, g.smem_bytes, st>>>(ta, tb, p);
+  return check_cuda(cudaGetLastError(), "conv launch");
+}
+
+int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const float* bias_packed, const void* residual,
+               void* y, cudaStream_t st) {
+  int rc = require_init();
+  if (rc != VCB_OK) return rc;
+  ConvGeom g;
+  rc = conv_geometry(d, g);
+  if (rc != VCB_OK) return rc;
+  if (x == nullptr || w_packed == nullptr || bias_packed == nullptr || y == nullptr ||
+      (d.res_mode != VCB_RES_NONE && residual == nullptr))
+    return set_error(VCB_ERR_INVALID, "conv: null pointer");
+  if (((uintptr_t)x & 15) || ((uintptr_t)w_packed & 15) || ((uintptr_t)y & 15) || ((uintptr_t)residual & 15) ||
+      ((uintptr_t)bias_packed & 15))
+    return set_error(VCB_ERR_INVALID, "conv: pointers must be 16-byte aligned");
+
+  ConvParams p{};
+  p.N = d.n; p.H = d.h; p.W = d.w; p.Cin = d.cin; p.cin_pitch = d.cin_pitch;
+  p.P = g.P; p.Q = g.Q; p.PQ = g.P * g.Q; p.M = g.M;
+  p.kh = d.kh; p.kw = d.kw; p.stride = d.stride; p.pad = d.pad;
+  p.Cout = d.cout; p.cout_store = (d.cout + 7) / 8 * 8; p.out_pitch = d.cout_pitch;
+  p.chunks_per_tap = g.chunks_per_tap; p.num_k_iters = g.num_k_iters;
+  p.block_n = g.block_n; p.n_tiles = g.n_tiles; p.m_tiles = g.m_tiles; p.num_tiles = g.m_tiles * g.n_tiles;
+  p.num_stages = g.stages; p.acc_stages = g.acc_stages; p.tmem_cols = g.tmem_cols;
+  p.act = d.act; p.res_mode = d.res_mode; p.res_pitch = d.res_pitch; p.out_fp32 = d.out_dtype == VCB_F32 ? 1 : 0;
+  p.x = reinterpret_cast<const __half*>(x);
+  p.bias = bias_packed;
+  p.residual = reinterpret_cast<const __half*>(residual);
+  p.out = y;
+  p.fault = state().fault_dev;
+
+  alignas(64) CUtensorMap ta, tb;
+  memset(&ta, 0, sizeof(ta));
+  {   // B: [cout_pad][k_pad] fp16, box = 64 (K) x block_n rows, 128-byte swizzle
+    const cuuint64_t dims[2] = {(cuuint64_t)g.k_pad, (cuuint64_t)g.cout_pad};
+    const cuuint64_t strides[1] = {(cuuint64_t)g.k_pad * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)g.block_n};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = state().encode_tiled(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_packed), dims, strides,
+                                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  }
+  if (g.a_mode == A_TMA) {
+    // A: NHWC activations as a (C, W, H, N) tensor in im2col mode.  Bounding box of base pixels:
+    // lower corner = -pad, upper corner = pad - (k - 1); traversal stride = conv stride; one load =
+    // 128 consecutive output pixels x 64 channels at filter offset (s, r).
+    const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
+    const cuuint64_t strides[3] = {(cuuint64_t)d.cin_pitch * 2, (cuuint64_t)d.w * d.cin_pitch * 2,
+                                   (cuuint64_t)d.h * d.w * d.cin_pitch * 2};
+    const int lower[2] = {-d.pad, -d.pad};
+    const int upper[2] = {d.pad - (d.kw - 1), d.pad - (d.kh - 1)};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+    const CUresult r = state().encode_im2col(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
+                                             upper, (cuuint32_t)kBlockK, (cuuint32_t)kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeIm2col failed: %d", (int)r);
+    // Driver quirk for small tensors in im2col mode (same adjustment CUTLASS applies, see
+    // cute/atom/copy_traits_sm90_im2col.hpp make_im2col_tma_copy_desc): clear bit 21 of the second
+    // descriptor word when the tensor spans < 128 KiB on drivers <= 13.1.
+    if (state().driver_version <= 13010) {
+      const unsigned long long span = (unsigned long long)d.n * d.h * d.w * d.cin_pitch * 2ull;
+      if (span < 131072ull) reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ull << 21);
+    }
+  }
+  switch (g.a_mode) {
+    case A_TMA: return launch_conv<A_TMA>(ta, tb, p, g, st);
+    case A_GATHER: return launch_conv<A_GATHER>(ta, tb, p, g, st);
+    default: return launch_conv<A_C4>(ta, tb, p, g, st);
+  }
+}
+
+}  // namespace vcb

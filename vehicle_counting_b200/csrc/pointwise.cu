@@ -1,0 +1,298 @@
+// K2 / K6 / K7 -- HBM-bound data-movement kernels around the convolutions: frame ingest, nearest
+// upsample into a concat slice, the SPPF max-pool cascade, generic max-pool, the ReID average-pool +
+// L2-norm tail and the train-mode BatchNorm statistics / apply pair.  All are 16-byte vectorised over
+// the NHWC channel dimension; none reuses data enough to want shared-memory staging except SPPF.
+#include "vcb_internal.h"
+
+namespace vcb {
+
+static inline int grid_for(long long work, int block, int max_blocks = 148 * 16) {
+  long long b = (work + block - 1) / block;
+  if (b < 1) b = 1;
+  return (int)(b < max_blocks ? b : max_blocks);
+}
+
+// ---------------------------------------------------------------- frames (uint8 HWC3) -> fp16 NHWC4
+// [upstream AutoShape.forward: x = torch.from_numpy(x).to(device).type_as(p) / 255]
+__global__ void frames_to_f16c4_kernel(const uint8_t* __restrict__ in, uint2* __restrict__ out, long long pixels) {
+  const long long quads = pixels >> 2;   // 4 pixels = 12 input bytes = 3 aligned words
+  const float k = 1.0f / 255.0f;
+  (void)k;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(in) + q * 3;
+    const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+    const uint8_t b[12] = {(uint8_t)w0, (uint8_t)(w0 >> 8), (uint8_t)(w0 >> 16), (uint8_t)(w0 >> 24),
+                           (uint8_t)w1, (uint8_t)(w1 >> 8), (uint8_t)(w1 >> 16), (uint8_t)(w1 >> 24),
+                           (uint8_t)w2, (uint8_t)(w2 >> 8), (uint8_t)(w2 >> 16), (uint8_t)(w2 >> 24)};
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const __half2 lo = __floats2half2_rn((float)b[px * 3] / 255.0f, (float)b[px * 3 + 1] / 255.0f);
+      const __half2 hi = __floats2half2_rn((float)b[px * 3 + 2] / 255.0f, 0.0f);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo);
+      o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      out[q * 4 + px] = o;
+    }
+  }
+  // tail pixels (pixels % 4)
+  const long long tail0 = quads << 2;
+  for (long long px = tail0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; px < pixels; px += (long long)gridDim.x * blockDim.x) {
+    const uint8_t* s = in + px * 3;
+    const __half2 lo = __floats2half2_rn((float)s[0] / 255.0f, (float)s[1] / 255.0f);
+    const __half2 hi = __floats2half2_rn((float)s[2] / 255.0f, 0.0f);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&lo);
+    o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    out[px] = o;
+  }
+}
+
+int frames_to_f16c4(const uint8_t* frames, void* out, int n, int h, int w, cudaStream_t st) {
+  if (!frames || !out || n <= 0 || h <= 0 || w <= 0) return set_error(VCB_ERR_INVALID, "frames_to_f16c4: bad argument");
+  if (((uintptr_t)frames & 3) || ((uintptr_t)out & 7)) return set_error(VCB_ERR_INVALID, "frames_to_f16c4: misaligned pointer");
+  const long long pixels = (long long)n * h * w;
+  frames_to_f16c4_kernel<<<grid_for(pixels / 4 + 1, 256), 256, 0, st>>>(frames, reinterpret_cast<uint2*>(out), pixels);
+  return check_cuda(cudaGetLastError(), "frames_to_f16c4 launch");
+}
+
+// ---------------------------------------------------------------- nearest x2 upsample into a channel slice
+__global__ void upsample2x_kernel(const uint4* __restrict__ src, int src_pitch8, uint4* __restrict__ dst, int dst_pitch8, int n,
+                                  int h, int w, int c8) {
+  const long long total = (long long)n * (2 * h) * (2 * w) * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c8);
+    long long t = i / c8;
+    const int ox = (int)(t % (2 * w));
+    t /= (2 * w);
+    const int oy = (int)(t % (2 * h));
+    const int b = (int)(t / (2 * h));
+    const uint4 v = __ldg(src + ((long long)(b * h + (oy >> 1)) * w + (ox >> 1)) * src_pitch8 + cc);
+    dst[((long long)(b * 2 * h + oy) * (2 * w) + ox) * dst_pitch8 + cc] = v;
+  }
+}
+
+int upsample2x(const void* src, int src_pitch, void* dst, int dst_pitch, int n, int h, int w, int c, cudaStream_t st) {
+  if (!src || !dst || n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c & 7) || (src_pitch & 7) || (dst_pitch & 7) ||
+      ((uintptr_t)src & 15) || ((uintptr_t)dst & 15))
+    return set_error(VCB_ERR_INVALID, "upsample2x: bad argument (channels/pitches must be multiples of 8, pointers 16B aligned)");
+  const long long total = (long long)n * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src), src_pitch / 8,
+                                                           reinterpret_cast<uint4*>(dst), dst_pitch / 8, n, h, w, c / 8);
+  return check_cuda(cudaGetLastError(), "upsample2x launch");
+}
+
+// ---------------------------------------------------------------- SPPF cascade: y1 = mp5(x), y2 = mp5(y1), y3 = mp5(y2)
+__device__ __forceinline__ uint4 hmax8(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __half2* pa = reinterpret_cast<const __half2*>(&a);
+  const __half2* pb = reinterpret_cast<const __half2*>(&b);
+  __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+// one CTA per (frame, 8-channel group): the whole h*w map of that group lives in shared memory
+__global__ void sppf_pool_kernel(uint4* __restrict__ buf, int pitch8, int h, int w, int c8) {
+  extern __shared__ uint4 sm[];
+  uint4* A = sm;
+  uint4* B = sm + h * w;
+  const int b = blockIdx.x / c8, cc = blockIdx.x % c8;
+  uint4* base = buf + (long long)b * h * w * pitch8 + cc;
+  const int hw = h * w;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) A[i] = base[(long long)i * pitch8];
+  __syncthreads();
+  for (int round = 1; round <= 3; ++round) {
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {       // horizontal 5-max A -> B
+      const int y = i / w, x = i - y * w;
+      uint4 m = A[i];
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int xx = x + dx;
+        if (dx != 0 && xx >= 0 && xx < w) m = hmax8(m, A[y * w + xx]);
+      }
+      B[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {       // vertical 5-max B -> A, and out
+      const int y = i / w, x = i - y * w;
+      uint4 m = B[i];
+      for (int dy = -2; dy <= 2; ++dy) {
+        const int yy = y + dy;
+        if (dy != 0 && yy >= 0 && yy < h) m = hmax8(m, B[yy * w + x]);
+      }
+      A[i] = m;
+      base[(long long)i * pitch8 + (long long)round * c8] = m;
+    }
+    __syncthreads();
+  }
+}
+
+int sppf_pool(void* buf, int pitch, int n, int h, int w, int c, cudaStream_t st) {
+  if (!buf || n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c & 7) || (pitch & 7) || pitch < 4 * c || ((uintptr_t)buf & 15))
+    return set_error(VCB_ERR_INVALID, "sppf_pool: bad argument");
+  const size_t smem = (size_t)h * w * 16 * 2;
+  if (smem > 200 * 1024) return set_error(VCB_ERR_INVALID, "sppf_pool: feature map too large for the shared-memory cascade");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    const cudaError_t e = cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(sppf)");
+    configured = 200 * 1024;
+  }
+  sppf_pool_kernel<<<n * (c / 8), 256, smem, st>>>(reinterpret_cast<uint4*>(buf), pitch / 8, h, w, c / 8);
+  return check_cuda(cudaGetLastError(), "sppf_pool launch");
+}
+
+// ---------------------------------------------------------------- generic MaxPool2d(k, s, p), NHWC fp16
+__global__ void maxpool_kernel(const uint4* __restrict__ src, int src_pitch8, uint4* __restrict__ dst, int dst_pitch8, int n, int h,
+                               int w, int c8, int k, int s, int p, int ho, int wo) {
+  const long long total = (long long)n * ho * wo * c8;
+  const __half2 ninf = __float2half2_rn(-65504.0f);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c8);
+    long long t = i / c8;
+    const int ox = (int)(t % wo);
+    t /= wo;
+    const int oy = (int)(t % ho);
+    const int b = (int)(t / ho);
+    uint4 m;
+    __half2* pm = reinterpret_cast<__half2*>(&m);
+    pm[0] = pm[1] = pm[2] = pm[3] = ninf;
+    for (int dy = 0; dy < k; ++dy) {
+      const int y = oy * s - p + dy;
+      if (y < 0 || y >= h) continue;
+      for (int dx = 0; dx < k; ++dx) {
+        const int x = ox * s - p + dx;
+        if (x < 0 || x >= w) continue;
+        m = hmax8(m, __ldg(src + ((long long)(b * h + y) * w + x) * src_pitch8 + cc));
+      }
+    }
+    dst[((long long)(b * ho + oy) * wo + ox) * dst_pitch8 + cc] = m;
+  }
+}
+
+int maxpool(const void* src, int src_pitch, void* dst, int dst_pitch, int n, int h, int w, int c, int k, int s, int p,
+            cudaStream_t st) {
+  if (!src || !dst || n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c & 7) || (src_pitch & 7) || (dst_pitch & 7) || k <= 0 || s <= 0 ||
+      p < 0 || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15))
+    return set_error(VCB_ERR_INVALID, "maxpool: bad argument");
+  const int ho = (h + 2 * p - k) / s + 1, wo = (w + 2 * p - k) / s + 1;
+  if (ho <= 0 || wo <= 0) return set_error(VCB_ERR_INVALID, "maxpool: empty output");
+  const long long total = (long long)n * ho * wo * (c / 8);
+  maxpool_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src), src_pitch / 8,
+                                                        reinterpret_cast<uint4*>(dst), dst_pitch / 8, n, h, w, c / 8, k, s, p, ho, wo);
+  return check_cuda(cudaGetLastError(), "maxpool launch");
+}
+
+// ---------------------------------------------------------------- AvgPool(hw) + L2 normalise (model.py:71, :93-95)
+__global__ void avgpool_l2norm_kernel(const __half* __restrict__ x, int pitch, int hw, int c, float* __restrict__ out) {
+  extern __shared__ float vals[];           // c floats + 32 for the reduction
+  float* red = vals + c;
+  const __half* xb = x + (long long)blockIdx.x * hw * pitch;
+  float ss = 0.0f;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.0f;
+    for (int i = 0; i < hw; ++i) s += __half2float(xb[(long long)i * pitch + ch]);
+    s /= (float)hw;
+    vals[ch] = s;
+    ss += s * s;
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) red[0] = sqrtf(t);
+  }
+  __syncthreads();
+  const float nrm = red[0];
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) out[(long long)blockIdx.x * c + ch] = vals[ch] / nrm;
+}
+
+int avgpool_l2norm(const void* x, int pitch, int n, int hw, int c, float* out, cudaStream_t st) {
+  if (!x || !out || n <= 0 || hw <= 0 || c <= 0 || pitch < c) return set_error(VCB_ERR_INVALID, "avgpool_l2norm: bad argument");
+  avgpool_l2norm_kernel<<<n, 256, (size_t)(c + 32) * sizeof(float), st>>>(reinterpret_cast<const __half*>(x), pitch, hw, c, out);
+  return check_cuda(cudaGetLastError(), "avgpool_l2norm launch");
+}
+
+// ---------------------------------------------------------------- train-mode BatchNorm (reference Extractor never calls .eval())
+// grid = (num_seg, ceil(c/32)); block = 32 channels x 8 row lanes; double accumulation.
+__global__ void bn_train_stats_kernel(const float* __restrict__ x, int c, const int* __restrict__ seg_row_start,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int seg = blockIdx.x;
+  const int ch = blockIdx.y * 32 + threadIdx.x;
+  const int r0 = seg_row_start[seg], r1 = seg_row_start[seg + 1];
+  double a = 0.0, b = 0.0;
+  if (ch < c) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const double v = (double)x[(long long)r * c + ch];
+      a += v;
+      b += v * v;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < c) {
+    for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
+    const double cnt = (double)(r1 - r0);
+    const double mean = cnt > 0 ? a / cnt : 0.0;
+    double var = cnt > 0 ? b / cnt - mean * mean : 0.0;
+    if (var < 0) var = 0;
+    const float sc = gamma[ch] * (float)(1.0 / sqrt(var + (double)eps));
+    scale[(long long)seg * c + ch] = sc;
+    shift[(long long)seg * c + ch] = beta[ch] - (float)mean * sc;
+  }
+}
+
+int bn_train_stats(const float* x, int c, const int* seg_row_start, int num_seg, const float* gamma, const float* beta, float eps,
+                   float* scale, float* shift, cudaStream_t st) {
+  if (!x || !seg_row_start || !gamma || !beta || !scale || !shift || c <= 0 || num_seg <= 0)
+    return set_error(VCB_ERR_INVALID, "bn_train_stats: bad argument");
+  dim3 grid(num_seg, (c + 31) / 32), block(32, 8);
+  bn_train_stats_kernel<<<grid, block, 0, st>>>(x, c, seg_row_start, gamma, beta, eps, scale, shift);
+  return check_cuda(cudaGetLastError(), "bn_train_stats launch");
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ x, int c, long long rows, const int* __restrict__ row_seg,
+                                const float* __restrict__ scale, const float* __restrict__ shift, const __half* __restrict__ residual,
+                                int res_pitch, int act, __half* __restrict__ y, int y_pitch) {
+  const int c4 = c >> 2;
+  const long long total = rows * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4;
+    const int ch = (int)(i - r * c4) * 4;
+    const int seg = row_seg[r];
+    const float4 v = *reinterpret_cast<const float4*>(x + r * c + ch);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + (long long)seg * c + ch);
+    const float4 sh = *reinterpret_cast<const float4*>(shift + (long long)seg * c + ch);
+    float f[4] = {v.x * sc.x + sh.x, v.y * sc.y + sh.y, v.z * sc.z + sh.z, v.w * sc.w + sh.w};
+    if (residual != nullptr) {
+      const __half2* rp = reinterpret_cast<const __half2*>(residual + r * res_pitch + ch);
+      const float2 r0 = __half22float2(rp[0]), r1 = __half22float2(rp[1]);
+      f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+    }
+    if (act == VCB_ACT_RELU) {
+      for (int k = 0; k < 4; ++k) f[k] = fmaxf(f[k], 0.0f);
+    } else if (act == VCB_ACT_SILU) {
+      for (int k = 0; k < 4; ++k) f[k] = f[k] / (1.0f + __expf(-f[k]));
+    }
+    __half2* yp = reinterpret_cast<__half2*>(y + r * y_pitch + ch);
+    yp[0] = __floats2half2_rn(f[0], f[1]);
+    yp[1] = __floats2half2_rn(f[2], f[3]);
+  }
+}
+
+int bn_apply(const float* x, int c, int rows, const int* row_seg, const float* scale, const float* shift, const void* residual,
+             int res_pitch, int act, void* y, int y_pitch, cudaStream_t st) {
+  if (!x || !row_seg || !scale || !shift || !y || c <= 0 || (c & 3) || rows <= 0 || (y_pitch & 3) || (residual && (res_pitch & 3)))
+    return set_error(VCB_ERR_INVALID, "bn_apply: bad argument");
+  const long long total = (long long)rows * (c / 4);
+  bn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, c, rows, row_seg, scale, shift, reinterpret_cast<const __half*>(residual),
+                                                         res_pitch, act, reinterpret_cast<__half*>(y), y_pitch);
+  return check_cuda(cudaGetLastError(), "bn_apply launch");
+}
+
+}  // namespace vcb

@@ -1,0 +1,590 @@
+"""Static execution plans for the two networks on the hot path.
+
+`YoloEngine`  -- YOLOv5 v6.0 DetectionModel forward + Detect decode + NMS + scale_coords for a fixed
+                 (batch, H, W): what `YoloBackbone.detect` needs behind
+                 /root/reference/networks/yolo.py:70 (the AutoShape call).
+`ReidEngine`  -- ROI crop/resize/normalise + the DeepSORT `Net` (reid=True) forward: what
+                 `Extractor.__call__` computes (/root/reference/networks/deepsort/deep/
+                 feature_extractor.py:42-47, model.py:83-95).
+
+Both build a list of C-ABI calls over statically planned NHWC fp16 buffers (concat-free: producers
+write channel slices of the consumer's buffer), then capture the list into one CUDA graph that is
+replayed per batch.  PyTorch only owns the memory and the stream; BN folding / weight packing use
+torch elementwise ops once at load time, never per frame.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+
+# ---------------------------------------------------------------------------------------------
+# YOLOv5 v6.0 topology (models/yolov5*.yaml, upstream) -- the product's own statement of it
+# ---------------------------------------------------------------------------------------------
+ANCHORS_PX = ((10, 13, 16, 30, 33, 23), (30, 61, 62, 45, 59, 119), (116, 90, 156, 198, 373, 326))
+STRIDES = (8, 16, 32)
+MODEL_SCALES = {"yolov5n": (0.33, 0.25), "yolov5s": (0.33, 0.50), "yolov5m": (0.67, 0.75),
+                "yolov5l": (1.00, 1.00), "yolov5x": (1.33, 1.25)}
+# (from, repeats, kind, args): Conv(c, k, s, p) / C3(c, shortcut) / SPPF(c, k) / Up / Cat / Detect
+LAYERS_V6 = [
+    (-1, 1, "Conv", (64, 6, 2, 2)), (-1, 1, "Conv", (128, 3, 2, 1)), (-1, 3, "C3", (128, True)),
+    (-1, 1, "Conv", (256, 3, 2, 1)), (-1, 6, "C3", (256, True)), (-1, 1, "Conv", (512, 3, 2, 1)),
+    (-1, 9, "C3", (512, True)), (-1, 1, "Conv", (1024, 3, 2, 1)), (-1, 3, "C3", (1024, True)),
+    (-1, 1, "SPPF", (1024, 5)), (-1, 1, "Conv", (512, 1, 1, 0)), (-1, 1, "Up", ()), ((-1, 6), 1, "Cat", ()),
+    (-1, 3, "C3", (512, False)), (-1, 1, "Conv", (256, 1, 1, 0)), (-1, 1, "Up", ()), ((-1, 4), 1, "Cat", ()),
+    (-1, 3, "C3", (256, False)), (-1, 1, "Conv", (256, 3, 2, 1)), ((-1, 14), 1, "Cat", ()),
+    (-1, 3, "C3", (512, False)), (-1, 1, "Conv", (512, 3, 2, 1)), ((-1, 10), 1, "Cat", ()),
+    (-1, 3, "C3", (1024, False)), ((17, 20, 23), 1, "Detect", ()),
+]
+YOLO_BN_EPS = 1e-3     # upstream initialize_weights() sets eps=1e-3 on every BatchNorm2d
+
+
+def _ceil8(x: float) -> int:
+    return int(math.ceil(x / 8) * 8)
+
+
+def infer_model_name(sd: Dict[str, torch.Tensor]) -> str:
+    """Recover (depth, width) multiples from a v6.0 state_dict: stem width and C3 repeat count."""
+    c0 = sd["model.0.conv.weight"].shape[0]
+    n2 = len({k.split(".")[3] for k in sd if k.startswith("model.2.m.")})
+    for name, (gd, gw) in MODEL_SCALES.items():
+        if _ceil8(64 * gw) == c0 and max(round(3 * gd), 1) == n2:
+            return name
+    raise ValueError(f"not a YOLOv5 v6.0 n/s/m/l/x state_dict (stem width {c0}, C3 repeats {n2})")
+
+
+def fold_conv_bn(sd, prefix: str, eps: float, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Conv2d(bias=False)+BatchNorm2d -> (w', b') fp32 on `device` [upstream fuse_conv_and_bn].
+    Already-fused checkpoints (conv.bias present, no bn.*) pass through."""
+    w = sd[prefix + ".conv.weight"].to(device=device, dtype=torch.float32)
+    if prefix + ".bn.weight" in sd:
+        g = sd[prefix + ".bn.weight"].to(device=device, dtype=torch.float32)
+        b = sd[prefix + ".bn.bias"].to(device=device, dtype=torch.float32)
+        m = sd[prefix + ".bn.running_mean"].to(device=device, dtype=torch.float32)
+        v = sd[prefix + ".bn.running_var"].to(device=device, dtype=torch.float32)
+        s = g / torch.sqrt(v + eps)
+        return w * s.view(-1, 1, 1, 1), b - m * s
+    bias = sd.get(prefix + ".conv.bias")
+    bias = torch.zeros(w.shape[0], device=device) if bias is None else bias.to(device=device, dtype=torch.float32)
+    return w, bias
+
+
+@dataclass
+class TRef:
+    """A channel slice of an NHWC fp16 buffer."""
+    buf: torch.Tensor       # [n, h, w, pitch]
+    c0: int
+    c: int
+
+    @property
+    def pitch(self) -> int:
+        return self.buf.shape[-1]
+
+    @property
+    def h(self) -> int:
+        return self.buf.shape[1]
+
+    @property
+    def w(self) -> int:
+        return self.buf.shape[2]
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr() + self.c0 * self.buf.element_size()
+
+    def view(self) -> torch.Tensor:
+        return self.buf[..., self.c0:self.c0 + self.c]
+
+
+class _Plan:
+    """Ordered list of launch closures + bookkeeping of algorithmic work."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.steps: List[Callable[[object], None]] = []
+        self.conv_flops = 0.0
+        self.num_convs = 0
+        self.keep: list = []          # tensors that must outlive the plan (weights, descriptors)
+        self.graph: Optional[ops.Graph] = None
+        self.stream = torch.cuda.Stream(device=device)
+
+    def add(self, fn: Callable[[object], None]) -> None:
+        self.steps.append(fn)
+
+    def conv(self, x: TRef, n: int, w: torch.Tensor, b: Optional[torch.Tensor], y: TRef, k: int, s: int, p: int, act: int,
+             residual: Optional[TRef] = None, res_mode: int = L.RES_NONE, out_dtype: int = L.F16, a_mode: int = L.A_AUTO):
+        cout, cin = int(w.shape[0]), int(w.shape[1])
+        d = ops.make_conv_desc(n, x.h, x.w, cin, cout, k, s, p, cin_pitch=x.pitch, cout_pitch=y.pitch, act=act,
+                               res_mode=res_mode if residual is not None else L.RES_NONE,
+                               res_pitch=residual.pitch if residual is not None else 0, out_dtype=out_dtype, a_mode=a_mode)
+        ho, wo = ops.conv_out_hw(d)
+        assert (ho, wo) == (y.h, y.w), ((ho, wo), (y.h, y.w))
+        assert x.c == cin or (cin <= 4 and x.pitch == 4), (x.c, cin)
+        wp, bp = ops.pack_conv_weights(d, w, b)
+        xp, yp, rp = x.ptr, y.ptr, (residual.ptr if residual is not None else 0)
+        self.keep += [d, wp, bp, x.buf, y.buf] + ([residual.buf] if residual is not None else [])
+        self.conv_flops += 2.0 * n * ho * wo * cout * cin * k * k
+        self.num_convs += 1
+        self.add(lambda st, d=d, xp=xp, wp=wp, bp=bp, yp=yp, rp=rp: ops.conv2d(d, xp, wp, bp, yp, residual=rp, stream=st))
+
+    def run_eager(self, stream=None) -> None:
+        st = stream if stream is not None else self.stream
+        for fn in self.steps:
+            fn(st)
+
+    def capture(self) -> None:
+        torch.cuda.synchronize(self.device)
+        ops.graph_begin(self.stream)
+        try:
+            for fn in self.steps:
+                fn(self.stream)
+        finally:
+            self.graph = ops.graph_end(self.stream)
+
+    def run(self, use_graph: bool = True) -> None:
+        """Enqueue one pass on the plan's stream."""
+        if use_graph:
+            if self.graph is None:
+                self.capture()
+            self.graph.launch(self.stream)
+        else:
+            self.run_eager(self.stream)
+
+
+class YoloEngine:
+    """YOLOv5 v6.0 detector for a fixed batch of `batch` frames at inference size (h, w) (multiples of 32)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, h: int, w: int, *, device="cuda:0", conf=0.25, iou=0.45,
+                 max_det=300, max_wh=4096.0, max_nms=30000, model_name: Optional[str] = None, fp32_logits: bool = True,
+                 a_mode: int = L.A_AUTO):
+        assert h % 32 == 0 and w % 32 == 0, "inference shape must be a multiple of the max stride (32)"
+        self.device = torch.device(device)
+        L.init(self.device.index or 0)
+        self.batch, self.h, self.w = batch, h, w
+        self.conf, self.iou, self.max_det, self.max_wh, self.max_nms = conf, iou, max_det, max_wh, max_nms
+        self.name = model_name or infer_model_name(state_dict)
+        self.fp32_logits = fp32_logits
+        self.a_mode = a_mode
+        gd, gw = MODEL_SCALES[self.name]
+        det_w = state_dict["model.24.m.0.weight"]
+        self.nc = det_w.shape[0] // 3 - 5
+        self.no = self.nc + 5
+        if "model.24.anchors" in state_dict:      # checkpoint anchors are in grid units
+            a = state_dict["model.24.anchors"].float().cpu() * torch.tensor(STRIDES, dtype=torch.float32).view(-1, 1, 1)
+            self.anchors_px = [tuple(float(v) for v in a[i].flatten()) for i in range(3)]
+        else:
+            self.anchors_px = [tuple(float(v) for v in ANCHORS_PX[i]) for i in range(3)]
+        self.plan = _Plan(self.device)
+        self._build(state_dict, gd, gw)
+
+    # -- buffer helpers ------------------------------------------------------------------------
+    def _buf(self, h, w, c, dtype=torch.float16) -> torch.Tensor:
+        return torch.zeros(self.batch, h, w, c, dtype=dtype, device=self.device)
+
+    def _build(self, sd, gd, gw) -> None:
+        B, dev, plan = self.batch, self.device, self.plan
+        nl = len(LAYERS_V6)
+        # 1. channel / spatial bookkeeping
+        ch: List[int] = []
+        hw: List[Tuple[int, int]] = []
+        reps: List[int] = []
+        for i, (f, n, kind, args) in enumerate(LAYERS_V6):
+            def cin(j):
+                return (3 if i == 0 else ch[i - 1]) if j == -1 else ch[j]
+
+            def shp(j):
+                return ((self.h, self.w) if i == 0 else hw[i - 1]) if j == -1 else hw[j]
+            n = max(round(n * gd), 1) if n > 1 else n
+            reps.append(n)
+            if kind == "Conv":
+                c2, k, s, p = _ceil8(args[0] * gw), args[1], args[2], args[3]
+                hh, ww = shp(f)
+                ch.append(c2); hw.append(((hh + 2 * p - k) // s + 1, (ww + 2 * p - k) // s + 1))
+            elif kind in ("C3", "SPPF"):
+                ch.append(_ceil8(args[0] * gw)); hw.append(shp(f))
+            elif kind == "Up":
+                ch.append(cin(f)); hw.append((shp(f)[0] * 2, shp(f)[1] * 2))
+            elif kind == "Cat":
+                ch.append(sum(cin(j) for j in f)); hw.append(shp(f[0]))
+            else:
+                ch.append(0); hw.append((0, 0))
+        # 2. homes: an output that feeds a Cat lives inside the Cat's buffer (concat-free)
+        cat_buf: Dict[int, torch.Tensor] = {}
+        home: Dict[int, TRef] = {}
+        for i, (f, n, kind, args) in enumerate(LAYERS_V6):
+            if kind != "Cat":
+                continue
+            cat_buf[i] = self._buf(hw[i][0], hw[i][1], ch[i])
+            off = 0
+            for j in f:
+                src = i - 1 if j == -1 else j
+                assert src not in home, "an output may feed only one Concat"
+                home[src] = TRef(cat_buf[i], off, ch[src])
+                off += ch[src]
+            home[i] = TRef(cat_buf[i], 0, ch[i])
+        for i, (f, n, kind, args) in enumerate(LAYERS_V6):
+            if i not in home and kind not in ("Detect",):
+                home[i] = TRef(self._buf(hw[i][0], hw[i][1], ch[i]), 0, ch[i])
+        self.layer_out = home
+
+        # 3. input ingest
+        self.frames = torch.zeros(B, self.h, self.w, 3, dtype=torch.uint8, device=dev)
+        self.x_c4 = torch.zeros(B, self.h, self.w, 4, dtype=torch.float16, device=dev)
+        plan.add(lambda st: ops.frames_to_f16c4(self.frames, self.x_c4, stream=st))
+
+        def src_of(i, f) -> TRef:
+            return TRef(self.x_c4, 0, 3) if (i == 0 and f == -1) else home[i - 1 if f == -1 else f]
+
+        SILU = L.ACT_SILU
+        for i, (f, n, kind, args) in enumerate(LAYERS_V6):
+            pre = f"model.{i}"
+            if kind == "Conv":
+                k, s, p = args[1], args[2], args[3]
+                w_, b_ = fold_conv_bn(sd, pre, YOLO_BN_EPS, dev)
+                plan.conv(src_of(i, f), B, w_, b_, home[i], k, s, p, SILU,
+                          a_mode=L.A_C4 if i == 0 else self.a_mode)
+            elif kind == "C3":
+                x = src_of(i, f)
+                c2, shortcut = ch[i], args[1]
+                c_ = c2 // 2
+                hh, ww = hw[i]
+                cat = self._buf(hh, ww, 2 * c_)
+                nrep = reps[i]
+                # cv2 -> right half of the concat buffer
+                w_, b_ = fold_conv_bn(sd, pre + ".cv2", YOLO_BN_EPS, dev)
+                plan.conv(x, B, w_, b_, TRef(cat, c_, c_), 1, 1, 0, SILU, a_mode=self.a_mode)
+                # cv1 -> chain of bottlenecks -> left half
+                ping = [TRef(self._buf(hh, ww, c_), 0, c_), TRef(self._buf(hh, ww, c_), 0, c_)]
+                tmp = TRef(self._buf(hh, ww, c_), 0, c_)
+                cur = ping[0]
+                w_, b_ = fold_conv_bn(sd, pre + ".cv1", YOLO_BN_EPS, dev)
+                plan.conv(x, B, w_, b_, cur, 1, 1, 0, SILU, a_mode=self.a_mode)
+                for j in range(nrep):
+                    dst = TRef(cat, 0, c_) if j == nrep - 1 else ping[(j + 1) & 1]
+                    w1, b1 = fold_conv_bn(sd, f"{pre}.m.{j}.cv1", YOLO_BN_EPS, dev)
+                    plan.conv(cur, B, w1, b1, tmp, 1, 1, 0, SILU, a_mode=self.a_mode)
+                    w2, b2 = fold_conv_bn(sd, f"{pre}.m.{j}.cv2", YOLO_BN_EPS, dev)
+                    plan.conv(tmp, B, w2, b2, dst, 3, 1, 1, SILU, residual=cur if shortcut else None,
+                              res_mode=L.RES_AFTER_ACT, a_mode=self.a_mode)
+                    cur = dst
+                w_, b_ = fold_conv_bn(sd, pre + ".cv3", YOLO_BN_EPS, dev)
+                plan.conv(TRef(cat, 0, 2 * c_), B, w_, b_, home[i], 1, 1, 0, SILU, a_mode=self.a_mode)
+            elif kind == "SPPF":
+                x = src_of(i, f)
+                c_ = x.c // 2
+                hh, ww = hw[i]
+                cat = self._buf(hh, ww, 4 * c_)
+                w_, b_ = fold_conv_bn(sd, pre + ".cv1", YOLO_BN_EPS, dev)
+                plan.conv(x, B, w_, b_, TRef(cat, 0, c_), 1, 1, 0, SILU, a_mode=self.a_mode)
+                plan.add(lambda st, cat=cat, c_=c_, hh=hh, ww=ww: ops.sppf_pool(cat, 4 * c_, B, hh, ww, c_, stream=st))
+                w_, b_ = fold_conv_bn(sd, pre + ".cv2", YOLO_BN_EPS, dev)
+                plan.conv(TRef(cat, 0, 4 * c_), B, w_, b_, home[i], 1, 1, 0, SILU, a_mode=self.a_mode)
+            elif kind == "Up":
+                x = src_of(i, f)
+                y = home[i]
+                plan.add(lambda st, x=x, y=y: ops.upsample2x(x.ptr, x.pitch, y.ptr, y.pitch, B, x.h, x.w, x.c, stream=st))
+            elif kind == "Cat":
+                pass                                   # producers already wrote their slices
+            elif kind == "Detect":
+                self._build_head(sd, [home[j] for j in f])
+
+    def _build_head(self, sd, feats: Sequence[TRef]) -> None:
+        B, dev, plan = self.batch, self.device, self.plan
+        no3 = 3 * self.no
+        pitch = (no3 + 7) // 8 * 8
+        ldt = torch.float32 if self.fp32_logits else torch.float16
+        self.logits = []
+        dd = L.DetectDesc()
+        dd.n, dd.nc, dd.num_levels = B, self.nc, len(feats)
+        dd.logits_dtype = L.F32 if self.fp32_logits else L.F16
+        dd.conf_thres = float(self.conf)
+        P = 0
+        for li, ft in enumerate(feats):
+            lg = torch.zeros(B, ft.h, ft.w, pitch, dtype=ldt, device=dev)
+            self.logits.append(lg)
+            w_ = sd[f"model.24.m.{li}.weight"].to(device=dev, dtype=torch.float32)
+            b_ = sd[f"model.24.m.{li}.bias"].to(device=dev, dtype=torch.float32)
+            plan.conv(ft, B, w_, b_, TRef(lg, 0, no3), 1, 1, 0, L.ACT_NONE, out_dtype=dd.logits_dtype, a_mode=self.a_mode)
+            lv = dd.level[li]
+            lv.logits, lv.pitch, lv.ny, lv.nx = lg.data_ptr(), pitch, ft.h, ft.w
+            lv.stride = float(self.h // ft.h)
+            for a in range(3):
+                lv.anchor_w[a] = self.anchors_px[li][2 * a]
+                lv.anchor_h[a] = self.anchors_px[li][2 * a + 1]
+            P += 3 * ft.h * ft.w
+        self.num_pred = P
+        dd.max_candidates = P
+        self.cand_box = torch.zeros(B, P, 4, dtype=torch.float32, device=dev)
+        self.cand_score = torch.zeros(B, P, dtype=torch.float32, device=dev)
+        self.cand_cls = torch.zeros(B, P, dtype=torch.int32, device=dev)
+        self.cand_index = torch.zeros(B, P, dtype=torch.int32, device=dev)
+        self.cand_count = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.nms_ws = torch.zeros(max(ops.nms_workspace_bytes(B, P) // 8, 1), dtype=torch.int64, device=dev)
+        self.det = torch.zeros(B, self.max_det, 6, dtype=torch.float32, device=dev)
+        self.det_count = torch.zeros(B, dtype=torch.int32, device=dev)
+        # scale_coords parameters per frame: gain, pad_x, pad_y, w0, h0
+        self.scale = torch.zeros(5, B, dtype=torch.float32, device=dev)
+        self.scale_host = torch.zeros(5, B, dtype=torch.float32).pin_memory()
+        self.set_identity_scale()
+        nd = L.NmsDesc()
+        nd.n, nd.max_candidates, nd.max_det = B, P, self.max_det
+        nd.iou_thres, nd.max_wh, nd.max_nms = float(self.iou), float(self.max_wh), int(self.max_nms)
+        nd.gain, nd.pad_x, nd.pad_y, nd.w0, nd.h0 = (self.scale[i].data_ptr() for i in range(5))
+        self._dd, self._nd = dd, nd
+        plan.add(lambda st: ops.detect_decode(dd, self.cand_box, self.cand_score, self.cand_cls, self.cand_index,
+                                              self.cand_count, stream=st))
+        plan.add(lambda st: ops.nms(nd, self.cand_box, self.cand_score, self.cand_cls, self.cand_index, self.cand_count,
+                                    self.nms_ws, self.det, self.det_count, stream=st))
+        # pinned host mirrors of the result
+        self.det_host = torch.zeros(B, self.max_det, 6, dtype=torch.float32).pin_memory()
+        self.det_count_host = torch.zeros(B, dtype=torch.int32).pin_memory()
+
+    # -- per-call API --------------------------------------------------------------------------
+    def set_identity_scale(self) -> None:
+        self.scale_host[0].fill_(1.0); self.scale_host[1].zero_(); self.scale_host[2].zero_()
+        self.scale_host[3].fill_(float(self.w)); self.scale_host[4].fill_(float(self.h))
+        self.scale.copy_(self.scale_host)
+
+    def set_scale(self, shapes0: Sequence[Tuple[int, int]]) -> None:
+        """scale_coords parameters for original shapes (h0, w0) letterboxed into (self.h, self.w)."""
+        for i, (h0, w0) in enumerate(shapes0):
+            gain = min(self.h / h0, self.w / w0)
+            self.scale_host[0, i] = gain
+            self.scale_host[1, i] = (self.w - w0 * gain) / 2
+            self.scale_host[2, i] = (self.h - h0 * gain) / 2
+            self.scale_host[3, i] = float(w0)
+            self.scale_host[4, i] = float(h0)
+        with torch.cuda.stream(self.plan.stream):
+            self.scale.copy_(self.scale_host, non_blocking=True)
+
+    def upload(self, frames_host: torch.Tensor) -> None:
+        """H2D of a pinned uint8 [batch, h, w, 3] tensor on the plan's stream."""
+        with torch.cuda.stream(self.plan.stream):
+            self.frames.copy_(frames_host, non_blocking=True)
+
+    def forward(self, use_graph: bool = True) -> None:
+        """frames (device) -> det/det_count (device); asynchronous on the plan's stream."""
+        self.plan.run(use_graph)
+
+    def download(self) -> Tuple[np.ndarray, np.ndarray]:
+        with torch.cuda.stream(self.plan.stream):
+            self.det_host.copy_(self.det, non_blocking=True)
+            self.det_count_host.copy_(self.det_count, non_blocking=True)
+        self.plan.stream.synchronize()
+        return self.det_host.numpy(), self.det_count_host.numpy()
+
+    @property
+    def conv_flops_per_frame(self) -> float:
+        return self.plan.conv_flops / self.batch
+
+
+# ---------------------------------------------------------------------------------------------
+# ReID
+# ---------------------------------------------------------------------------------------------
+REID_SIZE = 50
+REID_MEAN = (0.485, 0.456, 0.406)
+REID_STD = (0.229, 0.224, 0.225)
+REID_BN_EPS = 1e-5
+REID_BLOCKS = [("layer1.0", 64, 64, False), ("layer1.1", 64, 64, False), ("layer2.0", 64, 128, True),
+               ("layer2.1", 128, 128, False), ("layer3.0", 128, 256, True), ("layer3.1", 256, 256, False),
+               ("layer4.0", 256, 512, True), ("layer4.1", 512, 512, False)]
+
+
+def _fold_plain(w, bias, bn, eps, device):
+    """conv weight [+bias] and BN tensors (gamma, beta, mean, var) -> folded (w', b') fp32."""
+    w = w.to(device=device, dtype=torch.float32)
+    g, b, m, v = (t.to(device=device, dtype=torch.float32) for t in bn)
+    s = g / torch.sqrt(v + eps)
+    b0 = torch.zeros_like(m) if bias is None else bias.to(device=device, dtype=torch.float32)
+    return w * s.view(-1, 1, 1, 1), (b0 - m) * s + b
+
+
+class ReidEngine:
+    """DeepSORT appearance CNN over up to `capacity` crops per call.
+
+    bn_mode="eval": BatchNorm folded into the convolutions (running statistics) -- the fast path, one dense
+    batch, results independent of batch composition.  bn_mode="train": the reference as shipped (it never
+    calls .eval()): per-call batch statistics; crops are grouped in segments = one reference
+    `Extractor.__call__` each (all detections of one class in one frame)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], capacity: int = 64, *, device="cuda:0", bn_mode: str = "eval",
+                 a_mode: int = L.A_AUTO):
+        assert bn_mode in ("eval", "train")
+        self.device = torch.device(device)
+        L.init(self.device.index or 0)
+        self.sd = {k: v for k, v in state_dict.items() if not k.startswith("classifier")}
+        self.capacity = capacity
+        self.bn_mode = bn_mode
+        self.a_mode = a_mode
+        self._plans: Dict[int, dict] = {}
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.rois = torch.zeros(capacity, 5, dtype=torch.int32, device=self.device)
+        self.rois_host = torch.zeros(capacity, 5, dtype=torch.int32).pin_memory()
+        self.features = torch.zeros(capacity, 512, dtype=torch.float32, device=self.device)
+        self.features_host = torch.zeros(capacity, 512, dtype=torch.float32).pin_memory()
+        self.conv_flops_per_crop = 0.0
+
+    def _bucket(self, n: int) -> int:
+        b = 8
+        while b < n:
+            b *= 2
+        return min(b, max(self.capacity, n))
+
+    def _bn(self, p):
+        sd = self.sd
+        return (sd[p + ".weight"], sd[p + ".bias"], sd[p + ".running_mean"], sd[p + ".running_var"])
+
+    # -- eval-mode plan (graph captured per crop-count bucket) -----------------------------------
+    def _build_eval(self, nb: int, frames: torch.Tensor) -> dict:
+        dev, sd = self.device, self.sd
+        plan = _Plan(dev)
+        plan.stream = self.stream
+        fh, fw = frames.shape[1], frames.shape[2]
+
+        def buf(h, c, dtype=torch.float16):
+            return torch.zeros(nb, h, h, c, dtype=dtype, device=dev)
+
+        rd = L.RoiDesc()
+        rd.num_rois, rd.out_size = nb, REID_SIZE
+        for c in range(3):
+            rd.mean[c] = REID_MEAN[c]; rd.inv_std[c] = 1.0 / REID_STD[c]
+        x0 = buf(REID_SIZE, 4)
+        plan.keep += [rd, frames]
+        plan.add(lambda st: ops.roi_resize_norm(rd, frames, fh, fw, self.rois, x0, stream=st))
+        RELU = L.ACT_RELU
+        w_, b_ = _fold_plain(sd["conv.0.weight"], sd["conv.0.bias"], self._bn("conv.1"), REID_BN_EPS, dev)
+        s0 = buf(50, 64)
+        plan.conv(TRef(x0, 0, 3), nb, w_, b_, TRef(s0, 0, 64), 3, 1, 1, RELU, a_mode=L.A_C4)
+        cur = TRef(buf(25, 64), 0, 64)
+        plan.add(lambda st, s0=s0, cur=cur: ops.maxpool(s0, 64, cur.buf, 64, nb, 50, 50, 64, 3, 2, 1, stream=st))
+        size = 25
+        for prefix, ci, co, down in REID_BLOCKS:
+            s = 2 if down else 1
+            osz = (size + 2 - 3) // s + 1
+            w1, b1 = _fold_plain(sd[prefix + ".conv1.weight"], None, self._bn(prefix + ".bn1"), REID_BN_EPS, dev)
+            t = TRef(buf(osz, co), 0, co)
+            plan.conv(cur, nb, w1, b1, t, 3, s, 1, RELU, a_mode=self.a_mode)
+            if down:
+                wd, bd = _fold_plain(sd[prefix + ".downsample.0.weight"], None, self._bn(prefix + ".downsample.1"), REID_BN_EPS, dev)
+                sc = TRef(buf(osz, co), 0, co)
+                plan.conv(cur, nb, wd, bd, sc, 1, 2, 0, L.ACT_NONE, a_mode=self.a_mode)
+            else:
+                sc = cur
+            w2, b2 = _fold_plain(sd[prefix + ".conv2.weight"], None, self._bn(prefix + ".bn2"), REID_BN_EPS, dev)
+            y = TRef(buf(osz, co), 0, co)
+            plan.conv(t, nb, w2, b2, y, 3, 1, 1, RELU, residual=sc, res_mode=L.RES_BEFORE_ACT, a_mode=self.a_mode)
+            cur, size = y, osz
+        assert size == 4
+        feats = self.features
+        plan.add(lambda st, cur=cur: ops.avgpool_l2norm(cur.buf, 512, nb, 16, 512, feats, stream=st))
+        self.conv_flops_per_crop = plan.conv_flops / nb
+        return {"plan": plan, "frames_ptr": frames.data_ptr(), "shape": tuple(frames.shape)}
+
+    # -- train-mode (reference-faithful) pass, launched eagerly ----------------------------------
+    def _run_train(self, frames: torch.Tensor, n: int, seg_sizes: Sequence[int]) -> None:
+        dev, sd, st = self.device, self.sd, self.stream
+        fh, fw = frames.shape[1], frames.shape[2]
+        nseg = len(seg_sizes)
+        cache = self._plans.setdefault(("train", n), {})
+        if not cache:
+            cache["w"] = {}
+
+            def pack(name, w, bias, d):
+                cache["w"][name] = ops.pack_conv_weights(d, w.to(device=dev, dtype=torch.float32),
+                                                         None if bias is None else bias.to(device=dev, dtype=torch.float32))
+        seg = np.asarray(seg_sizes, np.int64)
+
+        def seg_arrays(hw):
+            start = torch.from_numpy(np.concatenate([[0], np.cumsum(seg * hw)]).astype(np.int32)).to(dev)
+            row_seg = torch.from_numpy(np.repeat(np.arange(nseg, dtype=np.int32), seg * hw)).to(dev)
+            return start, row_seg
+
+        def conv_raw(x: TRef, wname, bias_name, co, k, s, p, a_mode):
+            w = sd[wname]
+            d = ops.make_conv_desc(n, x.h, x.w, int(w.shape[1]), co, k, s, p, cin_pitch=x.pitch, cout_pitch=co, act=L.ACT_NONE,
+                                   out_dtype=L.F32, a_mode=a_mode)
+            ho, wo = ops.conv_out_hw(d)
+            if wname not in cache["w"]:
+                cache["w"][wname] = ops.pack_conv_weights(d, w.to(device=dev, dtype=torch.float32),
+                                                          None if bias_name is None else sd[bias_name].to(device=dev, dtype=torch.float32),
+                                                          stream=st)
+            wp, bp = cache["w"][wname]
+            raw = torch.empty(n, ho, wo, co, dtype=torch.float32, device=dev)
+            ops.conv2d(d, x.ptr, wp, bp, raw, stream=st)
+            return raw, ho
+
+        def bn_act(raw, osz, bnp, act, residual: Optional[TRef]):
+            co = raw.shape[-1]
+            rows = n * osz * osz
+            start, row_seg = seg_arrays(osz * osz)
+            scale = torch.empty(nseg, co, device=dev); shift = torch.empty(nseg, co, device=dev)
+            g = sd[bnp + ".weight"].to(device=dev, dtype=torch.float32); b = sd[bnp + ".bias"].to(device=dev, dtype=torch.float32)
+            ops.bn_train_stats(raw, co, start, nseg, g, b, REID_BN_EPS, scale, shift, stream=st)
+            y = torch.empty(n, osz, osz, co, dtype=torch.float16, device=dev)
+            ops.bn_apply(raw, co, rows, row_seg, scale, shift, None if residual is None else residual.ptr,
+                         0 if residual is None else residual.pitch, act, y, co, stream=st)
+            return TRef(y, 0, co)
+
+        with torch.cuda.stream(st):
+            rd = L.RoiDesc()
+            rd.num_rois, rd.out_size = n, REID_SIZE
+            for c in range(3):
+                rd.mean[c] = REID_MEAN[c]; rd.inv_std[c] = 1.0 / REID_STD[c]
+            x0 = torch.zeros(n, REID_SIZE, REID_SIZE, 4, dtype=torch.float16, device=dev)
+            ops.roi_resize_norm(rd, frames, fh, fw, self.rois, x0, stream=st)
+            raw, osz = conv_raw(TRef(x0, 0, 3), "conv.0.weight", "conv.0.bias", 64, 3, 1, 1, L.A_C4)
+            s0 = bn_act(raw, osz, "conv.1", L.ACT_RELU, None)
+            cur = TRef(torch.empty(n, 25, 25, 64, dtype=torch.float16, device=dev), 0, 64)
+            ops.maxpool(s0.buf, 64, cur.buf, 64, n, 50, 50, 64, 3, 2, 1, stream=st)
+            for prefix, ci, co, down in REID_BLOCKS:
+                s = 2 if down else 1
+                raw, osz = conv_raw(cur, prefix + ".conv1.weight", None, co, 3, s, 1, self.a_mode)
+                t = bn_act(raw, osz, prefix + ".bn1", L.ACT_RELU, None)
+                if down:
+                    rawd, _ = conv_raw(cur, prefix + ".downsample.0.weight", None, co, 1, 2, 0, self.a_mode)
+                    sc = bn_act(rawd, osz, prefix + ".downsample.1", L.ACT_NONE, None)
+                else:
+                    sc = cur
+                raw2, _ = conv_raw(t, prefix + ".conv2.weight", None, co, 3, 1, 1, self.a_mode)
+                cur = bn_act(raw2, osz, prefix + ".bn2", L.ACT_RELU, sc)
+            ops.avgpool_l2norm(cur.buf, 512, n, 16, 512, self.features, stream=st)
+
+    # -- per-call API --------------------------------------------------------------------------
+    def run(self, frames: torch.Tensor, rois, n: Optional[int] = None, seg_sizes: Optional[Sequence[int]] = None,
+            use_graph: bool = True) -> torch.Tensor:
+        """frames: device uint8 [F, H, W, 3]; rois: host int32 [n,5] (frame, x1, y1, x2, y2) or None when
+        self.rois was filled on the device.  Returns the device tensor features[:n] (async on self.stream)."""
+        if rois is not None:
+            rois = np.ascontiguousarray(rois, dtype=np.int32).reshape(-1, 5)
+            n = rois.shape[0]
+            assert n <= self.capacity, (n, self.capacity)
+            self.rois_host.zero_()
+            self.rois_host[:n] = torch.from_numpy(rois)
+            with torch.cuda.stream(self.stream):
+                self.rois.copy_(self.rois_host, non_blocking=True)
+        assert n is not None
+        if n == 0:
+            return self.features[:0]
+        if self.bn_mode == "train":
+            self._run_train(frames, n, list(seg_sizes) if seg_sizes is not None else [n])
+            return self.features[:n]
+        nb = self._bucket(n)
+        key = (nb, frames.data_ptr(), tuple(frames.shape))
+        ent = self._plans.get(key)
+        if ent is None:
+            ent = self._build_eval(nb, frames)
+            self._plans[key] = ent
+        ent["plan"].run(use_graph)
+        return self.features[:n]
+
+    def download(self, n: int) -> np.ndarray:
+        with torch.cuda.stream(self.stream):
+            self.features_host[:n].copy_(self.features[:n], non_blocking=True)
+        self.stream.synchronize()
+        return self.features_host[:n].numpy().copy()

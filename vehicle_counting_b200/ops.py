@@ -1,0 +1,163 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/vcb200.h).
+
+Tensors are torch CUDA tensors used purely as device buffers; every function enqueues on the
+given (or current) CUDA stream and returns immediately.  NHWC fp16 activations carry an explicit
+channel pitch = size of the last dimension of the *buffer* they live in, so a producer can write a
+channel slice of a wider concat buffer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _st(stream) -> int:
+    return L.stream_handle(stream)
+
+
+# ------------------------------------------------------------------------------------------ conv
+def make_conv_desc(n, h, w, cin, cout, k, stride, pad, *, cin_pitch=None, cout_pitch=None, act=L.ACT_SILU,
+                   res_mode=L.RES_NONE, res_pitch=0, out_dtype=L.F16, a_mode=L.A_AUTO, block_n=0, stages=0,
+                   kw=None) -> L.ConvDesc:
+    d = L.ConvDesc()
+    d.n, d.h, d.w = n, h, w
+    d.cin, d.cin_pitch = cin, cin if cin_pitch is None else cin_pitch
+    d.cout = cout
+    d.cout_pitch = ((cout + 7) // 8 * 8) if cout_pitch is None else cout_pitch
+    d.kh, d.kw = k, (k if kw is None else kw)
+    d.stride, d.pad = stride, pad
+    d.act, d.res_mode, d.res_pitch = act, res_mode, res_pitch
+    d.out_dtype, d.a_mode, d.block_n, d.stages = out_dtype, a_mode, block_n, stages
+    return d
+
+
+def conv_out_hw(d: L.ConvDesc) -> Tuple[int, int]:
+    ho, wo = C.c_int32(), C.c_int32()
+    L.check(L.load().vcb_conv_out_hw(C.byref(d), C.byref(ho), C.byref(wo)), "vcb_conv_out_hw")
+    return ho.value, wo.value
+
+
+def conv_packed_sizes(d: L.ConvDesc) -> Tuple[int, int]:
+    a, b = C.c_int64(), C.c_int64()
+    L.check(L.load().vcb_conv_packed_sizes(C.byref(d), C.byref(a), C.byref(b)), "vcb_conv_packed_sizes")
+    return a.value, b.value
+
+
+def pack_conv_weights(d: L.ConvDesc, w_oihw: torch.Tensor, bias: Optional[torch.Tensor], stream=None):
+    """fp32 OIHW (BN folded) + bias on the device -> (packed fp16 blob, padded fp32 bias)."""
+    lib = L.init(w_oihw.device.index or 0)
+    nw, nb = conv_packed_sizes(d)
+    w_oihw = w_oihw.contiguous().float()
+    assert tuple(w_oihw.shape) == (d.cout, d.cin, d.kh, d.kw), (tuple(w_oihw.shape), (d.cout, d.cin, d.kh, d.kw))
+    wp = torch.empty(nw, dtype=torch.float16, device=w_oihw.device)
+    bp = torch.empty(nb, dtype=torch.float32, device=w_oihw.device)
+    if bias is not None:
+        bias = bias.contiguous().float()
+    L.check(lib.vcb_conv_pack_weights(C.byref(d), L.ptr(w_oihw), L.ptr(bias), L.ptr(wp), L.ptr(bp), _st(stream)),
+            "vcb_conv_pack_weights")
+    return wp, bp
+
+
+def conv2d(d: L.ConvDesc, x, wp, bp, y, residual=None, stream=None) -> None:
+    lib = L.load()
+    L.check(lib.vcb_conv2d_fwd(C.byref(d), L.ptr(x), L.ptr(wp), L.ptr(bp), L.ptr(residual), L.ptr(y), _st(stream)),
+            "vcb_conv2d_fwd")
+
+
+# ------------------------------------------------------------------------------------------ data movement
+def frames_to_f16c4(frames_u8: torch.Tensor, out: torch.Tensor, stream=None) -> None:
+    n, h, w, c = frames_u8.shape
+    assert c == 3 and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+    L.check(L.load().vcb_frames_to_f16c4(L.ptr(frames_u8), L.ptr(out), n, h, w, _st(stream)), "vcb_frames_to_f16c4")
+
+
+def upsample2x(src, src_pitch, dst, dst_pitch, n, h, w, c, stream=None) -> None:
+    L.check(L.load().vcb_upsample2x(L.ptr(src), src_pitch, L.ptr(dst), dst_pitch, n, h, w, c, _st(stream)),
+            "vcb_upsample2x")
+
+
+def sppf_pool(buf, pitch, n, h, w, c, stream=None) -> None:
+    L.check(L.load().vcb_sppf_pool(L.ptr(buf), pitch, n, h, w, c, _st(stream)), "vcb_sppf_pool")
+
+
+def maxpool(src, src_pitch, dst, dst_pitch, n, h, w, c, k, s, p, stream=None) -> None:
+    L.check(L.load().vcb_maxpool(L.ptr(src), src_pitch, L.ptr(dst), dst_pitch, n, h, w, c, k, s, p, _st(stream)),
+            "vcb_maxpool")
+
+
+def avgpool_l2norm(x, pitch, n, hw, c, out, stream=None) -> None:
+    L.check(L.load().vcb_avgpool_l2norm(L.ptr(x), pitch, n, hw, c, L.ptr(out), _st(stream)), "vcb_avgpool_l2norm")
+
+
+def bn_train_stats(x, c, seg_row_start, num_seg, gamma, beta, eps, scale, shift, stream=None) -> None:
+    L.check(L.load().vcb_bn_train_stats(L.ptr(x), c, L.ptr(seg_row_start), num_seg, L.ptr(gamma), L.ptr(beta),
+                                        eps, L.ptr(scale), L.ptr(shift), _st(stream)), "vcb_bn_train_stats")
+
+
+def bn_apply(x, c, rows, row_seg, scale, shift, residual, res_pitch, act, y, y_pitch, stream=None) -> None:
+    L.check(L.load().vcb_bn_apply(L.ptr(x), c, rows, L.ptr(row_seg), L.ptr(scale), L.ptr(shift),
+                                  L.ptr(residual), res_pitch, act, L.ptr(y), y_pitch, _st(stream)), "vcb_bn_apply")
+
+
+# ------------------------------------------------------------------------------------------ detect / nms
+def detect_decode(desc: L.DetectDesc, cand_box, cand_score, cand_cls, cand_index, cand_count, stream=None) -> None:
+    L.check(L.load().vcb_detect_decode(C.byref(desc), L.ptr(cand_box), L.ptr(cand_score), L.ptr(cand_cls), L.ptr(cand_index),
+                                       L.ptr(cand_count), _st(stream)), "vcb_detect_decode")
+
+
+def nms_workspace_bytes(n: int, max_candidates: int) -> int:
+    return int(L.load().vcb_nms_workspace_bytes(n, max_candidates))
+
+
+def nms(desc: L.NmsDesc, cand_box, cand_score, cand_cls, cand_index, cand_count, ws, det, det_count, stream=None) -> None:
+    L.check(L.load().vcb_nms(C.byref(desc), L.ptr(cand_box), L.ptr(cand_score), L.ptr(cand_cls), L.ptr(cand_index),
+                             L.ptr(cand_count), L.ptr(ws), L.ptr(det), L.ptr(det_count), _st(stream)), "vcb_nms")
+
+
+# ------------------------------------------------------------------------------------------ ROI
+def roi_resize_norm(desc: L.RoiDesc, frames_u8, fh, fw, rois, out, stream=None) -> None:
+    L.check(L.load().vcb_roi_resize_norm(C.byref(desc), L.ptr(frames_u8), fh, fw, L.ptr(rois), L.ptr(out), _st(stream)),
+            "vcb_roi_resize_norm")
+
+
+def boxes_to_rois(boxes_f64, frame_of, num, fw, fh, rois, stream=None) -> None:
+    L.check(L.load().vcb_boxes_to_rois(L.ptr(boxes_f64), L.ptr(frame_of), num, fw, fh, L.ptr(rois), _st(stream)),
+            "vcb_boxes_to_rois")
+
+
+# ------------------------------------------------------------------------------------------ graphs
+class Graph:
+    """A captured CUDA graph of library calls (vcb_graph_*)."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+
+    @property
+    def num_kernels(self) -> int:
+        return int(L.load().vcb_graph_num_kernels(self._h))
+
+    def launch(self, stream=None) -> None:
+        L.check(L.load().vcb_graph_launch(self._h, _st(stream)), "vcb_graph_launch")
+
+    def __del__(self):
+        try:
+            if self._h:
+                L.load().vcb_graph_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def graph_begin(stream) -> None:
+    L.check(L.load().vcb_graph_begin(_st(stream)), "vcb_graph_begin")
+
+
+def graph_end(stream) -> Graph:
+    h = C.c_void_p()
+    L.check(L.load().vcb_graph_end(_st(stream), C.byref(h)), "vcb_graph_end")
+    return Graph(h.value)
