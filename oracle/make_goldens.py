@@ -1,0 +1,118 @@
+"""ORACLE tooling: generate the committed golden vectors under tests/golden/ and the git-ignored
+weight repack under oracle/_ref/.  Run in the build container (needs /root/reference):
+
+    python -m oracle.make_goldens
+
+Outputs
+  tests/golden/reid_golden.npz     seeded BGR crops + embeddings computed by the REFERENCE's own
+                                   Extractor/Net with the shipped ckpt.t7: as shipped (train-mode BN),
+                                   and with .eval(); plus the reference preprocessing of the crops
+  tests/golden/deepsort_golden.npz a short synthetic sequence through the REFERENCE DeepSort.update
+                                   (integer output rows per frame) with the features it was fed
+  tests/golden/yolo_golden.npz     oracle (restatement) outputs on a seeded 2-frame 64x96 clip for
+                                   yolov5n: raw heads + post-NMS rows (guards the oracle against drift;
+                                   upstream itself is not importable -> "parity unpinned")
+  oracle/_ref/reid_ckpt.npz        fp32 repack of ckpt.t7's `net_dict` (derived artefact, git-ignored,
+                                   travels to the GPU box with the working tree)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import ref_shim, reid, yolov5  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF_OUT = os.path.join(ROOT, "oracle", "_ref")
+
+
+def reid_crops(seed=7):
+    rng = np.random.default_rng(seed)
+    sizes = [(80, 40), (33, 120), (50, 50), (200, 90), (17, 23), (64, 64), (5, 9), (130, 131)]
+    crops = []
+    for (h, w) in sizes:
+        # smooth-ish structured content rather than pure noise: low-res noise upsampled + noise
+        base = rng.integers(0, 256, ((h + 7) // 8, (w + 7) // 8, 3)).astype(np.float32)
+        up = np.kron(base, np.ones((8, 8, 1), np.float32))[:h, :w]
+        im = np.clip(up + rng.normal(0, 12, (h, w, 3)), 0, 255).astype(np.uint8)
+        crops.append(im)
+    return crops
+
+
+def make_reid():
+    ex = ref_shim.reference_extractor()
+    crops = reid_crops()
+    pre = ex._preprocess(crops).numpy()
+    assert ex.net.training, "reference Extractor is expected to stay in train mode"
+    f_train = ex(crops)                       # as shipped: batch statistics of THIS call
+    f_train_first3 = ex(crops[:3])            # same crops, different call composition
+    ex2 = ref_shim.reference_extractor()      # fresh copy: the train-mode calls above moved running stats
+    ex2.net.eval()
+    f_eval = ex2(crops)
+    flat = np.concatenate([c.reshape(-1) for c in crops])
+    shapes = np.array([c.shape[:2] for c in crops], np.int32)
+    np.savez_compressed(os.path.join(GOLD, "reid_golden.npz"), crops_flat=flat, crop_shapes=shapes,
+                        preprocessed=pre.astype(np.float32), feat_train=f_train, feat_train_first3=f_train_first3,
+                        feat_eval=f_eval)
+    sd = reid.load_state_dict(ref_shim.REID_CKPT)
+    os.makedirs(REF_OUT, exist_ok=True)
+    np.savez(os.path.join(REF_OUT, "reid_ckpt.npz"), **{k: v.numpy() for k, v in sd.items()})
+    print("reid golden:", f_train.shape, f_eval.shape, "ckpt tensors:", len(sd))
+
+
+def make_deepsort():
+    """3 boxes drifting 3 px/frame over a textured frame, n_init=3 (cam_04 settings)."""
+    rng = np.random.default_rng(3)
+    H, W = 240, 320
+    frame = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    ds = ref_shim.reference_deepsort(max_dist=0.2, min_confidence=0.3, nms_max_overlap=0.5, max_iou_distance=0.7,
+                                     max_age=70, n_init=3, nn_budget=100)
+    feats_log, rows, boxes_log = [], [], []
+    boxes0 = np.array([[20, 30, 80, 120], [150, 40, 230, 160], [100, 150, 160, 230]], np.float64)
+    conf = np.array([0.9, 0.8, 0.7])
+    T = 8
+    for t in range(T):
+        b = boxes0 + 3.0 * t
+        crops = reid.get_crops(b, frame)
+        feats_log.append(ds.extractor(crops))
+        out = ds.update(b.copy(), conf.copy(), frame)
+        out = np.asarray(out, dtype=np.int64).reshape(-1, 7) if len(out) else np.zeros((0, 7), np.int64)
+        rows.append(out)
+        boxes_log.append(b)
+    np.savez_compressed(os.path.join(GOLD, "deepsort_golden.npz"), frame=frame, boxes=np.stack(boxes_log), conf=conf,
+                        feats=np.stack(feats_log), row_counts=np.array([r.shape[0] for r in rows]),
+                        rows=np.concatenate(rows, 0) if rows else np.zeros((0, 7), np.int64))
+    print("deepsort golden rows per frame:", [r.shape[0] for r in rows])
+
+
+def make_yolo():
+    torch.manual_seed(0)
+    m = yolov5.build("yolov5n", seed=0, obj_bias=-1.0)
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, (64, 96, 3), dtype=np.uint8) for _ in range(2)]
+    dets, pred, raw = yolov5.autoshape_forward(m, imgs, size=96, return_raw=True)
+    np.savez_compressed(os.path.join(GOLD, "yolo_golden.npz"), imgs=np.stack(imgs),
+                        raw0=raw[0].numpy(), raw1=raw[1].numpy(), raw2=raw[2].numpy(),
+                        det_counts=np.array([d.shape[0] for d in dets]),
+                        dets=torch.cat(dets, 0).numpy() if dets else np.zeros((0, 6), np.float32))
+    print("yolo golden dets:", [d.shape[0] for d in dets])
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    if not ref_shim.available():
+        raise SystemExit("reference tree not available; goldens can only be regenerated in the build container")
+    make_reid()
+    make_deepsort()
+    make_yolo()
+
+
+if __name__ == "__main__":
+    main()

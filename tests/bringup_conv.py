@@ -45,6 +45,8 @@ for mode in ("gather", "tma"):
     case(f"{mode}-blockn64-stages3", mode=mode, n=2, h=40, w=40, k=3, p=1, cin=64, cout=128, block_n=64, stages=4)
 case("c4-yolo-stem", mode="c4", n=2, h=64, w=64, cin=3, cin_pitch=4, cout=32, k=6, s=2, p=2, act="silu")
 case("c4-reid-stem", mode="c4", n=5, h=50, w=50, cin=3, cin_pitch=4, cout=64, k=3, s=1, p=1, act="relu")
+case("prof-1x1-96-96-m819k", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, act="silu")
+case("prof-3x3-192-192-p4", mode="tma", n=32, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", res="after")
 case("c4-yolo-stem-big", mode="c4", n=4, h=640, w=640, cin=3, cin_pitch=4, cout=48, k=6, s=2, p=2, act="silu")
 
 

@@ -1,0 +1,154 @@
+"""`get_model` / `YoloBackbone` with the reference's signatures (/root/reference/networks/yolo.py:11-99),
+backed by the CUDA engine instead of `torch.hub.load('ultralytics/yolov5', ...)`.
+
+`YoloBackbone.detect(batch, device)` keeps the reference contract: `batch['imgs']` is a list of HWC uint8
+RGB arrays (sizes may differ) and the result is one dict per image with float64 `bboxes`
+(x_min, y_min, w, h in original-image pixels), integer `classes` and `scores`, rows sorted by score,
+at most `max_det` rows, three empty arrays when nothing is found.  The host half of upstream's AutoShape
+(shape bookkeeping, cv2 letterbox) is restated here; everything after the uint8 batch reaches the device
+runs in libvcb200's kernels.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from ..engine import YoloEngine
+from ..weights import load_yolov5_state_dict, synth_yolov5_state_dict
+
+COCO_NAMES = ['person', 'bicycle', 'car', 'motorcycle', 'airplane', 'bus', 'train', 'truck', 'boat', 'traffic light',
+              'fire hydrant', 'stop sign', 'parking meter', 'bench', 'bird', 'cat', 'dog', 'horse', 'sheep', 'cow', 'elephant',
+              'bear', 'zebra', 'giraffe', 'backpack', 'umbrella', 'handbag', 'tie', 'suitcase', 'frisbee', 'skis', 'snowboard',
+              'sports ball', 'kite', 'baseball bat', 'baseball glove', 'skateboard', 'surfboard', 'tennis racket', 'bottle',
+              'wine glass', 'cup', 'fork', 'knife', 'spoon', 'bowl', 'banana', 'apple', 'sandwich', 'orange', 'broccoli',
+              'carrot', 'hot dog', 'pizza', 'donut', 'cake', 'chair', 'couch', 'potted plant', 'bed', 'dining table', 'toilet',
+              'tv', 'laptop', 'mouse', 'remote', 'keyboard', 'cell phone', 'microwave', 'oven', 'toaster', 'sink',
+              'refrigerator', 'book', 'clock', 'vase', 'scissors', 'teddy bear', 'hair drier', 'toothbrush']
+
+
+def get_model(args, config):
+    """networks/yolo.py:11-34.  `args.weight` must name a v6.0 state_dict file; the reference's download
+    branch (`args.weight is None`) needs a network and is replaced by an explicit error unless
+    VCB_SYNTH_WEIGHTS=1 asks for the seeded synthetic stand-in (benchmarks, tests)."""
+    filter_classes = None if not getattr(args, "mapping_dict", None) else args.mapping_dict.keys()
+    weight = getattr(args, "weight", None)
+    if weight is None:
+        if os.environ.get("VCB_SYNTH_WEIGHTS", "0") != "1":
+            raise FileNotFoundError(
+                f"no --weight given and pretrained '{config.model_name}' cannot be downloaded here "
+                "(set VCB_SYNTH_WEIGHTS=1 to run with seeded synthetic weights)")
+        weight = f"synthetic:{config.model_name}"
+    return YoloBackbone(weight=weight, min_iou=config.min_iou, min_conf=config.min_conf, max_det=config.max_det,
+                        filter_classes=filter_classes)
+
+
+class BaseBackbone(nn.Module):
+    def __init__(self, **kwargs):
+        super().__init__()
+
+    def forward(self, batch):
+        pass
+
+    def detect(self, batch):
+        pass
+
+
+def _make_divisible(x: float, d: int) -> int:
+    return int(math.ceil(x / d) * d)
+
+
+def _letterbox(im: np.ndarray, new_shape: Tuple[int, int]) -> np.ndarray:
+    """upstream utils/augmentations.py letterbox(auto=False, scaleup=True), on the host like upstream."""
+    import cv2
+    h, w = im.shape[:2]
+    r = min(new_shape[0] / h, new_shape[1] / w)
+    new_unpad = (int(round(w * r)), int(round(h * r)))
+    dw, dh = (new_shape[1] - new_unpad[0]) / 2, (new_shape[0] - new_unpad[1]) / 2
+    if (w, h) != new_unpad:
+        im = cv2.resize(im, new_unpad, interpolation=cv2.INTER_LINEAR)
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    if top or bottom or left or right:
+        im = cv2.copyMakeBorder(im, top, bottom, left, right, cv2.BORDER_CONSTANT, value=(114, 114, 114))
+    return im
+
+
+class YoloBackbone(BaseBackbone):
+    def __init__(self, weight, min_iou, min_conf, max_det, filter_classes=None, size: int = 640, device: Optional[str] = None,
+                 state_dict: Optional[Dict[str, torch.Tensor]] = None, class_names: Optional[Sequence[str]] = None, **kwargs):
+        super().__init__(**kwargs)
+        if state_dict is None:
+            if isinstance(weight, str) and weight.startswith("synthetic:"):
+                state_dict = synth_yolov5_state_dict(weight.split(":", 1)[1], seed=0)
+            else:
+                state_dict = load_yolov5_state_dict(weight)
+        self._sd = state_dict
+        self.size = size                       # AutoShape's `size=` (the reference always uses the default 640)
+        self.conf, self.iou, self.max_det = min_conf, min_iou, max_det
+        self.classes = list(filter_classes) if filter_classes is not None else None
+        self.multi_label = False
+        nc = state_dict["model.24.m.0.weight"].shape[0] // 3 - 5
+        if class_names is None:
+            class_names = COCO_NAMES if nc == 80 else [f"class{i}" for i in range(nc)]
+        self.class_names = list(class_names)
+        self._device = device
+        self._engines: Dict[Tuple[int, int, int], YoloEngine] = {}
+        self._pinned: Dict[Tuple[int, int, int], torch.Tensor] = {}
+        # a parameter so that `.parameters()` / `.to()` behave like the reference module (detect.py:27-28)
+        self._anchor = nn.Parameter(torch.zeros(1), requires_grad=False)
+
+    def _engine(self, b: int, h: int, w: int) -> YoloEngine:
+        key = (b, h, w)
+        if key not in self._engines:
+            dev = self._device or (f"cuda:{torch.cuda.current_device()}")
+            self._engines[key] = YoloEngine(self._sd, b, h, w, device=dev, conf=self.conf, iou=self.iou, max_det=self.max_det)
+            self._pinned[key] = torch.empty(b, h, w, 3, dtype=torch.uint8).pin_memory()
+        return self._engines[key]
+
+    @torch.no_grad()
+    def detect_raw(self, imgs: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
+        """-> (det float32 [B, max_det, 6] xyxy/conf/cls in original pixels, counts int32 [B])."""
+        shape0 = [im.shape[:2] for im in imgs]
+        shape1 = [0.0, 0.0]
+        for (h, w) in shape0:                                   # AutoShape: g = size / max(h, w)
+            g = self.size / max(h, w)
+            shape1 = [max(shape1[0], h * g), max(shape1[1], w * g)]
+        h1, w1 = (_make_divisible(v, 32) for v in shape1)
+        eng = self._engine(len(imgs), h1, w1)
+        host = self._pinned[(len(imgs), h1, w1)]
+        hv = host.numpy()
+        for i, im in enumerate(imgs):
+            hv[i] = im if im.shape[:2] == (h1, w1) else _letterbox(im, (h1, w1))
+        eng.set_scale(shape0)
+        eng.upload(host)
+        eng.forward()
+        det, cnt = eng.download()
+        if self.classes is not None:                            # optional class filter (yolo.py:64)
+            det, cnt = det.copy(), cnt.copy()
+            for b in range(len(imgs)):
+                rows = det[b, :cnt[b]]
+                keep = np.isin(rows[:, 5].astype(np.int64), np.asarray(self.classes, dtype=np.int64))
+                k = int(keep.sum())
+                det[b, :k] = rows[keep]
+                cnt[b] = k
+        return det, cnt
+
+    def detect(self, batch, device=None):
+        """networks/yolo.py:68-99"""
+        det, cnt = self.detect_raw(batch["imgs"])
+        out = []
+        for b in range(len(batch["imgs"])):
+            n = int(cnt[b])
+            if n > 0:
+                # the reference round-trips through DataFrame.to_json (10 decimal digits) before np.array
+                d = np.round(det[b, :n].astype(np.float64), 10)
+                boxes = np.stack([d[:, 0], d[:, 1], d[:, 2] - d[:, 0], d[:, 3] - d[:, 1]], 1)
+                out.append({"bboxes": boxes, "classes": det[b, :n, 5].astype(np.int64), "scores": d[:, 4]})
+            else:
+                out.append({"bboxes": np.array(()), "classes": np.array(()), "scores": np.array(())})
+        return out
