@@ -62,7 +62,7 @@ typedef struct VcbConvDesc {
   int32_t a_mode;             /* VCB_A_*: how the im2col operand reaches shared memory */
   int32_t block_n;            /* 0 = auto; N tile (multiple of 16, <= 256) */
   int32_t stages;             /* 0 = auto; smem pipeline depth */
-  int32_t reserved[4];
+  int32_t reserved[4];        /* [0]=1: debug epilogue with direct global stores; [1]=1: debug 8-byte C4 gather */
 } VcbConvDesc;
 
 /* element counts of the packed fp16 weight blob and the padded fp32 bias for this descriptor */

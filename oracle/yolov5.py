@@ -300,6 +300,43 @@ def build(name: str = "yolov5s", seed: int = 0, nc: int = 80, **kw) -> Detection
     return seeded_init_(DetectionModel(name, nc), seed, **kw)
 
 
+def fp16_storage_twin(model: DetectionModel) -> DetectionModel:
+    """The same algorithm with the CUDA path's STORAGE precision emulated, arithmetic still fp32 on the CPU:
+    Conv+BN folded (upstream fuse_conv_and_bn) with the folded weights rounded to fp16, the input and every
+    activation tensor rounded to fp16 where the CUDA path stores it (after SiLU, or after the shortcut add of a
+    Bottleneck), Detect logits left in fp32.  Separates "fp16 storage" error (inherent to the precision the
+    north star prescribes) from kernel error when comparing head tensors."""
+    import copy
+    m = copy.deepcopy(model).eval()
+    r16 = lambda t: t.half().float()
+    for mod in m.modules():
+        if isinstance(mod, Conv):
+            bn = mod.bn
+            scale = bn.weight.data / torch.sqrt(bn.running_var.data + bn.eps)
+            w = mod.conv.weight.data * scale.view(-1, 1, 1, 1)
+            b = bn.bias.data - bn.running_mean.data * scale
+            fused = nn.Conv2d(mod.conv.in_channels, mod.conv.out_channels, mod.conv.kernel_size, mod.conv.stride,
+                              mod.conv.padding, bias=True)
+            fused.weight.data = r16(w)
+            fused.bias.data = b
+            mod.conv = fused
+            mod.bn = nn.Identity()
+    for mod in m.modules():
+        if isinstance(mod, Detect):
+            for c in mod.m:
+                c.weight.data = r16(c.weight.data)
+    skip = set()
+    for mod in m.modules():
+        if isinstance(mod, Bottleneck) and mod.add:
+            skip.add(mod.cv2)                               # rounded once, after the residual add
+            mod.register_forward_hook(lambda _m, _i, o: r16(o))
+    for mod in m.modules():
+        if isinstance(mod, Conv) and mod not in skip:
+            mod.register_forward_hook(lambda _m, _i, o: r16(o))
+    m.model[0].register_forward_pre_hook(lambda _m, inp: (r16(inp[0]),))
+    return m
+
+
 def fused_param_count(model: DetectionModel) -> int:
     """Parameter count after Conv+BN fusion (upstream `model.fuse()` + model_info)."""
     n = 0

@@ -24,7 +24,7 @@ CASES = []
 
 def case(name, **kw):
     base = dict(n=1, h=16, w=16, cin=64, cout=64, k=1, s=1, p=0, act="none", res="none", out="f16", mode="tma",
-                cin_pitch=None, cout_pitch=None, block_n=0, stages=0)
+                cin_pitch=None, cout_pitch=None, block_n=0, stages=0, epi_direct=False, c4_narrow=False)
     base.update(kw)
     CASES.append((name, base))
 
@@ -43,6 +43,12 @@ for mode in ("gather", "tma"):
     case(f"{mode}-resbefore-relu", mode=mode, n=4, h=13, w=13, k=3, p=1, cin=128, cout=128, act="relu", res="before")
     case(f"{mode}-big-persistent", mode=mode, n=8, h=80, w=80, k=3, p=1, cin=128, cout=256, act="silu")
     case(f"{mode}-blockn64-stages3", mode=mode, n=2, h=40, w=40, k=3, p=1, cin=64, cout=128, block_n=64, stages=4)
+case("direct-3x3-res", mode="tma", n=2, h=40, w=40, k=3, p=1, cin=96, cout=192, act="silu", res="after", epi_direct=True)
+case("direct-cout255-f32", mode="gather", n=2, h=20, w=20, cin=128, cout=255, cout_pitch=256, out="f32", epi_direct=True)
+case("tma-cout320-2tiles", mode="tma", n=2, h=20, w=20, k=1, cin=64, cout=320, act="silu")
+case("tma-cout16", mode="tma", n=2, h=20, w=20, k=3, p=1, cin=16, cout=16, act="silu")
+case("tma-cout40-f32-res", mode="tma", n=3, h=13, w=13, k=3, p=1, cin=64, cout=40, out="f32", act="relu")
+case("c4-yolo-stem-narrow", mode="c4", n=2, h=64, w=64, cin=3, cin_pitch=4, cout=32, k=6, s=2, p=2, act="silu", c4_narrow=True)
 case("c4-yolo-stem", mode="c4", n=2, h=64, w=64, cin=3, cin_pitch=4, cout=32, k=6, s=2, p=2, act="silu")
 case("c4-reid-stem", mode="c4", n=5, h=50, w=50, cin=3, cin_pitch=4, cout=64, k=3, s=1, p=1, act="relu")
 case("prof-1x1-96-96-m819k", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, act="silu")
@@ -74,7 +80,8 @@ def run_case(idx: int) -> dict:
     bias = torch.randn(cout, generator=g) * 0.5
     d = ops.make_conv_desc(n, h, w, cin, cout, k, s, p, cin_pitch=cin_pitch, cout_pitch=cout_pitch, act=act,
                            res_mode=res_mode, res_pitch=cout_pitch if res_mode else 0,
-                           out_dtype=L.F32 if c["out"] == "f32" else L.F16, a_mode=mode, block_n=c["block_n"], stages=c["stages"])
+                           out_dtype=L.F32 if c["out"] == "f32" else L.F16, a_mode=mode, block_n=c["block_n"], stages=c["stages"],
+                           epi_direct=c["epi_direct"], c4_narrow=c["c4_narrow"])
     ho, wo = ops.conv_out_hw(d)
     res_full = (torch.randn(n, ho, wo, cout_pitch, generator=g)).half() if res_mode else None
 
@@ -101,11 +108,19 @@ def run_case(idx: int) -> dict:
     ops.conv2d(d, xd, wp, bp, y, residual=resd)
     torch.cuda.synchronize()
     dt = time.time() - t0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.conv2d(d, xd, wp, bp, y, residual=resd)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 5 * 1e3
     got = y.float().cpu()
     err = (got[..., :cout] - ref).abs()
     scale = ref.abs().max().item()
     out = {"case": name, "idx": idx, "max_abs_err": err.max().item(), "ref_max": scale,
-           "rel": err.max().item() / max(scale, 1e-9), "ms_first_call": dt * 1e3}
+           "rel": err.max().item() / max(scale, 1e-9), "us": round(us, 1),
+           "tflops": round(2.0 * n * ho * wo * cout * cin * k * k / us / 1e6, 1)}
     # untouched padding channels must keep the sentinel (beyond cout_store) -- checks slice writes
     if cout_pitch > cout_store:
         out["pad_untouched"] = bool((got[..., cout_store:] == 777.0).all().item())

@@ -65,10 +65,12 @@ def main():
           f"{a.batch / ms_graph * 1e3:.0f} FPS, conv {flops / ms_graph / 1e9:.1f} TFLOP/s ({plan.num_convs} convs, "
           f"{eng.plan.graph.num_kernels} kernels)")
     order = np.argsort(-per)
-    for i in order[:25]:
-        print(f"  step {i:3d}: {per[i] * 1e3:8.1f} us")
+    for i in order[:30]:
+        fl = plan.step_flops[i]
+        print(f"  step {i:3d}: {per[i] * 1e3:8.1f} us  {fl / per[i] / 1e9 if fl else 0:7.1f} TF/s  {plan.labels[i]}")
     res["yolo"] = {"model": a.model, "batch": a.batch, "size": a.size, "ms_graph": ms_graph, "eager_ms": per.tolist(),
-                   "conv_flops": flops, "kernels": eng.plan.graph.num_kernels, "dets": eng.download()[1].tolist()}
+                   "conv_flops": flops, "kernels": eng.plan.graph.num_kernels, "dets": eng.download()[1].tolist(),
+                   "labels": plan.labels, "step_flops": plan.step_flops}
     if a.reid:
         rsd = synth_reid_state_dict(0)
         r = ReidEngine(rsd, capacity=a.reid, bn_mode="eval", a_mode=a_mode)
@@ -86,8 +88,9 @@ def main():
         torch.cuda.synchronize()
         ms_r = e0.elapsed_time(e1) / 10
         print(f"reid n={a.reid}: eager sum {per_r.sum():.3f} ms, graph {ms_r:.3f} ms -> {rp.conv_flops / ms_r / 1e9:.1f} TFLOP/s")
-        for i in np.argsort(-per_r)[:12]:
-            print(f"  step {i:3d}: {per_r[i] * 1e3:8.1f} us")
+        for i in np.argsort(-per_r)[:14]:
+            fl = rp.step_flops[i]
+            print(f"  step {i:3d}: {per_r[i] * 1e3:8.1f} us  {fl / per_r[i] / 1e9 if fl else 0:7.1f} TF/s  {rp.labels[i]}")
         res["reid"] = {"n": a.reid, "ms_graph": ms_r, "eager_ms": per_r.tolist(), "conv_flops": rp.conv_flops}
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(res, open(a.out, "w"))

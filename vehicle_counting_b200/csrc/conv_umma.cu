@@ -17,10 +17,12 @@
 // B (weights, packed [cout_pad][K_pad] fp16, K-major) always arrives by tiled TMA.  Both operands land
 // in the 128-byte-swizzled K-major layout the UMMA shared-memory descriptor expects.
 //
-// CTA = warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer, warp 5 MMA issuer
-// (+ TMEM allocator), warps 6-9 gather producers (A_GATHER / A_C4 only).  Persistent: each CTA walks
-// tiles blockIdx.x, +gridDim.x, ...; the fp32 accumulator is double-buffered in TMEM so the epilogue of
-// tile i overlaps the main loop of tile i+1.
+// CTA = warps 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2), warp 8 TMA producer,
+// warp 9 MMA issuer (+ TMEM allocator), warps 10-13 gather producers (A_GATHER / A_C4 only).
+// Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...; the fp32 accumulator is double-buffered
+// in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.  The epilogue converts 128 x 64
+// (fp16) / 128 x 32 (fp32) sub-tiles into a 128-byte-swizzled staging buffer and hands them to the TMA
+// store unit (coalesced, asynchronous, clipped to the tensor bounds), two buffers in flight.
 #include "vcb_internal.h"
 #include "vcb_ptx.cuh"
 
@@ -33,8 +35,15 @@ constexpr int kBlockK = 64;                       // fp16 elements = 128 bytes =
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kGatherLag = 2;                     // cp.async groups in flight per gather thread
-constexpr int kNumEpilogueThreads = 128;
+constexpr int kNumEpilogueThreads = 256;
+constexpr int kEpilogueWarps = 8;
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kGatherWarp0 = 10;
 constexpr int kGatherThreads = 128;
+constexpr int kStageOutBytes = kBlockM * 128;        // one staged output sub-tile (128 rows x 128 B)
+constexpr int kThreadsTma = (kMmaWarp + 1) * 32;     // 320
+constexpr int kThreadsGather = kThreadsTma + kGatherThreads;   // 448
 
 struct ConvParams {
   // geometry
@@ -49,6 +58,8 @@ struct ConvParams {
   int block_n, n_tiles, m_tiles, num_tiles;
   int num_stages, acc_stages, tmem_cols;
   int act, res_mode, res_pitch, out_fp32;
+  int epi_direct;      // 1: per-thread 16-byte global stores (debug / cross-check); 0: staged TMA store
+  int c4_wide;         // A_C4: 16-byte granules (two taps) instead of 8-byte ones
   const __half* x;
   const float* bias;
   const __half* residual;
@@ -62,31 +73,33 @@ struct RowInfo {     // one output pixel of the current M tile (gather modes)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == VCB_ACT_SILU) return v / (1.0f + __expf(-v));
+  if (act == VCB_ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));   // ex2.approx + rcp.approx: ~1e-6 relative
   if (act == VCB_ACT_RELU) return fmaxf(v, 0.0f);
   return v;
 }
 
+// Shared-memory carve-up (all offsets from a 1024-byte aligned base):
+//   [num_stages x (A tile 16 KiB | B tile block_n*128 B)] [2 x 16 KiB output staging] [barriers] [tmem slot] [row table]
 template <int A_MODE>
-__global__ void __launch_bounds__(A_MODE == A_TMA ? 192 : 320, 1)
+__global__ void __launch_bounds__(A_MODE == A_TMA ? kThreadsTma : kThreadsGather, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const ConvParams p) {
+                 const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
   const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
-  const uint32_t bars = smem_base + (uint32_t)p.num_stages * stage_bytes;   // 8-byte aligned
+  const uint32_t out_stage = smem_base + (uint32_t)p.num_stages * stage_bytes;          // 1024-aligned
+  const uint32_t bars = out_stage + 2u * kStageOutBytes;                                  // 8-byte aligned
   auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(kMaxStages + s); };
   auto tmem_full_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + a); };
   auto tmem_empty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
-  const uint32_t row_table = tmem_slot + 16u;   // 128 x RowInfo (8 B)
   // generic pointers to the same locations (for plain loads/stores)
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + (size_t)p.num_stages * stage_bytes + 8 * (2 * kMaxStages + 4));
-  RowInfo* rows = reinterpret_cast<RowInfo*>(smem_gen + (size_t)p.num_stages * stage_bytes + 8 * (2 * kMaxStages + 4) + 16);
+  uint8_t* tail_gen = smem_gen + (size_t)p.num_stages * stage_bytes + 2 * kStageOutBytes + 8 * (2 * kMaxStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_gen);
+  RowInfo* rows = reinterpret_cast<RowInfo*>(tail_gen + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -103,11 +116,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     fence_mbar_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     if (A_MODE == A_TMA) tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (!p.epi_direct) tma_prefetch_desc(&tmap_out);
   }
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
@@ -116,7 +130,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 4) {
+  if (warp == kProducerWarp) {
     // ======================= TMA producer (one thread) =======================
     if (lane == 0) {
       uint32_t it = 0;
@@ -149,7 +163,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ======================= MMA issuer (one thread) =======================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16((uint32_t)p.block_n);
@@ -178,75 +192,146 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp < 4) {
-    // ======================= epilogue: TMEM -> registers -> global =======================
-    uint32_t tile_iter = 0;
+  } else if (warp < kEpilogueWarps) {
+    // ======================= epilogue: TMEM -> registers -> (smem -> TMA store | global) =======================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const int half = warp >> 2;                  // which half of a sub-tile's columns
+    const int row_in_tile = q * 32 + lane;
+    const int sub_cols = p.out_fp32 ? 32 : 64;   // columns per staged sub-tile (128 bytes per row)
+    const int my_cols = sub_cols >> 1;           // 32 (fp16) or 16 (fp32) columns per thread per sub-tile
+    const int num_sub = (p.block_n + sub_cols - 1) / sub_cols;
+    const bool issuer = threadIdx.x == 0;
+    uint32_t tile_iter = 0, sub_count = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
       const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
       const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
       mbar_wait(tmem_full_bar(acc), acc_ph, p.fault, FAULT_TMEM_FULL_WAIT, (int)acc);
       tcgen05_fence_after();
-      const int row = m_tile * kBlockM + warp * 32 + lane;
+      const int row = m_tile * kBlockM + row_in_tile;
       const bool row_ok = row < p.M;
-      const uint32_t t_row = tmem_base + acc * (uint32_t)p.block_n + ((uint32_t)(warp * 32) << 16);
+      const uint32_t t_row = tmem_base + acc * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
       const size_t out_row = (size_t)row * (size_t)p.out_pitch;
       const size_t res_row = (size_t)row * (size_t)p.res_pitch;
-      for (int col0 = 0; col0 < p.block_n; col0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(t_row + (uint32_t)col0, v);
-        tmem_ld_wait();
-        const int n0 = n_tile * p.block_n + col0;
+      for (int sub = 0; sub < num_sub; ++sub, ++sub_count) {
+        const uint32_t stage_buf = out_stage + (sub_count & 1u) * kStageOutBytes;
+        if (!p.epi_direct) {
+          if (issuer) tma_store_wait_read<1>();            // the store that used this buffer two sub-tiles ago is drained
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
+        const int col_base = sub * sub_cols + half * my_cols;            // first column (within the N tile) of this thread
 #pragma unroll
-        for (int half8 = 0; half8 < 2; ++half8) {
-          const int nn = n0 + half8 * 8;
-          if (!row_ok || nn >= p.cout_store) continue;
-          float f[8];
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nn));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nn + 4));
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[half8 * 8 + i]) + bb[i];
-          if (p.res_mode != VCB_RES_NONE) {
-            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + res_row + nn));
-            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-            float rr[8];
+        for (int g16 = 0; g16 < 2; ++g16) {                               // up to two 16-column groups
+          const int col0 = col_base + g16 * 16;
+          if (g16 * 16 >= my_cols || col0 >= p.block_n) continue;         // warp-uniform
+          uint32_t v[16];
+          tmem_ld_x16(t_row + (uint32_t)col0, v);
+          tmem_ld_wait();
+          const int n0 = n_tile * p.block_n + col0;
+          float f[16];
+          {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float2 t = __half22float2(rh[i]);
-              rr[2 * i] = t.x;
-              rr[2 * i + 1] = t.y;
+              const float4 b4 = __ldg(bp + i);
+              f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
+              f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+              f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+              f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
             }
-            if (p.res_mode == VCB_RES_BEFORE_ACT) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i] + rr[i], p.act);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act) + rr[i];
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
           }
-          if (p.out_fp32) {
-            float* o = reinterpret_cast<float*>(p.out) + out_row + nn;
-            *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
-          } else {
-            __half2 h[4];
+          const bool res_ok = p.res_mode != VCB_RES_NONE && row_ok && n0 < p.cout_store;
+          float rr[16];
+          if (res_ok) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-            __half* o = reinterpret_cast<__half*>(p.out) + out_row + nn;
-            *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+            for (int hh = 0; hh < 2; ++hh) {
+              if (n0 + hh * 8 < p.cout_store) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + res_row + n0 + hh * 8));
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 t = __half22float2(rh[i]);
+                  rr[hh * 8 + 2 * i] = t.x;
+                  rr[hh * 8 + 2 * i + 1] = t.y;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rr[hh * 8 + i] = 0.f;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rr[i] = 0.f;
+          }
+          if (p.res_mode == VCB_RES_BEFORE_ACT) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i] + rr[i], p.act);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.act) + rr[i];
+          }
+          if (p.epi_direct) {
+            if (row_ok) {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int nn = n0 + hh * 8;
+                if (nn >= p.cout_store) continue;
+                if (p.out_fp32) {
+                  float* o = reinterpret_cast<float*>(p.out) + out_row + nn;
+                  *reinterpret_cast<float4*>(o) = make_float4(f[hh * 8 + 0], f[hh * 8 + 1], f[hh * 8 + 2], f[hh * 8 + 3]);
+                  *reinterpret_cast<float4*>(o + 4) = make_float4(f[hh * 8 + 4], f[hh * 8 + 5], f[hh * 8 + 6], f[hh * 8 + 7]);
+                } else {
+                  __half2 h2[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(f[hh * 8 + 2 * i], f[hh * 8 + 2 * i + 1]);
+                  __half* o = reinterpret_cast<__half*>(p.out) + out_row + nn;
+                  *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h2);
+                }
+              }
+            }
+          } else {
+            // staged row = 128 bytes; this thread owns 16-byte chunks [half*4, half*4+4); 128-byte swizzle
+            const uint32_t row_addr = stage_buf + (uint32_t)row_in_tile * 128u;
+            const int sw = row_in_tile & 7;
+            if (p.out_fp32) {            // 16 floats = 4 chunks
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t dst = row_addr + (uint32_t)(((half * 4 + i) ^ sw) << 4);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(f[4 * i]), "f"(f[4 * i + 1]),
+                             "f"(f[4 * i + 2]), "f"(f[4 * i + 3]) : "memory");
+              }
+            } else {                     // 16 halves = 2 chunks per 16-column group
+              uint32_t h2[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                h2[i] = *reinterpret_cast<const uint32_t*>(&t);
+              }
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const uint32_t dst = row_addr + (uint32_t)(((half * 4 + g16 * 2 + i) ^ sw) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(h2[4 * i]), "r"(h2[4 * i + 1]),
+                             "r"(h2[4 * i + 2]), "r"(h2[4 * i + 3]) : "memory");
+              }
+            }
+          }
+        }
+        if (!p.epi_direct) {
+          fence_proxy_async_smem();                         // staged writes -> visible to the TMA (async proxy)
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (issuer) {
+            tma_store_2d(&tmap_out, stage_buf, n_tile * p.block_n + sub * sub_cols, m_tile * kBlockM);
+            tma_store_commit();
           }
         }
       }
       tcgen05_fence_before();
       mbar_arrive(tmem_empty_bar(acc));
     }
+    if (!p.epi_direct && issuer) tma_store_wait_all<0>();
   } else if (A_MODE != A_TMA) {
-    // ======================= gather producers (warps 6-9) =======================
-    const int gtid = threadIdx.x - 192;
+    // ======================= gather producers (warps 10-13) =======================
+    const int gtid = threadIdx.x - kGatherWarp0 * 32;
     uint32_t it = 0;          // K-steps issued by this thread (same sequence in every gather thread)
     uint32_t arrived = 0;     // K-steps already signalled on their full barrier
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -290,6 +375,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             cp_async_16(a_dst + (uint32_t)rr * 128u + (uint32_t)((j ^ (rr & 7)) << 4), src, ok);
           }
           if (++c == p.chunks_per_tap) { c = 0; if (++s == p.kw) { s = 0; ++r; } }
+        } else if (p.c4_wide) {   // A_C4, 16-byte granules: chunk j of the row = taps (2u, 2u+1), u = kit*8 + j
+          const int j = gtid & 7;
+          const int t0 = (kit * 8 + j) * 2;
+          const int tr = t0 / p.kw, ts = t0 - tr * p.kw;      // ts is even (kw even), so both taps share the row
+          const bool t_ok = t0 < p.kh * p.kw;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (gtid >> 3) + 16 * i;
+            const RowInfo ri = rows[rr];
+            const int h = ri.h0 + tr, w = ri.w0 + ts;         // w even and W even: the pixel pair is in or out together
+            const bool ok = t_ok && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+            const __half* src = ok ? p.x + (size_t)(ri.img_base + h * p.W + w) * 4 : p.x;
+            cp_async_16(a_dst + (uint32_t)rr * 128u + (uint32_t)((j ^ (rr & 7)) << 4), src, ok);
+          }
         } else {   // A_C4: 16 taps x 4 channels per K-step, 8-byte granules
           const int u = gtid & 15;
           const int t = kit * 16 + u;
@@ -322,7 +421,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -398,7 +497,10 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
   } else {
     g.n_tiles = (cout16 + 255) / 256;
     g.block_n = ((cout16 + g.n_tiles - 1) / g.n_tiles + 15) / 16 * 16;
+    // with several N tiles every staged 64-column sub-tile must belong to one tile only
+    if (g.n_tiles > 1) g.block_n = (g.block_n + 63) / 64 * 64;
   }
+  if (g.n_tiles > 1 && g.block_n % 64 != 0) return set_error(VCB_ERR_INVALID, "conv: block_n must be a multiple of 64 when cout spans several N tiles");
   g.cout_pad = g.n_tiles * g.block_n;
   g.m_tiles = (g.M + kBlockM - 1) / kBlockM;
   const int cout_store = (d.cout + 7) / 8 * 8;
@@ -411,7 +513,7 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
   while (pow2 < cols) pow2 <<= 1;
   g.tmem_cols = pow2;
   const size_t stage_bytes = (size_t)kATileBytes + (size_t)g.block_n * 128;
-  const size_t fixed = 1024 /*align slack*/ + 8 * (2 * kMaxStages + 4) + 16 + kBlockM * sizeof(RowInfo) + 64;
+  const size_t fixed = 1024 /*align slack*/ + 2 * kStageOutBytes + 8 * (2 * kMaxStages + 4) + 16 + kBlockM * sizeof(RowInfo) + 64;
   int stages = (int)((size_t)(227 * 1024 - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (d.stages != 0) stages = d.stages < stages ? d.stages : stages;
@@ -452,7 +554,8 @@ int conv_pack_weights(const VcbConvDesc& d, const float* w, const float* bias, v
 }
 
 template <int A_MODE>
-static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, const ConvGeom& g, cudaStream_t st) {
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvParams& p, const ConvGeom& g,
+                       cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     const cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<A_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -460,7 +563,7 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvP
     attr_set = true;
   }
   const int grid = p.num_tiles < state().num_sms ? p.num_tiles : state().num_sms;
-  conv_umma_kernel<A_MODE><<<grid, A_MODE == A_TMA ? 192 : 320, g.smem_bytes, st>>>(ta, tb, p);
+  conv_umma_kernel<A_MODE><<<grid, A_MODE == A_TMA ? kThreadsTma : kThreadsGather, g.smem_bytes, st>>>(ta, tb, to, p);
   return check_cuda(cudaGetLastError(), "conv launch");
 }
 
@@ -492,9 +595,23 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   p.residual = reinterpret_cast<const __half*>(residual);
   p.out = y;
   p.fault = state().fault_dev;
+  p.epi_direct = d.reserved[0] == 1 ? 1 : 0;
+  p.c4_wide = (g.a_mode == A_C4 && d.kw % 2 == 0 && d.stride % 2 == 0 && d.pad % 2 == 0 && d.w % 2 == 0 && d.reserved[1] != 1) ? 1 : 0;
 
-  alignas(64) CUtensorMap ta, tb;
+  alignas(64) CUtensorMap ta, tb, to;
   memset(&ta, 0, sizeof(ta));
+  memset(&to, 0, sizeof(to));
+  if (!p.epi_direct) {   // output: [M][cout] slice of an NHWC buffer with row pitch cout_pitch; box = 128 bytes x 128 rows
+    const bool f32 = d.out_dtype == VCB_F32;
+    const cuuint64_t dims[2] = {(cuuint64_t)d.cout, (cuuint64_t)g.M};
+    const cuuint64_t strides[1] = {(cuuint64_t)d.cout_pitch * (f32 ? 4 : 2)};
+    const cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : 64), (cuuint32_t)kBlockM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = state().encode_tiled(&to, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, y, dims,
+                                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed: %d", (int)r);
+  }
   {   // B: [cout_pad][k_pad] fp16, box = 64 (K) x block_n rows, 128-byte swizzle
     const cuuint64_t dims[2] = {(cuuint64_t)g.k_pad, (cuuint64_t)g.cout_pad};
     const cuuint64_t strides[1] = {(cuuint64_t)g.k_pad * 2};
@@ -529,9 +646,9 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
     }
   }
   switch (g.a_mode) {
-    case A_TMA: return launch_conv<A_TMA>(ta, tb, p, g, st);
-    case A_GATHER: return launch_conv<A_GATHER>(ta, tb, p, g, st);
-    default: return launch_conv<A_C4>(ta, tb, p, g, st);
+    case A_TMA: return launch_conv<A_TMA>(ta, tb, to, p, g, st);
+    case A_GATHER: return launch_conv<A_GATHER>(ta, tb, to, p, g, st);
+    default: return launch_conv<A_C4>(ta, tb, to, p, g, st);
   }
 }
 

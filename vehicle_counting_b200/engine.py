@@ -108,14 +108,18 @@ class _Plan:
     def __init__(self, device: torch.device):
         self.device = device
         self.steps: List[Callable[[object], None]] = []
+        self.labels: List[str] = []
+        self.step_flops: List[float] = []
         self.conv_flops = 0.0
         self.num_convs = 0
         self.keep: list = []          # tensors that must outlive the plan (weights, descriptors)
         self.graph: Optional[ops.Graph] = None
         self.stream = torch.cuda.Stream(device=device)
 
-    def add(self, fn: Callable[[object], None]) -> None:
+    def add(self, fn: Callable[[object], None], label: str = "op", flops: float = 0.0) -> None:
         self.steps.append(fn)
+        self.labels.append(label)
+        self.step_flops.append(flops)
 
     def conv(self, x: TRef, n: int, w: torch.Tensor, b: Optional[torch.Tensor], y: TRef, k: int, s: int, p: int, act: int,
              residual: Optional[TRef] = None, res_mode: int = L.RES_NONE, out_dtype: int = L.F16, a_mode: int = L.A_AUTO):
@@ -129,9 +133,11 @@ class _Plan:
         wp, bp = ops.pack_conv_weights(d, w, b)
         xp, yp, rp = x.ptr, y.ptr, (residual.ptr if residual is not None else 0)
         self.keep += [d, wp, bp, x.buf, y.buf] + ([residual.buf] if residual is not None else [])
-        self.conv_flops += 2.0 * n * ho * wo * cout * cin * k * k
+        fl = 2.0 * n * ho * wo * cout * cin * k * k
+        self.conv_flops += fl
         self.num_convs += 1
-        self.add(lambda st, d=d, xp=xp, wp=wp, bp=bp, yp=yp, rp=rp: ops.conv2d(d, xp, wp, bp, yp, residual=rp, stream=st))
+        self.add(lambda st, d=d, xp=xp, wp=wp, bp=bp, yp=yp, rp=rp: ops.conv2d(d, xp, wp, bp, yp, residual=rp, stream=st),
+                 f"conv{k}x{k}s{s} {cin}->{cout} M={n * ho * wo}" + (" +res" if residual is not None else ""), fl)
 
     def run_eager(self, stream=None) -> None:
         st = stream if stream is not None else self.stream
