@@ -62,7 +62,8 @@ typedef struct VcbConvDesc {
   int32_t a_mode;             /* VCB_A_*: how the im2col operand reaches shared memory */
   int32_t block_n;            /* 0 = auto; N tile (multiple of 16, <= 256) */
   int32_t stages;             /* 0 = auto; smem pipeline depth */
-  int32_t reserved[4];        /* [0]=1: debug epilogue with direct global stores; [1]=1: debug 8-byte C4 gather */
+  int32_t reserved[4];        /* [0]=1: debug epilogue with direct global stores; [1]=1: debug 8-byte C4 gather;
+                               * [2]=16/32/64: force the K chunk (swizzle) width of the TMA path */
 } VcbConvDesc;
 
 /* element counts of the packed fp16 weight blob and the padded fp32 bias for this descriptor */
@@ -78,6 +79,9 @@ int vcb_conv_out_hw(const VcbConvDesc* d, int32_t* ho, int32_t* wo);
 /* ---- K2: data-movement / pooling kernels (upstream Upsample, SPPF max-pools, ReID MaxPool2d) --- */
 /* uint8 RGB/BGR HWC frames -> fp16 NHWC4 (4th channel zero), value/255 (AutoShape: x/255) */
 int vcb_frames_to_f16c4(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t stream);
+/* uint8 HWC3 frames -> fp16 space-to-depth NHWC16: out[n][y/2][x/2][(dy*2+dx)*3+c] = in/255, channels 12..15 zero
+ * (h, w even).  Turns the 6x6/s2/p2 YOLOv5 stem into a 3x3/s1/p1 convolution that the im2col TMA can feed. */
+int vcb_frames_to_f16_s2d(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t stream);
 /* nearest x2 upsample of a channel slice into a channel slice (nn.Upsample(None, 2, 'nearest')) */
 int vcb_upsample2x(const void* src, int32_t src_pitch, void* dst, int32_t dst_pitch, int32_t n, int32_t h,
                    int32_t w, int32_t c, vcb_stream_t stream);
@@ -144,9 +148,10 @@ typedef struct VcbRoiDesc {
   int32_t num_rois;
   int32_t out_size;        /* 50 */
   float mean[3], inv_std[3];   /* applied to channel 0,1,2 of the stored frame order */
+  int32_t out_channels;    /* channel pitch of `out`: 4 (default when 0), 8 or 16; channels >= 3 are written as zero */
 } VcbRoiDesc;
 /* frames: uint8 [*][fh][fw][3]; rois: int32 [num_rois][5] = frame, x1, y1, x2, y2 (already int-truncated and
- * clipped, end exclusive); out: fp16 [num_rois][out][out][4] (4th channel zero) */
+ * clipped, end exclusive); out: fp16 [num_rois][out][out][out_channels] */
 int vcb_roi_resize_norm(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, int32_t fw, const int32_t* rois,
                         void* out, vcb_stream_t stream);
 /* float64 xyxy boxes -> the reference's integer crop rectangle (deep_sort.py:78-95), on device.

@@ -24,7 +24,7 @@ CASES = []
 
 def case(name, **kw):
     base = dict(n=1, h=16, w=16, cin=64, cout=64, k=1, s=1, p=0, act="none", res="none", out="f16", mode="tma",
-                cin_pitch=None, cout_pitch=None, block_n=0, stages=0, epi_direct=False, c4_narrow=False)
+                cin_pitch=None, cout_pitch=None, block_n=0, stages=0, epi_direct=False, c4_narrow=False, bk=0)
     base.update(kw)
     CASES.append((name, base))
 
@@ -48,6 +48,13 @@ case("direct-cout255-f32", mode="gather", n=2, h=20, w=20, cin=128, cout=255, co
 case("tma-cout320-2tiles", mode="tma", n=2, h=20, w=20, k=1, cin=64, cout=320, act="silu")
 case("tma-cout16", mode="tma", n=2, h=20, w=20, k=3, p=1, cin=16, cout=16, act="silu")
 case("tma-cout40-f32-res", mode="tma", n=3, h=13, w=13, k=3, p=1, cin=64, cout=40, out="f32", act="relu")
+case("tma-bk16-s2dstem", mode="tma", n=4, h=320, w=320, k=3, p=1, cin=16, cout=48, act="silu")
+case("tma-bk16-reidstem", mode="tma", n=64, h=50, w=50, k=3, p=1, cin=16, cout=64, act="relu")
+case("tma-bk16-cin24", mode="tma", n=2, h=20, w=20, k=3, p=1, cin=24, cout=32, act="silu")
+case("tma-bk32-cin96-s2", mode="tma", n=2, h=40, w=40, k=3, s=2, p=1, cin=96, cout=192, act="silu")
+case("tma-bk64forced-cin96", mode="tma", n=2, h=40, w=40, k=3, p=1, cin=96, cout=192, act="silu", res="after", bk=64)
+case("tma-bk32forced-cin128-1x1", mode="tma", n=2, h=40, w=40, k=1, cin=128, cout=64, act="silu", bk=32)
+case("tma-bk16forced-cin64", mode="tma", n=2, h=20, w=20, k=3, p=1, cin=64, cout=64, act="relu", bk=16)
 case("c4-yolo-stem-narrow", mode="c4", n=2, h=64, w=64, cin=3, cin_pitch=4, cout=32, k=6, s=2, p=2, act="silu", c4_narrow=True)
 case("c4-yolo-stem", mode="c4", n=2, h=64, w=64, cin=3, cin_pitch=4, cout=32, k=6, s=2, p=2, act="silu")
 case("c4-reid-stem", mode="c4", n=5, h=50, w=50, cin=3, cin_pitch=4, cout=64, k=3, s=1, p=1, act="relu")
@@ -81,7 +88,7 @@ def run_case(idx: int) -> dict:
     d = ops.make_conv_desc(n, h, w, cin, cout, k, s, p, cin_pitch=cin_pitch, cout_pitch=cout_pitch, act=act,
                            res_mode=res_mode, res_pitch=cout_pitch if res_mode else 0,
                            out_dtype=L.F32 if c["out"] == "f32" else L.F16, a_mode=mode, block_n=c["block_n"], stages=c["stages"],
-                           epi_direct=c["epi_direct"], c4_narrow=c["c4_narrow"])
+                           epi_direct=c["epi_direct"], c4_narrow=c["c4_narrow"], bk=c["bk"])
     ho, wo = ops.conv_out_hw(d)
     res_full = (torch.randn(n, ho, wo, cout_pitch, generator=g)).half() if res_mode else None
 

@@ -22,6 +22,21 @@ def test_frames_to_f16c4(lib):
         assert (got[..., 3] == 0).all()
 
 
+def test_frames_to_f16_s2d(lib):
+    from vehicle_counting_b200 import ops
+    rng = np.random.default_rng(1)
+    for shape in [(2, 64, 48), (1, 2, 2), (3, 640, 640)]:
+        fr = torch.from_numpy(rng.integers(0, 256, shape + (3,), dtype=np.uint8))
+        n, h, w = shape
+        out = torch.full((n, h // 2, w // 2, 16), 5.0, dtype=torch.float16, device=DEV)
+        ops.frames_to_f16_s2d(fr.to(DEV), out)
+        x = (fr.float() / 255.0).half()                                   # [n, h, w, 3]
+        ref = x.view(n, h // 2, 2, w // 2, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(n, h // 2, w // 2, 12)
+        got = out.cpu()
+        assert torch.equal(got[..., :12], ref)                            # bit-exact
+        assert (got[..., 12:] == 0).all()
+
+
 def test_upsample2x_into_slice(lib):
     from vehicle_counting_b200 import ops
     g = torch.Generator().manual_seed(0)
@@ -231,14 +246,15 @@ def test_roi_resize_norm_matches_oracle(lib):
     ops.boxes_to_rois(torch.from_numpy(boxes).to(DEV), torch.from_numpy(frame_of).to(DEV), len(boxes), fw, fh, rois)
     want = np.array([(f,) + R.crop_box(b, fw, fh) for f, b in zip(frame_of, boxes)], np.int32)
     np.testing.assert_array_equal(rois.cpu().numpy(), want)          # integer crop rule: bit-exact
-    rd = L.RoiDesc()
-    rd.num_rois, rd.out_size = len(boxes), 50
-    for c in range(3):
-        rd.mean[c] = R.NORM_MEAN[c]; rd.inv_std[c] = 1.0 / R.NORM_STD[c]
-    out = torch.zeros(len(boxes), 50, 50, 4, dtype=torch.float16, device=DEV)
-    ops.roi_resize_norm(rd, torch.from_numpy(frames).to(DEV), fh, fw, rois, out)
     crops = [frames[f][y1:y2, x1:x2] for f, x1, y1, x2, y2 in want]
     ref = R.preprocess(crops).permute(0, 2, 3, 1)                   # NHWC fp32
-    got = out.float().cpu()
-    assert (got[..., 3] == 0).all()
-    assert (got[..., :3] - ref).abs().max().item() < 2.5e-3        # fp16 storage of values up to ~2.7
+    for oc in (4, 16):
+        rd = L.RoiDesc()
+        rd.num_rois, rd.out_size, rd.out_channels = len(boxes), 50, oc
+        for c in range(3):
+            rd.mean[c] = R.NORM_MEAN[c]; rd.inv_std[c] = 1.0 / R.NORM_STD[c]
+        out = torch.full((len(boxes), 50, 50, oc), 3.0, dtype=torch.float16, device=DEV)
+        ops.roi_resize_norm(rd, torch.from_numpy(frames).to(DEV), fh, fw, rois, out)
+        got = out.float().cpu()
+        assert (got[..., 3:] == 0).all()
+        assert (got[..., :3] - ref).abs().max().item() < 2.5e-3    # fp16 storage of values up to ~2.7

@@ -64,6 +64,7 @@ class RoiDesc(C.Structure):
     _fields_ = [
         ("num_rois", C.c_int32), ("out_size", C.c_int32),
         ("mean", C.c_float * 3), ("inv_std", C.c_float * 3),
+        ("out_channels", C.c_int32),
     ]
 
 
@@ -82,6 +83,7 @@ _SIGNATURES = {
     "vcb_conv2d_fwd": ([C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP], _I32),
     "vcb_conv_out_hw": ([C.POINTER(ConvDesc), C.POINTER(_I32), C.POINTER(_I32)], _I32),
     "vcb_frames_to_f16c4": ([_VP, _VP, _I32, _I32, _I32, _VP], _I32),
+    "vcb_frames_to_f16_s2d": ([_VP, _VP, _I32, _I32, _I32, _VP], _I32),
     "vcb_upsample2x": ([_VP, _I32, _VP, _I32, _I32, _I32, _I32, _I32, _VP], _I32),
     "vcb_sppf_pool": ([_VP, _I32, _I32, _I32, _I32, _I32, _VP], _I32),
     "vcb_maxpool": ([_VP, _I32, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP], _I32),

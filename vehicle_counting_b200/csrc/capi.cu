@@ -10,6 +10,7 @@ namespace vcb {
 
 // other translation units
 int frames_to_f16c4(const uint8_t*, void*, int, int, int, cudaStream_t);
+int frames_to_f16_s2d(const uint8_t*, void*, int, int, int, cudaStream_t);
 int upsample2x(const void*, int, void*, int, int, int, int, int, cudaStream_t);
 int sppf_pool(void*, int, int, int, int, int, cudaStream_t);
 int maxpool(const void*, int, void*, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -126,6 +127,10 @@ int vcb_conv2d_fwd(const VcbConvDesc* d, const void* x, const void* wp, const fl
 int vcb_frames_to_f16c4(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t st) {
   const int rc = require_init(); if (rc) return rc;
   return frames_to_f16c4(frames, out, n, h, w, (cudaStream_t)st);
+}
+int vcb_frames_to_f16_s2d(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return frames_to_f16_s2d(frames, out, n, h, w, (cudaStream_t)st);
 }
 int vcb_upsample2x(const void* src, int32_t sp, void* dst, int32_t dp, int32_t n, int32_t h, int32_t w, int32_t c, vcb_stream_t st) {
   const int rc = require_init(); if (rc) return rc;

@@ -53,9 +53,13 @@ struct ConvParams {
   int Cout;            // logical output channels
   int cout_store;      // channels actually written (Cout rounded up to 8, <= out_pitch)
   int out_pitch;
-  int chunks_per_tap;  // ceil(Cin / 64)           (A_TMA, A_GATHER)
-  int num_k_iters;
+  int chunks_per_tap;  // ceil(Cin / bk)           (A_TMA, A_GATHER)
+  int num_k_iters;     // pipeline stages consumed per tile = ceil(total_chunks / chunks_per_stage)
+  int bk;              // K elements per chunk: 64 (128B swizzle), 32 (64B), 16 (32B); gather modes use 64
+  int chunks_per_stage;   // 64 / bk: a stage always carries up to 64 K elements
+  int total_chunks;    // taps * chunks_per_tap
   int block_n, n_tiles, m_tiles, num_tiles;
+  int num_pair_tiles;  // cta_group::2 kernel: ceil(m_tiles / 2) * n_tiles
   int num_stages, acc_stages, tmem_cols;
   int act, res_mode, res_pitch, out_fp32;
   int epi_direct;      // 1: per-thread 16-byte global stores (debug / cross-check); 0: staged TMA store
@@ -78,121 +82,20 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// Shared-memory carve-up (all offsets from a 1024-byte aligned base):
-//   [num_stages x (A tile 16 KiB | B tile block_n*128 B)] [2 x 16 KiB output staging] [barriers] [tmem slot] [row table]
-template <int A_MODE>
-__global__ void __launch_bounds__(A_MODE == A_TMA ? kThreadsTma : kThreadsGather, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
-  const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
-  const uint32_t out_stage = smem_base + (uint32_t)p.num_stages * stage_bytes;          // 1024-aligned
-  const uint32_t bars = out_stage + 2u * kStageOutBytes;                                  // 8-byte aligned
-  auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(kMaxStages + s); };
-  auto tmem_full_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + a); };
-  auto tmem_empty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
-  // generic pointers to the same locations (for plain loads/stores)
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint8_t* tail_gen = smem_gen + (size_t)p.num_stages * stage_bytes + 2 * kStageOutBytes + 8 * (2 * kMaxStages + 4);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_gen);
-  RowInfo* rows = reinterpret_cast<RowInfo*>(tail_gen + 16);
-
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue (warps 0-7): TMEM -> registers -> bias/activation/residual -> swizzled smem sub-tiles -> TMA store.
+// kTwoCta: the CTA is one half of a cta_group::2 pair; it drains its own 128 accumulator rows of the 256-row pair
+// tile and releases the accumulator on the LEADER's tmem_empty barrier (remote arrive for the peer CTA).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool kTwoCta>
+__device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtensorMap* tmap_out_ptr, uint32_t tmem_base,
+                                              uint32_t out_stage, uint32_t tmem_full0, uint32_t tmem_empty0, int first_tile,
+                                              int tile_step, int cta_rank) {
+  const CUtensorMap& tmap_out = *tmap_out_ptr;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    const uint32_t full_count = (A_MODE == A_TMA) ? 1u : (1u + kGatherThreads);
-    for (int s = 0; s < p.num_stages; ++s) {
-      mbar_init(full_bar(s), full_count);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), kNumEpilogueThreads);
-    }
-    fence_mbar_init();
-  }
-  if (warp == kProducerWarp && lane == 0) {
-    if (A_MODE == A_TMA) tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-    if (!p.epi_direct) tma_prefetch_desc(&tmap_out);
-  }
-  if (warp == kMmaWarp) {
-    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    tmem_relinquish();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == kProducerWarp) {
-    // ======================= TMA producer (one thread) =======================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-        int cw = 0, ch = 0, cn = 0;
-        if (A_MODE == A_TMA) {
-          const int m0 = m_tile * kBlockM;
-          cn = m0 / p.PQ;
-          const int rem = m0 - cn * p.PQ;
-          const int p0 = rem / p.Q, q0 = rem - p0 * p.Q;
-          cw = q0 * p.stride - p.pad;
-          ch = p0 * p.stride - p.pad;
-        }
-        int r = 0, s = 0, c = 0;
-        for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
-          const int st = it % p.num_stages;
-          const uint32_t ph = (it / p.num_stages) & 1u;
-          mbar_wait(empty_bar(st), ph ^ 1u, p.fault, FAULT_EMPTY_WAIT, st);
-          const uint32_t a_dst = smem_base + (uint32_t)st * stage_bytes;
-          const uint32_t b_dst = a_dst + kATileBytes;
-          if (A_MODE == A_TMA) {
-            mbar_arrive_expect_tx(full_bar(st), kATileBytes + b_tile_bytes);
-            tma_load_im2col_4d(&tmap_a, full_bar(st), a_dst, c * kBlockK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
-            if (++c == p.chunks_per_tap) { c = 0; if (++s == p.kw) { s = 0; ++r; } }
-          } else {
-            mbar_arrive_expect_tx(full_bar(st), b_tile_bytes);
-          }
-          tma_load_2d(&tmap_b, full_bar(st), b_dst, kit * kBlockK, n_tile * p.block_n);
-        }
-      }
-    }
-  } else if (warp == kMmaWarp) {
-    // ======================= MMA issuer (one thread) =======================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16((uint32_t)p.block_n);
-      uint32_t it = 0, tile_iter = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
-        const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
-        const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
-        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u, p.fault, FAULT_TMEM_EMPTY_WAIT, (int)acc);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.block_n;
-        for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
-          const int st = it % p.num_stages;
-          const uint32_t ph = (it / p.num_stages) & 1u;
-          mbar_wait(full_bar(st), ph, p.fault, FAULT_FULL_WAIT, st);
-          tcgen05_fence_after();
-          const uint32_t a_addr = smem_base + (uint32_t)st * stage_bytes;
-          const uint64_t a_desc = umma_desc_sw128(a_addr);
-          const uint64_t b_desc = umma_desc_sw128(a_addr + kATileBytes);
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // +32 bytes per UMMA_K step inside the swizzle row: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kit | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(empty_bar(st));
-          if (kit == p.num_k_iters - 1) umma_commit(tmem_full_bar(acc));
-        }
-      }
-    }
-  } else if (warp < kEpilogueWarps) {
+  auto tmem_full_bar = [&](int a) { return tmem_full0 + 8u * (uint32_t)a; };
+  auto tmem_empty_bar = [&](int a) { return tmem_empty0 + 8u * (uint32_t)a; };
     // ======================= epilogue: TMEM -> registers -> (smem -> TMA store | global) =======================
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int half = warp >> 2;                  // which half of a sub-tile's columns
@@ -202,8 +105,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int num_sub = (p.block_n + sub_cols - 1) / sub_cols;
     const bool issuer = threadIdx.x == 0;
     uint32_t tile_iter = 0, sub_count = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+    for (int tile = first_tile; tile < (kTwoCta ? p.num_pair_tiles : p.num_tiles); tile += tile_step, ++tile_iter) {
+      const int m_tile = kTwoCta ? 2 * (tile / p.n_tiles) + cta_rank : tile / p.n_tiles;
+      const int n_tile = tile % p.n_tiles;
       const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
       const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
       mbar_wait(tmem_full_bar(acc), acc_ph, p.fault, FAULT_TMEM_FULL_WAIT, (int)acc);
@@ -326,9 +230,149 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
       tcgen05_fence_before();
-      mbar_arrive(tmem_empty_bar(acc));
+      if (kTwoCta && cta_rank != 0) mbar_arrive_remote(tmem_empty_bar(acc), 0);
+      else mbar_arrive(tmem_empty_bar(acc));
     }
     if (!p.epi_direct && issuer) tma_store_wait_all<0>();
+}
+
+// Shared-memory carve-up (all offsets from a 1024-byte aligned base):
+//   [num_stages x (A tile 16 KiB | B tile block_n*128 B)] [2 x 16 KiB output staging] [barriers] [tmem slot] [row table]
+template <int A_MODE, int BK>
+__global__ void __launch_bounds__(A_MODE == A_TMA ? kThreadsTma : kThreadsGather, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
+  const uint32_t out_stage = smem_base + (uint32_t)p.num_stages * stage_bytes;          // 1024-aligned
+  const uint32_t bars = out_stage + 2u * kStageOutBytes;                                  // 8-byte aligned
+  auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(kMaxStages + s); };
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
+  // generic pointers to the same locations (for plain loads/stores)
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* tail_gen = smem_gen + (size_t)p.num_stages * stage_bytes + 2 * kStageOutBytes + 8 * (2 * kMaxStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_gen);
+  RowInfo* rows = reinterpret_cast<RowInfo*>(tail_gen + 16);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    const uint32_t full_count = (A_MODE == A_TMA) ? 1u : (1u + kGatherThreads);
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(full_bar(s), full_count);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), kNumEpilogueThreads);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kProducerWarp && lane == 0) {
+    if (A_MODE == A_TMA) tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    if (!p.epi_direct) tma_prefetch_desc(&tmap_out);
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == kProducerWarp) {
+    // ======================= TMA producer (one thread) =======================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        int cw = 0, ch = 0, cn = 0;
+        if (A_MODE == A_TMA) {
+          const int m0 = m_tile * kBlockM;
+          cn = m0 / p.PQ;
+          const int rem = m0 - cn * p.PQ;
+          const int p0 = rem / p.Q, q0 = rem - p0 * p.Q;
+          cw = q0 * p.stride - p.pad;
+          ch = p0 * p.stride - p.pad;
+        }
+        int r = 0, s = 0, c = 0, kidx = 0;
+        constexpr uint32_t a_chunk = (uint32_t)(kBlockM * BK * 2);
+        const uint32_t b_chunk = (uint32_t)(p.block_n * BK * 2);
+        constexpr int G = kBlockK / BK;
+        for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
+          const int st = it % p.num_stages;
+          const uint32_t ph = (it / p.num_stages) & 1u;
+          mbar_wait(empty_bar(st), ph ^ 1u, p.fault, FAULT_EMPTY_WAIT, st);
+          const uint32_t a_dst = smem_base + (uint32_t)st * stage_bytes;
+          const uint32_t b_dst = a_dst + kATileBytes;
+          const int nch = (G == 1) ? 1 : min(G, p.total_chunks - kit * G);
+          if (A_MODE == A_TMA) {
+            mbar_arrive_expect_tx(full_bar(st), (uint32_t)nch * (a_chunk + b_chunk));
+            for (int g = 0; g < nch; ++g, ++kidx) {
+              tma_load_im2col_4d(&tmap_a, full_bar(st), a_dst + (uint32_t)g * a_chunk, c * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+              tma_load_2d(&tmap_b, full_bar(st), b_dst + (uint32_t)g * b_chunk, kidx * BK, n_tile * p.block_n);
+              if (++c == p.chunks_per_tap) { c = 0; if (++s == p.kw) { s = 0; ++r; } }
+            }
+          } else {
+            mbar_arrive_expect_tx(full_bar(st), b_tile_bytes);
+            tma_load_2d(&tmap_b, full_bar(st), b_dst, kit * kBlockK, n_tile * p.block_n);
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ======================= MMA issuer (one thread) =======================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16((uint32_t)p.block_n);
+      constexpr uint32_t a_chunk = (uint32_t)(kBlockM * BK * 2);
+      const uint32_t b_chunk = (uint32_t)(p.block_n * BK * 2);
+      constexpr uint32_t sbo = (uint32_t)(8 * BK * 2);                               // 8 rows of one swizzle row each
+      constexpr uint32_t layout_type = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);       // SWIZZLE_128B / 64B / 32B
+      constexpr int ksteps = BK / 16;
+      constexpr int G = kBlockK / BK;                                                // chunks per stage
+      // descriptor high words are loop invariants; only the 14-bit start-address field changes
+      const uint64_t desc_hi = umma_desc_kmajor(0, sbo, layout_type);
+      uint32_t it = 0, tile_iter = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
+        const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
+        const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
+        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u, p.fault, FAULT_TMEM_EMPTY_WAIT, (int)acc);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.block_n;
+        for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
+          const int st = it % p.num_stages;
+          const uint32_t ph = (it / p.num_stages) & 1u;
+          mbar_wait(full_bar(st), ph, p.fault, FAULT_FULL_WAIT, st);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base + (uint32_t)st * stage_bytes;
+          const int nch = (G == 1) ? 1 : min(G, p.total_chunks - kit * G);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (g < nch) {
+              const uint64_t a_desc = desc_hi | (uint64_t)(((a_addr + (uint32_t)g * a_chunk) & 0x3FFFF) >> 4);
+              const uint64_t b_desc = desc_hi | (uint64_t)(((a_addr + kATileBytes + (uint32_t)g * b_chunk) & 0x3FFFF) >> 4);
+#pragma unroll
+              for (int k = 0; k < ksteps; ++k) {
+                // +32 bytes per UMMA_K step inside the swizzle row: +2 in the (addr >> 4) field
+                umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kit | g | k) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(empty_bar(st));
+          if (kit == p.num_k_iters - 1) umma_commit(tmem_full_bar(acc));
+        }
+      }
+    }
+  } else if (warp < kEpilogueWarps) {
+    conv_epilogue<false>(p, &tmap_out, tmem_base, out_stage, tmem_full_bar(0), tmem_empty_bar(0), blockIdx.x, gridDim.x, 0);
   } else if (A_MODE != A_TMA) {
     // ======================= gather producers (warps 10-13) =======================
     const int gtid = threadIdx.x - kGatherWarp0 * 32;
@@ -454,6 +498,7 @@ struct ConvGeom {
   int a_mode;   // A_TMA / A_GATHER / A_C4
   int P, Q, M;
   int cin_pad, k_pad, num_k_iters, chunks_per_tap;
+  int bk, chunks_per_stage, total_chunks;
   int block_n, n_tiles, cout_pad, m_tiles;
   int stages, acc_stages, tmem_cols;
   size_t smem_bytes;
@@ -474,21 +519,30 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
   if (mode == VCB_A_C4) {
     if (d.cin_pitch != 4 || d.cin > 4) return set_error(VCB_ERR_INVALID, "conv: A_C4 needs cin<=4 and cin_pitch==4");
     g.a_mode = A_C4;
+    g.bk = kBlockK;
     g.cin_pad = 4;
     g.chunks_per_tap = 0;
-    g.num_k_iters = (d.kh * d.kw + 15) / 16;
+    g.total_chunks = (d.kh * d.kw + 15) / 16;          // 16 taps x 4 channels per K-step
   } else {
     if (d.cin % 8 != 0 || d.cin_pitch % 8 != 0 || d.cin_pitch < d.cin)
       return set_error(VCB_ERR_INVALID, "conv: cin and cin_pitch must be multiples of 8 (cin_pitch >= cin)");
     g.a_mode = (mode == VCB_A_GATHER) ? A_GATHER : A_TMA;
-    g.chunks_per_tap = (d.cin + kBlockK - 1) / kBlockK;
-    g.cin_pad = g.chunks_per_tap * kBlockK;
-    g.num_k_iters = d.kh * d.kw * g.chunks_per_tap;
+    // K chunk = one TMA box of bk channels of one tap; the widest swizzle that divides cin avoids zero K padding
+    g.bk = kBlockK;
+    if (g.a_mode == A_TMA) {
+      if (d.reserved[2] == 16 || d.reserved[2] == 32 || d.reserved[2] == 64) g.bk = d.reserved[2];
+      else g.bk = (d.cin % 64 == 0) ? 64 : ((d.cin % 32 == 0) ? 32 : (d.cin <= 16 ? 16 : 64));   // measured: 16-wide chunks only pay for stems
+    }
+    g.chunks_per_tap = (d.cin + g.bk - 1) / g.bk;
+    g.cin_pad = g.chunks_per_tap * g.bk;
+    g.total_chunks = d.kh * d.kw * g.chunks_per_tap;
     if (g.a_mode == A_TMA && (d.pad > 127 || d.kh > 128 || d.kw > 128 || d.stride > 8))
       return set_error(VCB_ERR_INVALID, "conv: geometry outside the im2col TMA limits");
   }
+  g.chunks_per_stage = kBlockK / g.bk;
+  g.num_k_iters = (g.total_chunks + g.chunks_per_stage - 1) / g.chunks_per_stage;
   if (d.h > 16000 || d.w > 16000) return set_error(VCB_ERR_INVALID, "conv: image too large");
-  g.k_pad = g.num_k_iters * kBlockK;
+  g.k_pad = g.total_chunks * g.bk;
   const int cout16 = (d.cout + 15) / 16 * 16;
   if (d.block_n != 0) {
     if (d.block_n % 16 != 0 || d.block_n < 16 || d.block_n > 256) return set_error(VCB_ERR_INVALID, "conv: bad block_n");
@@ -553,17 +607,17 @@ int conv_pack_weights(const VcbConvDesc& d, const float* w, const float* bias, v
   return check_cuda(cudaGetLastError(), "pack_weights launch");
 }
 
-template <int A_MODE>
+template <int A_MODE, int BK>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvParams& p, const ConvGeom& g,
                        cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<A_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<A_MODE, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv)");
     attr_set = true;
   }
   const int grid = p.num_tiles < state().num_sms ? p.num_tiles : state().num_sms;
-  conv_umma_kernel<A_MODE><<<grid, A_MODE == A_TMA ? kThreadsTma : kThreadsGather, g.smem_bytes, st>>>(ta, tb, to, p);
+  conv_umma_kernel<A_MODE, BK><<<grid, A_MODE == A_TMA ? kThreadsTma : kThreadsGather, g.smem_bytes, st>>>(ta, tb, to, p);
   return check_cuda(cudaGetLastError(), "conv launch");
 }
 
@@ -587,6 +641,7 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   p.kh = d.kh; p.kw = d.kw; p.stride = d.stride; p.pad = d.pad;
   p.Cout = d.cout; p.cout_store = (d.cout + 7) / 8 * 8; p.out_pitch = d.cout_pitch;
   p.chunks_per_tap = g.chunks_per_tap; p.num_k_iters = g.num_k_iters;
+  p.bk = g.bk; p.chunks_per_stage = g.chunks_per_stage; p.total_chunks = g.total_chunks;
   p.block_n = g.block_n; p.n_tiles = g.n_tiles; p.m_tiles = g.m_tiles; p.num_tiles = g.m_tiles * g.n_tiles;
   p.num_stages = g.stages; p.acc_stages = g.acc_stages; p.tmem_cols = g.tmem_cols;
   p.act = d.act; p.res_mode = d.res_mode; p.res_pitch = d.res_pitch; p.out_fp32 = d.out_dtype == VCB_F32 ? 1 : 0;
@@ -598,6 +653,7 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   p.epi_direct = d.reserved[0] == 1 ? 1 : 0;
   p.c4_wide = (g.a_mode == A_C4 && d.kw % 2 == 0 && d.stride % 2 == 0 && d.pad % 2 == 0 && d.w % 2 == 0 && d.reserved[1] != 1) ? 1 : 0;
 
+  const CUtensorMapSwizzle swz = g.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (g.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   alignas(64) CUtensorMap ta, tb, to;
   memset(&ta, 0, sizeof(ta));
   memset(&to, 0, sizeof(to));
@@ -615,10 +671,10 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   {   // B: [cout_pad][k_pad] fp16, box = 64 (K) x block_n rows, 128-byte swizzle
     const cuuint64_t dims[2] = {(cuuint64_t)g.k_pad, (cuuint64_t)g.cout_pad};
     const cuuint64_t strides[1] = {(cuuint64_t)g.k_pad * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)g.block_n};
+    const cuuint32_t box[2] = {(cuuint32_t)g.bk, (cuuint32_t)g.block_n};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = state().encode_tiled(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_packed), dims, strides,
-                                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   }
@@ -633,8 +689,8 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
     const int upper[2] = {d.pad - (d.kw - 1), d.pad - (d.kh - 1)};
     const cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
     const CUresult r = state().encode_im2col(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
-                                             upper, (cuuint32_t)kBlockK, (cuuint32_t)kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                             upper, (cuuint32_t)g.bk, (cuuint32_t)kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                             swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeIm2col failed: %d", (int)r);
     // Driver quirk for small tensors in im2col mode (same adjustment CUTLASS applies, see
@@ -646,9 +702,12 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
     }
   }
   switch (g.a_mode) {
-    case A_TMA: return launch_conv<A_TMA>(ta, tb, to, p, g, st);
-    case A_GATHER: return launch_conv<A_GATHER>(ta, tb, to, p, g, st);
-    default: return launch_conv<A_C4>(ta, tb, to, p, g, st);
+    case A_TMA:
+      if (g.bk == 64) return launch_conv<A_TMA, 64>(ta, tb, to, p, g, st);
+      if (g.bk == 32) return launch_conv<A_TMA, 32>(ta, tb, to, p, g, st);
+      return launch_conv<A_TMA, 16>(ta, tb, to, p, g, st);
+    case A_GATHER: return launch_conv<A_GATHER, 64>(ta, tb, to, p, g, st);
+    default: return launch_conv<A_C4, 64>(ta, tb, to, p, g, st);
   }
 }
 

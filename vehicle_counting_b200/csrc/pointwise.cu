@@ -55,6 +55,42 @@ int frames_to_f16c4(const uint8_t* frames, void* out, int n, int h, int w, cudaS
   return check_cuda(cudaGetLastError(), "frames_to_f16c4 launch");
 }
 
+// ---------------------------------------------------------------- frames (uint8 HWC3) -> fp16 space-to-depth NHWC16
+// out[n][y/2][x/2][(dy*2+dx)*3 + c] = in[n][y][x][c] / 255, channels 12..15 zero.  With this layout the 6x6/s2/p2 stem
+// of YOLOv5 v6.0 is exactly a 3x3/s1/p1 convolution over 12 (+4 zero) channels: w'[a][b][(dy,dx,c)] = w[2a+dy][2b+dx][c].
+__global__ void frames_to_f16_s2d_kernel(const uint8_t* __restrict__ in, uint4* __restrict__ out, int n, int h, int w) {
+  const int h2 = h >> 1, w2 = w >> 1;
+  const long long total = (long long)n * h2 * w2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x2 = (int)(i % w2);
+    long long t = i / w2;
+    const int y2 = (int)(t % h2);
+    const int b = (int)(t / h2);
+    const uint8_t* r0 = in + (((long long)b * h + 2 * y2) * w + 2 * x2) * 3;   // two pixels = 6 contiguous bytes per row
+    const uint8_t* r1 = r0 + (long long)w * 3;
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      v[k] = (float)__ldg(r0 + k) / 255.0f;       // (dy=0, dx=0..1, c)
+      v[6 + k] = (float)__ldg(r1 + k) / 255.0f;   // (dy=1, dx=0..1, c)
+    }
+    v[12] = v[13] = v[14] = v[15] = 0.0f;
+    __half2 hv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hv[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+    out[i * 2] = *reinterpret_cast<const uint4*>(hv);
+    out[i * 2 + 1] = *reinterpret_cast<const uint4*>(hv + 4);
+  }
+}
+
+int frames_to_f16_s2d(const uint8_t* frames, void* out, int n, int h, int w, cudaStream_t st) {
+  if (!frames || !out || n <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1) || ((uintptr_t)out & 15))
+    return set_error(VCB_ERR_INVALID, "frames_to_f16_s2d: bad argument (h, w must be even, out 16-byte aligned)");
+  const long long total = (long long)n * (h / 2) * (w / 2);
+  frames_to_f16_s2d_kernel<<<grid_for(total, 256), 256, 0, st>>>(frames, reinterpret_cast<uint4*>(out), n, h, w);
+  return check_cuda(cudaGetLastError(), "frames_to_f16_s2d launch");
+}
+
 // ---------------------------------------------------------------- nearest x2 upsample into a channel slice
 __global__ void upsample2x_kernel(const uint4* __restrict__ src, int src_pitch8, uint4* __restrict__ dst, int dst_pitch8, int n,
                                   int h, int w, int c8) {

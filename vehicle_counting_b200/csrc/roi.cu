@@ -13,15 +13,17 @@
 
 namespace vcb {
 
+template <int OC>   // output channel pitch: 4, 8 or 16 halves per pixel (channels >= 3 are zero)
 __global__ void roi_resize_norm_kernel(const VcbRoiDesc d, const uint8_t* __restrict__ frames, int fh, int fw,
                                        const int* __restrict__ rois, uint2* __restrict__ out) {
+  constexpr int U = OC / 4;   // uint2 words per pixel
   const int r = blockIdx.x;
   const int f = rois[r * 5 + 0], x1 = rois[r * 5 + 1], y1 = rois[r * 5 + 2], x2 = rois[r * 5 + 3], y2 = rois[r * 5 + 4];
   const int cw = x2 - x1, chh = y2 - y1;
   const int S = d.out_size;
-  uint2* o = out + (long long)r * S * S;
+  uint2* o = out + (long long)r * S * S * U;
   if (cw <= 0 || chh <= 0 || x1 < 0 || y1 < 0 || x2 > fw || y2 > fh) {   // the reference would raise inside cv2.resize
-    for (int i = threadIdx.x; i < S * S; i += blockDim.x) o[i] = make_uint2(0u, 0u);
+    for (int i = threadIdx.x; i < S * S * U; i += blockDim.x) o[i] = make_uint2(0u, 0u);
     return;
   }
   const uint8_t* img = frames + (long long)f * fh * fw * 3;
@@ -55,7 +57,9 @@ __global__ void roi_resize_norm_kernel(const VcbRoiDesc d, const uint8_t* __rest
     uint2 w;
     w.x = *reinterpret_cast<const uint32_t*>(&lo);
     w.y = *reinterpret_cast<const uint32_t*>(&hi);
-    o[i] = w;
+    o[(long long)i * U] = w;
+#pragma unroll
+    for (int u = 1; u < U; ++u) o[(long long)i * U + u] = make_uint2(0u, 0u);
   }
 }
 
@@ -63,7 +67,11 @@ int roi_resize_norm(const VcbRoiDesc& d, const uint8_t* frames, int fh, int fw, 
   if (d.num_rois < 0 || d.out_size <= 0 || !frames || !rois || !out || fh <= 0 || fw <= 0 || ((uintptr_t)out & 7))
     return set_error(VCB_ERR_INVALID, "roi_resize_norm: bad argument");
   if (d.num_rois == 0) return VCB_OK;
-  roi_resize_norm_kernel<<<d.num_rois, 256, 0, st>>>(d, frames, fh, fw, rois, reinterpret_cast<uint2*>(out));
+  const int oc = d.out_channels == 0 ? 4 : d.out_channels;
+  if (oc == 4) roi_resize_norm_kernel<4><<<d.num_rois, 256, 0, st>>>(d, frames, fh, fw, rois, reinterpret_cast<uint2*>(out));
+  else if (oc == 8) roi_resize_norm_kernel<8><<<d.num_rois, 256, 0, st>>>(d, frames, fh, fw, rois, reinterpret_cast<uint2*>(out));
+  else if (oc == 16) roi_resize_norm_kernel<16><<<d.num_rois, 256, 0, st>>>(d, frames, fh, fw, rois, reinterpret_cast<uint2*>(out));
+  else return set_error(VCB_ERR_INVALID, "roi_resize_norm: out_channels must be 4, 8 or 16");
   return check_cuda(cudaGetLastError(), "roi_resize_norm launch");
 }
 

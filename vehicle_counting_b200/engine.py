@@ -75,6 +75,17 @@ def fold_conv_bn(sd, prefix: str, eps: float, device) -> Tuple[torch.Tensor, tor
     return w, bias
 
 
+def stem_weights_to_s2d(w: torch.Tensor) -> torch.Tensor:
+    """[cout, 3, 6, 6] stride-2 stem -> the equivalent [cout, 16, 3, 3] stride-1 kernel over the space-to-depth input:
+    w'[o, (dy*2+dx)*3 + c, a, b] = w[o, c, 2a+dy, 2b+dx]; channels 12..15 are zero."""
+    co = w.shape[0]
+    w6 = w.view(co, 3, 3, 2, 3, 2)                      # [o, c, a, dy, b, dx]
+    w2 = w6.permute(0, 3, 5, 1, 2, 4).reshape(co, 12, 3, 3)   # [o, (dy, dx, c), a, b]
+    out = torch.zeros(co, 16, 3, 3, dtype=w.dtype, device=w.device)
+    out[:, :12] = w2
+    return out
+
+
 @dataclass
 class TRef:
     """A channel slice of an NHWC fp16 buffer."""
@@ -122,7 +133,9 @@ class _Plan:
         self.step_flops.append(flops)
 
     def conv(self, x: TRef, n: int, w: torch.Tensor, b: Optional[torch.Tensor], y: TRef, k: int, s: int, p: int, act: int,
-             residual: Optional[TRef] = None, res_mode: int = L.RES_NONE, out_dtype: int = L.F16, a_mode: int = L.A_AUTO):
+             residual: Optional[TRef] = None, res_mode: int = L.RES_NONE, out_dtype: int = L.F16, a_mode: int = L.A_AUTO,
+             flops: Optional[float] = None):
+        """`flops`: algorithmic FLOPs of the layer when the launched geometry is a re-expression of it (stems)."""
         cout, cin = int(w.shape[0]), int(w.shape[1])
         d = ops.make_conv_desc(n, x.h, x.w, cin, cout, k, s, p, cin_pitch=x.pitch, cout_pitch=y.pitch, act=act,
                                res_mode=res_mode if residual is not None else L.RES_NONE,
@@ -130,10 +143,11 @@ class _Plan:
         ho, wo = ops.conv_out_hw(d)
         assert (ho, wo) == (y.h, y.w), ((ho, wo), (y.h, y.w))
         assert x.c == cin or (cin <= 4 and x.pitch == 4), (x.c, cin)
+
         wp, bp = ops.pack_conv_weights(d, w, b)
         xp, yp, rp = x.ptr, y.ptr, (residual.ptr if residual is not None else 0)
         self.keep += [d, wp, bp, x.buf, y.buf] + ([residual.buf] if residual is not None else [])
-        fl = 2.0 * n * ho * wo * cout * cin * k * k
+        fl = 2.0 * n * ho * wo * cout * cin * k * k if flops is None else flops
         self.conv_flops += fl
         self.num_convs += 1
         self.add(lambda st, d=d, xp=xp, wp=wp, bp=bp, yp=yp, rp=rp: ops.conv2d(d, xp, wp, bp, yp, residual=rp, stream=st),
@@ -240,12 +254,14 @@ class YoloEngine:
         self.layer_out = home
 
         # 3. input ingest
+        # uint8 frames -> fp16 space-to-depth NHWC16 (12 used): the 6x6/s2/p2 stem becomes a 3x3/s1/p1 conv over 16
+        # channels that the im2col TMA feeds like any other layer (csrc/pointwise.cu frames_to_f16_s2d_kernel)
         self.frames = torch.zeros(B, self.h, self.w, 3, dtype=torch.uint8, device=dev)
-        self.x_c4 = torch.zeros(B, self.h, self.w, 4, dtype=torch.float16, device=dev)
-        plan.add(lambda st: ops.frames_to_f16c4(self.frames, self.x_c4, stream=st))
+        self.x_s2d = torch.zeros(B, self.h // 2, self.w // 2, 16, dtype=torch.float16, device=dev)
+        plan.add(lambda st: ops.frames_to_f16_s2d(self.frames, self.x_s2d, stream=st), "ingest u8->f16 s2d")
 
         def src_of(i, f) -> TRef:
-            return TRef(self.x_c4, 0, 3) if (i == 0 and f == -1) else home[i - 1 if f == -1 else f]
+            return TRef(self.x_s2d, 0, 16) if (i == 0 and f == -1) else home[i - 1 if f == -1 else f]
 
         SILU = L.ACT_SILU
         for i, (f, n, kind, args) in enumerate(LAYERS_V6):
@@ -253,8 +269,13 @@ class YoloEngine:
             if kind == "Conv":
                 k, s, p = args[1], args[2], args[3]
                 w_, b_ = fold_conv_bn(sd, pre, YOLO_BN_EPS, dev)
-                plan.conv(src_of(i, f), B, w_, b_, home[i], k, s, p, SILU,
-                          a_mode=L.A_C4 if i == 0 else self.a_mode)
+                if i == 0:
+                    assert (k, s, p) == (6, 2, 2) and w_.shape[1] == 3
+                    w_, k, s, p = stem_weights_to_s2d(w_), 3, 1, 1
+                    stem_flops = 2.0 * B * hw[0][0] * hw[0][1] * w_.shape[0] * 3 * 36      # the 6x6 conv's own count
+                    plan.conv(src_of(i, f), B, w_, b_, home[i], k, s, p, SILU, a_mode=self.a_mode, flops=stem_flops)
+                    continue
+                plan.conv(src_of(i, f), B, w_, b_, home[i], k, s, p, SILU, a_mode=self.a_mode)
             elif kind == "C3":
                 x = src_of(i, f)
                 c2, shortcut = ch[i], args[1]
@@ -288,13 +309,13 @@ class YoloEngine:
                 cat = self._buf(hh, ww, 4 * c_)
                 w_, b_ = fold_conv_bn(sd, pre + ".cv1", YOLO_BN_EPS, dev)
                 plan.conv(x, B, w_, b_, TRef(cat, 0, c_), 1, 1, 0, SILU, a_mode=self.a_mode)
-                plan.add(lambda st, cat=cat, c_=c_, hh=hh, ww=ww: ops.sppf_pool(cat, 4 * c_, B, hh, ww, c_, stream=st))
+                plan.add(lambda st, cat=cat, c_=c_, hh=hh, ww=ww: ops.sppf_pool(cat, 4 * c_, B, hh, ww, c_, stream=st), "sppf 3x maxpool5")
                 w_, b_ = fold_conv_bn(sd, pre + ".cv2", YOLO_BN_EPS, dev)
                 plan.conv(TRef(cat, 0, 4 * c_), B, w_, b_, home[i], 1, 1, 0, SILU, a_mode=self.a_mode)
             elif kind == "Up":
                 x = src_of(i, f)
                 y = home[i]
-                plan.add(lambda st, x=x, y=y: ops.upsample2x(x.ptr, x.pitch, y.ptr, y.pitch, B, x.h, x.w, x.c, stream=st))
+                plan.add(lambda st, x=x, y=y: ops.upsample2x(x.ptr, x.pitch, y.ptr, y.pitch, B, x.h, x.w, x.c, stream=st), "upsample2x")
             elif kind == "Cat":
                 pass                                   # producers already wrote their slices
             elif kind == "Detect":
@@ -344,9 +365,9 @@ class YoloEngine:
         nd.gain, nd.pad_x, nd.pad_y, nd.w0, nd.h0 = (self.scale[i].data_ptr() for i in range(5))
         self._dd, self._nd = dd, nd
         plan.add(lambda st: ops.detect_decode(dd, self.cand_box, self.cand_score, self.cand_cls, self.cand_index,
-                                              self.cand_count, stream=st))
+                                              self.cand_count, stream=st), "detect decode")
         plan.add(lambda st: ops.nms(nd, self.cand_box, self.cand_score, self.cand_cls, self.cand_index, self.cand_count,
-                                    self.nms_ws, self.det, self.det_count, stream=st))
+                                    self.nms_ws, self.det, self.det_count, stream=st), "nms")
         # pinned host mirrors of the result
         self.det_host = torch.zeros(B, self.max_det, 6, dtype=torch.float32).pin_memory()
         self.det_count_host = torch.zeros(B, dtype=torch.int32).pin_memory()
@@ -411,6 +432,12 @@ def _fold_plain(w, bias, bn, eps, device):
     return w * s.view(-1, 1, 1, 1), (b0 - m) * s + b
 
 
+def _pad_cin(w: torch.Tensor, cin: int) -> torch.Tensor:
+    out = torch.zeros(w.shape[0], cin, w.shape[2], w.shape[3], dtype=w.dtype, device=w.device)
+    out[:, :w.shape[1]] = w
+    return out
+
+
 class ReidEngine:
     """DeepSORT appearance CNN over up to `capacity` crops per call.
 
@@ -457,18 +484,19 @@ class ReidEngine:
             return torch.zeros(nb, h, h, c, dtype=dtype, device=dev)
 
         rd = L.RoiDesc()
-        rd.num_rois, rd.out_size = nb, REID_SIZE
+        rd.num_rois, rd.out_size, rd.out_channels = nb, REID_SIZE, 16
         for c in range(3):
             rd.mean[c] = REID_MEAN[c]; rd.inv_std[c] = 1.0 / REID_STD[c]
-        x0 = buf(REID_SIZE, 4)
+        x0 = buf(REID_SIZE, 16)          # 3 real + 13 zero channels: one 32-byte TMA box per tap (bk = 16)
         plan.keep += [rd, frames]
-        plan.add(lambda st: ops.roi_resize_norm(rd, frames, fh, fw, self.rois, x0, stream=st))
+        plan.add(lambda st: ops.roi_resize_norm(rd, frames, fh, fw, self.rois, x0, stream=st), "roi crop+resize+norm")
         RELU = L.ACT_RELU
         w_, b_ = _fold_plain(sd["conv.0.weight"], sd["conv.0.bias"], self._bn("conv.1"), REID_BN_EPS, dev)
         s0 = buf(50, 64)
-        plan.conv(TRef(x0, 0, 3), nb, w_, b_, TRef(s0, 0, 64), 3, 1, 1, RELU, a_mode=L.A_C4)
+        plan.conv(TRef(x0, 0, 16), nb, _pad_cin(w_, 16), b_, TRef(s0, 0, 64), 3, 1, 1, RELU, a_mode=self.a_mode,
+                  flops=2.0 * nb * 2500 * 64 * 27)
         cur = TRef(buf(25, 64), 0, 64)
-        plan.add(lambda st, s0=s0, cur=cur: ops.maxpool(s0, 64, cur.buf, 64, nb, 50, 50, 64, 3, 2, 1, stream=st))
+        plan.add(lambda st, s0=s0, cur=cur: ops.maxpool(s0, 64, cur.buf, 64, nb, 50, 50, 64, 3, 2, 1, stream=st), "maxpool3x3s2")
         size = 25
         for prefix, ci, co, down in REID_BLOCKS:
             s = 2 if down else 1
@@ -488,7 +516,7 @@ class ReidEngine:
             cur, size = y, osz
         assert size == 4
         feats = self.features
-        plan.add(lambda st, cur=cur: ops.avgpool_l2norm(cur.buf, 512, nb, 16, 512, feats, stream=st))
+        plan.add(lambda st, cur=cur: ops.avgpool_l2norm(cur.buf, 512, nb, 16, 512, feats, stream=st), "avgpool+l2norm")
         self.conv_flops_per_crop = plan.conv_flops / nb
         return {"plan": plan, "frames_ptr": frames.data_ptr(), "shape": tuple(frames.shape)}
 
@@ -513,6 +541,8 @@ class ReidEngine:
 
         def conv_raw(x: TRef, wname, bias_name, co, k, s, p, a_mode):
             w = sd[wname]
+            if w.shape[1] != x.c:
+                w = _pad_cin(w, x.c)
             d = ops.make_conv_desc(n, x.h, x.w, int(w.shape[1]), co, k, s, p, cin_pitch=x.pitch, cout_pitch=co, act=L.ACT_NONE,
                                    out_dtype=L.F32, a_mode=a_mode)
             ho, wo = ops.conv_out_hw(d)
@@ -539,12 +569,12 @@ class ReidEngine:
 
         with torch.cuda.stream(st):
             rd = L.RoiDesc()
-            rd.num_rois, rd.out_size = n, REID_SIZE
+            rd.num_rois, rd.out_size, rd.out_channels = n, REID_SIZE, 16
             for c in range(3):
                 rd.mean[c] = REID_MEAN[c]; rd.inv_std[c] = 1.0 / REID_STD[c]
-            x0 = torch.zeros(n, REID_SIZE, REID_SIZE, 4, dtype=torch.float16, device=dev)
+            x0 = torch.zeros(n, REID_SIZE, REID_SIZE, 16, dtype=torch.float16, device=dev)
             ops.roi_resize_norm(rd, frames, fh, fw, self.rois, x0, stream=st)
-            raw, osz = conv_raw(TRef(x0, 0, 3), "conv.0.weight", "conv.0.bias", 64, 3, 1, 1, L.A_C4)
+            raw, osz = conv_raw(TRef(x0, 0, 16), "conv.0.weight", "conv.0.bias", 64, 3, 1, 1, self.a_mode)
             s0 = bn_act(raw, osz, "conv.1", L.ACT_RELU, None)
             cur = TRef(torch.empty(n, 25, 25, 64, dtype=torch.float16, device=dev), 0, 64)
             ops.maxpool(s0.buf, 64, cur.buf, 64, n, 50, 50, 64, 3, 2, 1, stream=st)

@@ -23,7 +23,7 @@ def _st(stream) -> int:
 # ------------------------------------------------------------------------------------------ conv
 def make_conv_desc(n, h, w, cin, cout, k, stride, pad, *, cin_pitch=None, cout_pitch=None, act=L.ACT_SILU,
                    res_mode=L.RES_NONE, res_pitch=0, out_dtype=L.F16, a_mode=L.A_AUTO, block_n=0, stages=0,
-                   kw=None, epi_direct=False, c4_narrow=False) -> L.ConvDesc:
+                   kw=None, epi_direct=False, c4_narrow=False, bk=0) -> L.ConvDesc:
     d = L.ConvDesc()
     d.n, d.h, d.w = n, h, w
     d.cin, d.cin_pitch = cin, cin if cin_pitch is None else cin_pitch
@@ -35,6 +35,7 @@ def make_conv_desc(n, h, w, cin, cout, k, stride, pad, *, cin_pitch=None, cout_p
     d.out_dtype, d.a_mode, d.block_n, d.stages = out_dtype, a_mode, block_n, stages
     d.reserved[0] = 1 if epi_direct else 0      # debug: per-thread global stores instead of the staged TMA store
     d.reserved[1] = 1 if c4_narrow else 0       # debug: force 8-byte granules in the C4 gather
+    d.reserved[2] = bk                          # 0 = auto; 16/32/64 forces the K chunk width of the TMA path
     return d
 
 
@@ -76,6 +77,12 @@ def frames_to_f16c4(frames_u8: torch.Tensor, out: torch.Tensor, stream=None) -> 
     n, h, w, c = frames_u8.shape
     assert c == 3 and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
     L.check(L.load().vcb_frames_to_f16c4(L.ptr(frames_u8), L.ptr(out), n, h, w, _st(stream)), "vcb_frames_to_f16c4")
+
+
+def frames_to_f16_s2d(frames_u8: torch.Tensor, out: torch.Tensor, stream=None) -> None:
+    n, h, w, c = frames_u8.shape
+    assert c == 3 and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+    L.check(L.load().vcb_frames_to_f16_s2d(L.ptr(frames_u8), L.ptr(out), n, h, w, _st(stream)), "vcb_frames_to_f16_s2d")
 
 
 def upsample2x(src, src_pitch, dst, dst_pitch, n, h, w, c, stream=None) -> None:
