@@ -62,8 +62,9 @@ typedef struct VcbConvDesc {
   int32_t a_mode;             /* VCB_A_*: how the im2col operand reaches shared memory */
   int32_t block_n;            /* 0 = auto; N tile (multiple of 16, <= 256) */
   int32_t stages;             /* 0 = auto; smem pipeline depth */
-  int32_t reserved[4];        /* [0]=1: debug epilogue with direct global stores; [1]=1: debug 8-byte C4 gather;
-                               * [2]=16/32/64: force the K chunk (swizzle) width of the TMA path */
+  int32_t reserved[4];        /* [0]=1: debug epilogue with direct global stores; [1]=1: debug 8-byte C4 gather, 2: im2col-mode TMA even for 1x1 convs;
+                               * [2]=16/32/64: force the K chunk (swizzle) width of the TMA path;
+                               * [3]=1: single-CTA kernel only, 2: require the CTA-pair (cta_group::2) kernel */
 } VcbConvDesc;
 
 /* element counts of the packed fp16 weight blob and the padded fp32 bias for this descriptor */

@@ -24,7 +24,7 @@ CASES = []
 
 def case(name, **kw):
     base = dict(n=1, h=16, w=16, cin=64, cout=64, k=1, s=1, p=0, act="none", res="none", out="f16", mode="tma",
-                cin_pitch=None, cout_pitch=None, block_n=0, stages=0, epi_direct=False, c4_narrow=False, bk=0)
+                cin_pitch=None, cout_pitch=None, block_n=0, stages=0, epi_direct=False, c4_narrow=False, bk=0, cta_pair=0, a_im2col=False)
     base.update(kw)
     CASES.append((name, base))
 
@@ -55,6 +55,48 @@ case("tma-bk32-cin96-s2", mode="tma", n=2, h=40, w=40, k=3, s=2, p=1, cin=96, co
 case("tma-bk64forced-cin96", mode="tma", n=2, h=40, w=40, k=3, p=1, cin=96, cout=192, act="silu", res="after", bk=64)
 case("tma-bk32forced-cin128-1x1", mode="tma", n=2, h=40, w=40, k=1, cin=128, cout=64, act="silu", bk=32)
 case("tma-bk16forced-cin64", mode="tma", n=2, h=20, w=20, k=3, p=1, cin=64, cout=64, act="relu", bk=16)
+case("pair-odd-mtiles", mode="tma", n=5, h=13, w=13, k=3, p=1, cin=128, cout=128, act="relu", res="before", cta_pair=2)
+case("pair-cout384-bk32", mode="tma", n=3, h=20, w=20, k=3, p=1, cin=96, cout=384, act="silu", cta_pair=2)
+case("pair-cout255-f32", mode="tma", n=2, h=20, w=20, cin=128, cout=255, cout_pitch=256, out="f32", cta_pair=2)
+case("pair-bk16-stem", mode="tma", n=2, h=64, w=64, k=3, p=1, cin=16, cout=48, act="silu", cta_pair=2)
+case("single-3x3-192", mode="tma", n=32, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", res="after", cta_pair=1)
+case("single-1x1-96", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, act="silu", cta_pair=1)
+case("single-cout384", mode="tma", n=2, h=20, w=20, k=3, p=1, cin=192, cout=384, act="silu", cta_pair=1)
+case("im2col-1x1-96-single", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, act="silu", cta_pair=1, a_im2col=True)
+case("im2col-1x1-96-pair", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, act="silu", a_im2col=True)
+case("tiled-1x1-192-192", mode="tma", n=32, h=80, w=80, k=1, cin=192, cout=192, act="silu")
+case("im2col-1x1-192-192", mode="tma", n=32, h=80, w=80, k=1, cin=192, cout=192, act="silu", a_im2col=True)
+case("tiled-1x1-pitch-tail", mode="tma", n=3, h=13, w=13, k=1, cin=64, cout=40, cin_pitch=128, cout_pitch=48, act="relu")
+for _st in (2, 3, 4):
+    case(f"sweep-single-st{_st}", mode="tma", n=32, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=1, stages=_st)
+for _st in (2, 3, 4, 6):
+    case(f"sweep-pair-st{_st}", mode="tma", n=32, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=2, stages=_st)
+for _bn in (64,):
+    case(f"sweep-single-bn{_bn}", mode="tma", n=32, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=1, block_n=_bn)
+    case(f"sweep-pair-bn{_bn}", mode="tma", n=32, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=2, block_n=_bn)
+case("sweep-single-splitb", mode="tma", n=32, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=1, epi_direct=2)
+case("sweep-single-splitb-big", mode="tma", n=128, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=1, epi_direct=2)
+case("sweep-1x1-192-single", mode="tma", n=32, h=80, w=80, k=1, cin=192, cout=192, act="silu", cta_pair=1)
+case("sweep-1x1-192-splitb", mode="tma", n=32, h=80, w=80, k=1, cin=192, cout=192, act="silu", cta_pair=1, epi_direct=2)
+case("sweep-single-big-noepi", mode="tma", n=128, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=1, epi_direct=3)
+case("sweep-pair-big-noepi", mode="tma", n=128, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=2, epi_direct=3)
+case("sweep-single-big-acc1", mode="tma", n=128, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=1, epi_direct=4)
+case("sweep-1x1-192-noepi", mode="tma", n=32, h=80, w=80, k=1, cin=192, cout=192, act="silu", cta_pair=1, epi_direct=3)
+case("sweep-512-big", mode="tma", n=2048, h=4, w=4, k=3, p=1, cin=512, cout=512, act="relu", cta_pair=1)
+case("sweep-512-big-pair", mode="tma", n=2048, h=4, w=4, k=3, p=1, cin=512, cout=512, act="relu", cta_pair=2)
+case("sweep-512-big-noepi", mode="tma", n=2048, h=4, w=4, k=3, p=1, cin=512, cout=512, act="relu", cta_pair=1, epi_direct=3)
+for _res, _tag in ((8, "bres"), (7, "occ1"), (0, "occ2")):
+    case(f"occ-48-48-{_tag}", mode="tma", n=32, h=160, w=160, k=3, p=1, cin=48, cout=48, act="silu", res="after", epi_direct=_res)
+    case(f"occ-64-64-{_tag}", mode="tma", n=512, h=25, w=25, k=3, p=1, cin=64, cout=64, act="relu", epi_direct=_res)
+    case(f"occ-96-96-{_tag}", mode="tma", n=32, h=80, w=80, k=3, p=1, cin=96, cout=96, act="silu", epi_direct=_res)
+    case(f"occ-stem-{_tag}", mode="tma", n=16, h=320, w=320, k=3, p=1, cin=16, cout=48, act="silu", epi_direct=_res)
+    case(f"occ-1x1-96-96-{_tag}", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, act="silu", epi_direct=_res)
+    case(f"occ-1x1-192-96-{_tag}", mode="tma", n=32, h=80, w=80, k=1, cin=192, cout=96, act="silu", epi_direct=_res)
+case("bres-small-odd", mode="tma", n=150, h=13, w=13, k=3, p=1, cin=64, cout=40, act="relu")
+case("sweep-single-direct", mode="tma", n=32, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=1, epi_direct=True)
+case("sweep-single-noact", mode="tma", n=32, h=40, w=40, k=3, p=1, cin=192, cout=192, act="none", cta_pair=1)
+case("sweep-single-big", mode="tma", n=128, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=1)
+case("sweep-pair-big", mode="tma", n=128, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=2)
 case("c4-yolo-stem-narrow", mode="c4", n=2, h=64, w=64, cin=3, cin_pitch=4, cout=32, k=6, s=2, p=2, act="silu", c4_narrow=True)
 case("c4-yolo-stem", mode="c4", n=2, h=64, w=64, cin=3, cin_pitch=4, cout=32, k=6, s=2, p=2, act="silu")
 case("c4-reid-stem", mode="c4", n=5, h=50, w=50, cin=3, cin_pitch=4, cout=64, k=3, s=1, p=1, act="relu")
@@ -88,7 +130,7 @@ def run_case(idx: int) -> dict:
     d = ops.make_conv_desc(n, h, w, cin, cout, k, s, p, cin_pitch=cin_pitch, cout_pitch=cout_pitch, act=act,
                            res_mode=res_mode, res_pitch=cout_pitch if res_mode else 0,
                            out_dtype=L.F32 if c["out"] == "f32" else L.F16, a_mode=mode, block_n=c["block_n"], stages=c["stages"],
-                           epi_direct=c["epi_direct"], c4_narrow=c["c4_narrow"], bk=c["bk"])
+                           epi_direct=c["epi_direct"], c4_narrow=c["c4_narrow"], bk=c["bk"], cta_pair=c["cta_pair"], a_im2col=c["a_im2col"])
     ho, wo = ops.conv_out_hw(d)
     res_full = (torch.randn(n, ho, wo, cout_pitch, generator=g)).half() if res_mode else None
 
@@ -151,6 +193,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", type=int, default=None)
     ap.add_argument("--only", type=str, default=None, help="substring filter")
+    ap.add_argument("--skip", type=str, default="", help="comma separated substrings to skip")
     ap.add_argument("--out", type=str, default=os.path.join(ROOT, "gpurun_out", "bringup_conv.jsonl"))
     a = ap.parse_args()
     if a.case is not None:
@@ -161,6 +204,8 @@ def main():
     with open(a.out, "w") as fo:
         for i, (name, _) in enumerate(CASES):
             if a.only and a.only not in name:
+                continue
+            if a.skip and any(k and k in name for k in a.skip.split(",")):
                 continue
             try:
                 pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", str(i)], capture_output=True,

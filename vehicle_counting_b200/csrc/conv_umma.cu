@@ -62,8 +62,15 @@ struct ConvParams {
   int num_pair_tiles;  // cta_group::2 kernel: ceil(m_tiles / 2) * n_tiles
   int num_stages, acc_stages, tmem_cols;
   int act, res_mode, res_pitch, out_fp32;
+  int out_stage_bufs;  // 1 or 2 staged sub-tiles in flight
+  int out_stage_bytes; // output staging area: 8 warps x 2 boxes x (2 KiB fp16 | 4 KiB fp32)
   int epi_direct;      // 1: per-thread 16-byte global stores (debug / cross-check); 0: staged TMA store
   int c4_wide;         // A_C4: 16-byte granules (two taps) instead of 8-byte ones
+  int dbg_skip_epilogue;   // timing experiment: epilogue only hands the accumulator back (results are garbage)
+  int b_resident;      // A_TMA single-CTA, one N tile, small weights: the whole packed B stays in shared memory
+  int b_res_bytes;     // bytes of the resident weight region (multiple of 1024)
+  int split_b;         // A_TMA single-CTA: weight tiles are issued by a second producer warp
+  int a_tiled;         // A_TMA, 1x1/s1/p0: A is the plain [M][C] matrix -> tiled-mode TMA instead of im2col mode
   const __half* x;
   const float* bias;
   const __half* residual;
@@ -91,6 +98,9 @@ template <bool kTwoCta>
 __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtensorMap* tmap_out_ptr, uint32_t tmem_base,
                                               uint32_t out_stage, uint32_t tmem_full0, uint32_t tmem_empty0, int first_tile,
                                               int tile_step, int cta_rank) {
+  // 8 warps: warp (q = warp & 3, half = warp >> 2) reads accumulator rows [32q, 32q+32) and one half of the columns of
+  // each staged sub-tile (128 rows x 128 bytes); one TMA store per sub-tile, two sub-tiles in flight.  (A variant with
+  // one small TMA store per warp and no CTA-wide barrier measured 20-50 % slower: few large TMA boxes win.)
   const CUtensorMap& tmap_out = *tmap_out_ptr;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -112,15 +122,24 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtenso
       const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
       mbar_wait(tmem_full_bar(acc), acc_ph, p.fault, FAULT_TMEM_FULL_WAIT, (int)acc);
       tcgen05_fence_after();
+      if (p.dbg_skip_epilogue) {
+        tcgen05_fence_before();
+        if (kTwoCta && cta_rank != 0) mbar_arrive_remote(tmem_empty_bar(acc), 0);
+        else mbar_arrive(tmem_empty_bar(acc));
+        continue;
+      }
       const int row = m_tile * kBlockM + row_in_tile;
       const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + acc * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
       const size_t out_row = (size_t)row * (size_t)p.out_pitch;
       const size_t res_row = (size_t)row * (size_t)p.res_pitch;
       for (int sub = 0; sub < num_sub; ++sub, ++sub_count) {
-        const uint32_t stage_buf = out_stage + (sub_count & 1u) * kStageOutBytes;
+        const uint32_t stage_buf = out_stage + ((p.out_stage_bufs == 2) ? (sub_count & 1u) : 0u) * kStageOutBytes;
         if (!p.epi_direct) {
-          if (issuer) tma_store_wait_read<1>();            // the store that used this buffer two sub-tiles ago is drained
+          if (issuer) {                                    // the store that last used this buffer is drained
+            if (p.out_stage_bufs == 2) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+          }
           asm volatile("bar.sync 2, 256;" ::: "memory");
         }
         const int col_base = sub * sub_cols + half * my_cols;            // first column (within the N tile) of this thread
@@ -239,23 +258,25 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtenso
 // Shared-memory carve-up (all offsets from a 1024-byte aligned base):
 //   [num_stages x (A tile 16 KiB | B tile block_n*128 B)] [2 x 16 KiB output staging] [barriers] [tmem slot] [row table]
 template <int A_MODE, int BK>
-__global__ void __launch_bounds__(A_MODE == A_TMA ? kThreadsTma : kThreadsGather, 1)
+__global__ void __launch_bounds__(A_MODE == A_TMA ? kThreadsTma + 32 : kThreadsGather, A_MODE == A_TMA ? 2 : 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
-  const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
-  const uint32_t out_stage = smem_base + (uint32_t)p.num_stages * stage_bytes;          // 1024-aligned
-  const uint32_t bars = out_stage + 2u * kStageOutBytes;                                  // 8-byte aligned
+  const uint32_t stage_bytes = kATileBytes + (p.b_resident ? 0u : b_tile_bytes);
+  const uint32_t b_res = smem_base + (uint32_t)p.num_stages * stage_bytes;              // resident weights (may be empty)
+  const uint32_t out_stage = b_res + (uint32_t)p.b_res_bytes;                             // 1024-aligned
+  const uint32_t bars = out_stage + (uint32_t)p.out_stage_bytes;                          // 8-byte aligned
   auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(kMaxStages + s); };
   auto tmem_full_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + a); };
   auto tmem_empty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
+  const uint32_t bres_bar = tmem_slot + 8u;          // second half of the 16-byte slot region
   // generic pointers to the same locations (for plain loads/stores)
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint8_t* tail_gen = smem_gen + (size_t)p.num_stages * stage_bytes + 2 * kStageOutBytes + 8 * (2 * kMaxStages + 4);
+  uint8_t* tail_gen = smem_gen + (size_t)p.num_stages * stage_bytes + p.b_res_bytes + p.out_stage_bytes + 8 * (2 * kMaxStages + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_gen);
   RowInfo* rows = reinterpret_cast<RowInfo*>(tail_gen + 16);
 
@@ -263,7 +284,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    const uint32_t full_count = (A_MODE == A_TMA) ? 1u : (1u + kGatherThreads);
+    const uint32_t full_count = (A_MODE == A_TMA) ? (p.split_b ? 2u : 1u) : (1u + kGatherThreads);
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(full_bar(s), full_count);
       mbar_init(empty_bar(s), 1);
@@ -272,6 +293,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(tmem_full_bar(a), 1);
       mbar_init(tmem_empty_bar(a), kNumEpilogueThreads);
     }
+    mbar_init(bres_bar, 1);
     fence_mbar_init();
   }
   if (warp == kProducerWarp && lane == 0) {
@@ -292,6 +314,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ======================= TMA producer (one thread) =======================
     if (lane == 0) {
       uint32_t it = 0;
+      if (A_MODE == A_TMA && p.b_resident && (int)blockIdx.x < p.num_tiles) {
+        // small layers: every packed weight chunk is loaded once per CTA and stays put
+        const uint32_t bc = (uint32_t)(p.block_n * BK * 2);
+        mbar_arrive_expect_tx(bres_bar, (uint32_t)p.total_chunks * bc);
+        for (int kc = 0; kc < p.total_chunks; ++kc) tma_load_2d(&tmap_b, bres_bar, b_res + (uint32_t)kc * bc, kc * BK, 0);
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         int cw = 0, ch = 0, cn = 0;
@@ -315,10 +343,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t b_dst = a_dst + kATileBytes;
           const int nch = (G == 1) ? 1 : min(G, p.total_chunks - kit * G);
           if (A_MODE == A_TMA) {
-            mbar_arrive_expect_tx(full_bar(st), (uint32_t)nch * (a_chunk + b_chunk));
+            mbar_arrive_expect_tx(full_bar(st), (uint32_t)nch * ((p.split_b || p.b_resident) ? a_chunk : a_chunk + b_chunk));
             for (int g = 0; g < nch; ++g, ++kidx) {
-              tma_load_im2col_4d(&tmap_a, full_bar(st), a_dst + (uint32_t)g * a_chunk, c * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
-              tma_load_2d(&tmap_b, full_bar(st), b_dst + (uint32_t)g * b_chunk, kidx * BK, n_tile * p.block_n);
+              if (p.a_tiled) tma_load_2d(&tmap_a, full_bar(st), a_dst + (uint32_t)g * a_chunk, c * BK, m_tile * kBlockM);
+              else tma_load_im2col_4d(&tmap_a, full_bar(st), a_dst + (uint32_t)g * a_chunk, c * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+              if (!p.split_b && !p.b_resident)
+                tma_load_2d(&tmap_b, full_bar(st), b_dst + (uint32_t)g * b_chunk, kidx * BK, n_tile * p.block_n);
               if (++c == p.chunks_per_tap) { c = 0; if (++s == p.kw) { s = 0; ++r; } }
             }
           } else {
@@ -341,6 +371,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // descriptor high words are loop invariants; only the 14-bit start-address field changes
       const uint64_t desc_hi = umma_desc_kmajor(0, sbo, layout_type);
       uint32_t it = 0, tile_iter = 0;
+      if (p.b_resident && (int)blockIdx.x < p.num_tiles) mbar_wait(bres_bar, 0u, p.fault, FAULT_FULL_WAIT, 300);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
         const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
         const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
@@ -358,7 +389,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int g = 0; g < G; ++g) {
             if (g < nch) {
               const uint64_t a_desc = desc_hi | (uint64_t)(((a_addr + (uint32_t)g * a_chunk) & 0x3FFFF) >> 4);
-              const uint64_t b_desc = desc_hi | (uint64_t)(((a_addr + kATileBytes + (uint32_t)g * b_chunk) & 0x3FFFF) >> 4);
+              const uint32_t b_addr = p.b_resident ? b_res + (uint32_t)(kit * G + g) * b_chunk : a_addr + kATileBytes + (uint32_t)g * b_chunk;
+              const uint64_t b_desc = desc_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
 #pragma unroll
               for (int k = 0; k < ksteps; ++k) {
                 // +32 bytes per UMMA_K step inside the swizzle row: +2 in the (addr >> 4) field
@@ -373,7 +405,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp < kEpilogueWarps) {
     conv_epilogue<false>(p, &tmap_out, tmem_base, out_stage, tmem_full_bar(0), tmem_empty_bar(0), blockIdx.x, gridDim.x, 0);
-  } else if (A_MODE != A_TMA) {
+  } else if (A_MODE == A_TMA) {
+    // ======================= optional second TMA producer (warp 10): weight tiles =======================
+    if (p.split_b && warp == kGatherWarp0 && lane == 0) {
+      const uint32_t b_chunk = (uint32_t)(p.block_n * BK * 2);
+      constexpr int G = kBlockK / BK;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int kidx = 0;
+        for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
+          const int st = it % p.num_stages;
+          const uint32_t ph = (it / p.num_stages) & 1u;
+          mbar_wait(empty_bar(st), ph ^ 1u, p.fault, FAULT_EMPTY_WAIT, 200 + st);
+          const uint32_t b_dst = smem_base + (uint32_t)st * stage_bytes + kATileBytes;
+          const int nch = (G == 1) ? 1 : min(G, p.total_chunks - kit * G);
+          mbar_arrive_expect_tx(full_bar(st), (uint32_t)nch * b_chunk);
+          for (int g = 0; g < nch; ++g, ++kidx)
+            tma_load_2d(&tmap_b, full_bar(st), b_dst + (uint32_t)g * b_chunk, kidx * BK, n_tile * p.block_n);
+        }
+      }
+    }
+  } else {
     // ======================= gather producers (warps 10-13) =======================
     const int gtid = threadIdx.x - kGatherWarp0 * 32;
     uint32_t it = 0;          // K-steps issued by this thread (same sequence in every gather thread)
@@ -468,6 +521,147 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster own one 256 x N tile.  Each CTA loads its own 128
+// pixel rows of A and HALF of the weight tile (N/2 rows); one tcgen05.mma issued by the leader CTA spans both SMs
+// (M = 256) and reads the B halves from both shared memories, so the L2 -> SM weight traffic and the number of MMA
+// instructions per FLOP are halved.  TMA loads of both CTAs signal the leader's full barrier; the leader's
+// tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs; both epilogues release the
+// accumulator on the leader's tmem_empty barrier.  A operand: im2col TMA only.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTma, 1)
+conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_tile_bytes = (uint32_t)p.block_n * 64u;                 // this CTA's half: N/2 rows x 128 B
+  const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
+  const uint32_t out_stage = smem_base + (uint32_t)p.num_stages * stage_bytes;
+  const uint32_t bars = out_stage + (uint32_t)p.out_stage_bytes;
+  auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(kMaxStages + s); };
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + (size_t)p.num_stages * stage_bytes + p.out_stage_bytes + 8 * (2 * kMaxStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(full_bar(s), 2);                        // one producer arrival per CTA (leader's copy is the live one)
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 2 * kNumEpilogueThreads);   // both CTAs' epilogues (leader's copy is the live one)
+    }
+    fence_mbar_init();
+  }
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc_2cta(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish_2cta();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                                   // peers' barriers exist before any remote arrive / TMA signal
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      constexpr uint32_t a_chunk = (uint32_t)(kBlockM * BK * 2);
+      const uint32_t b_chunk = (uint32_t)((p.block_n >> 1) * BK * 2);
+      constexpr int G = kBlockK / BK;
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters) {
+        const int pm = tile / p.n_tiles, n_tile = tile - pm * p.n_tiles;
+        const int m0 = (2 * pm + rank) * kBlockM;      // may lie past M for the last pair: the TMA zero-fills
+        const int cn = m0 / p.PQ;
+        const int rem = m0 - cn * p.PQ;
+        const int p0 = rem / p.Q, q0 = rem - p0 * p.Q;
+        const int cw = q0 * p.stride - p.pad, ch = p0 * p.stride - p.pad;
+        int r = 0, s = 0, c = 0, kidx = 0;
+        for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
+          const int st = it % p.num_stages;
+          const uint32_t ph = (it / p.num_stages) & 1u;
+          mbar_wait(empty_bar(st), ph ^ 1u, p.fault, FAULT_EMPTY_WAIT, st);
+          const uint32_t a_dst = smem_base + (uint32_t)st * stage_bytes;
+          const uint32_t b_dst = a_dst + kATileBytes;
+          const int nch = (G == 1) ? 1 : min(G, p.total_chunks - kit * G);
+          const uint32_t lead_full = mapa_shared(full_bar(st), 0);
+          if (leader) mbar_arrive_expect_tx(full_bar(st), 2u * (uint32_t)nch * (a_chunk + b_chunk));
+          else mbar_arrive_remote(full_bar(st), 0);
+          for (int g = 0; g < nch; ++g, ++kidx) {
+            if (p.a_tiled) tma_load_2d_2cta(&tmap_a, lead_full, a_dst + (uint32_t)g * a_chunk, c * BK, m0);
+            else tma_load_im2col_4d_2cta(&tmap_a, lead_full, a_dst + (uint32_t)g * a_chunk, c * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+            tma_load_2d_2cta(&tmap_b, lead_full, b_dst + (uint32_t)g * b_chunk, kidx * BK,
+                             n_tile * p.block_n + rank * (p.block_n >> 1));
+            if (++c == p.chunks_per_tap) { c = 0; if (++s == p.kw) { s = 0; ++r; } }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (leader && lane == 0) {
+      const uint32_t idesc = umma_idesc_f16((uint32_t)p.block_n, 256u);
+      constexpr uint32_t a_chunk = (uint32_t)(kBlockM * BK * 2);
+      const uint32_t b_chunk = (uint32_t)((p.block_n >> 1) * BK * 2);
+      constexpr uint32_t sbo = (uint32_t)(8 * BK * 2);
+      constexpr uint32_t layout_type = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);
+      constexpr int ksteps = BK / 16;
+      constexpr int G = kBlockK / BK;
+      const uint64_t desc_hi = umma_desc_kmajor(0, sbo, layout_type);
+      uint32_t it = 0, tile_iter = 0;
+      for (int tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
+        const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
+        const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
+        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u, p.fault, FAULT_TMEM_EMPTY_WAIT, (int)acc);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.block_n;
+        for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
+          const int st = it % p.num_stages;
+          const uint32_t ph = (it / p.num_stages) & 1u;
+          mbar_wait(full_bar(st), ph, p.fault, FAULT_FULL_WAIT, st);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base + (uint32_t)st * stage_bytes;
+          const int nch = (G == 1) ? 1 : min(G, p.total_chunks - kit * G);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (g < nch) {
+              const uint64_t a_desc = desc_hi | (uint64_t)(((a_addr + (uint32_t)g * a_chunk) & 0x3FFFF) >> 4);
+              const uint64_t b_desc = desc_hi | (uint64_t)(((a_addr + kATileBytes + (uint32_t)g * b_chunk) & 0x3FFFF) >> 4);
+#pragma unroll
+              for (int k = 0; k < ksteps; ++k)
+                umma_f16_2cta(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kit | g | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit_2cta(empty_bar(st), (uint16_t)3);
+          if (kit == p.num_k_iters - 1) umma_commit_2cta(tmem_full_bar(acc), (uint16_t)3);
+        }
+      }
+    }
+  } else if (warp < kEpilogueWarps) {
+    conv_epilogue<true>(p, &tmap_out, tmem_base, out_stage, tmem_full_bar(0), tmem_empty_bar(0), cluster_id, num_clusters, rank);
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();                                   // nobody exits (or frees TMEM) while the peer may still signal it
+  if (warp == kMmaWarp) tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight packing: OIHW fp32 (BN folded) -> [cout_pad][K_pad] fp16, K index = (tap * cin_pad + c) for
 // the 64-channel-chunk modes and (tap * 4 + c) for A_C4
@@ -501,6 +695,10 @@ struct ConvGeom {
   int bk, chunks_per_stage, total_chunks;
   int block_n, n_tiles, cout_pad, m_tiles;
   int stages, acc_stages, tmem_cols;
+  int out_bufs;         // staged output sub-tiles in flight (1 or 2)
+  int ctas_per_sm;      // 1, or 2 co-resident persistent CTAs for narrow-N layers (each <= 110 KiB smem, <= 256 TMEM columns)
+  int two_cta;          // CTA-pair kernel (cta_group::2)
+  int b_resident, b_res_bytes;
   size_t smem_bytes;
 };
 
@@ -562,19 +760,44 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
     return set_error(VCB_ERR_INVALID, "conv: cout_pitch must be a multiple of 8 and >= round_up(cout, 8)");
   if (d.res_mode != VCB_RES_NONE && (d.res_pitch % 8 != 0 || d.res_pitch < cout_store))
     return set_error(VCB_ERR_INVALID, "conv: bad residual pitch");
-  g.acc_stages = (2 * g.block_n <= 512) ? 2 : 1;
-  int cols = g.acc_stages * g.block_n, pow2 = 32;
-  while (pow2 < cols) pow2 <<= 1;
-  g.tmem_cols = pow2;
-  const size_t stage_bytes = (size_t)kATileBytes + (size_t)g.block_n * 128;
-  const size_t fixed = 1024 /*align slack*/ + 2 * kStageOutBytes + 8 * (2 * kMaxStages + 4) + 16 + kBlockM * sizeof(RowInfo) + 64;
-  int stages = (int)((size_t)(227 * 1024 - fixed) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (d.stages != 0) stages = d.stages < stages ? d.stages : stages;
+  // CTA pairs (cta_group::2): measured on B200 at parity with the single-CTA kernel for these layer shapes, so they are
+  // opt-in (reserved[3] == 2); reserved[3] == 1 forces the single-CTA kernel.
+  g.two_cta = (g.a_mode == A_TMA && g.m_tiles >= 2 && d.reserved[3] == 2) ? 1 : 0;
+  if (d.reserved[3] == 2 && !g.two_cta) return set_error(VCB_ERR_INVALID, "conv: the CTA-pair kernel needs the TMA path and >= 2 M tiles");
+  // resident weights: one N tile and a packed B of at most 48 KiB stay in shared memory for the whole kernel
+  // (measured: pays off together with two CTAs per SM because it shrinks the per-stage footprint to the A tile)
+  const size_t b_total = (size_t)g.total_chunks * g.block_n * g.bk * 2;
+  g.b_resident = (g.a_mode == A_TMA && !g.two_cta && g.n_tiles == 1 && b_total <= 48 * 1024 && g.m_tiles > 148 && d.reserved[0] != 5) ? 1 : 0;
+  g.b_res_bytes = g.b_resident ? (int)((b_total + 1023) / 1024 * 1024) : 0;
+  const size_t stage_bytes = (size_t)kATileBytes + (g.b_resident ? 0 : (size_t)g.block_n * (g.two_cta ? 64 : 128));
+  const size_t tail = 1024 /*align slack*/ + g.b_res_bytes + 8 * (2 * kMaxStages + 4) + 16 + kBlockM * sizeof(RowInfo) + 64;
   const int min_stages = (g.a_mode == A_TMA) ? 2 : kGatherLag + 2;
-  if (stages < min_stages) return set_error(VCB_ERR_INVALID, "conv: not enough shared memory for the pipeline");
-  g.stages = stages;
-  g.smem_bytes = fixed + (size_t)stages * stage_bytes;
+  // Dependent tcgen05.mma on one accumulator issue ~200 cycles apart (measured), so one CTA cannot keep the tensor pipe
+  // busy; two co-resident persistent CTAs per SM give it two independent accumulator chains.  Try 2 CTAs/SM first
+  // (half the shared memory and half the TMEM each), fall back to 1.
+  const bool allow2 = g.a_mode == A_TMA && !g.two_cta && d.reserved[0] != 7 && (long long)g.m_tiles * g.n_tiles > 2 * 148;
+  int chosen = 0;
+  for (int ctas = allow2 ? 2 : 1; ctas >= 1 && !chosen; --ctas) {
+    const size_t budget = (size_t)(227 * 1024) / ctas;
+    const int tmem_budget = 512 / ctas;
+    if (g.block_n > tmem_budget) continue;
+    const int acc = (2 * g.block_n <= tmem_budget) ? 2 : 1;
+    int pow2 = 32;
+    while (pow2 < acc * g.block_n) pow2 <<= 1;
+    for (int bufs = 2; bufs >= 1 && !chosen; --bufs) {
+      const size_t fixed = tail + (size_t)bufs * kStageOutBytes;
+      if (budget < fixed + (size_t)min_stages * stage_bytes) continue;
+      int stages = (int)((budget - fixed) / stage_bytes);
+      if (stages > kMaxStages) stages = kMaxStages;
+      if (d.stages != 0 && d.stages < stages) stages = d.stages;
+      if (stages < min_stages) continue;
+      if (ctas == 2 && bufs == 2 && stages < 3) continue;     // prefer a third stage over a second staging buffer
+      g.ctas_per_sm = ctas; g.acc_stages = acc; g.tmem_cols = pow2; g.stages = stages; g.out_bufs = bufs;
+      g.smem_bytes = fixed + (size_t)stages * stage_bytes;
+      chosen = 1;
+    }
+  }
+  if (!chosen) return set_error(VCB_ERR_INVALID, "conv: not enough shared memory for the pipeline");
   return VCB_OK;
 }
 
@@ -607,6 +830,21 @@ int conv_pack_weights(const VcbConvDesc& d, const float* w, const float* bias, v
   return check_cuda(cudaGetLastError(), "pack_weights launch");
 }
 
+template <int BK>
+static int launch_conv_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvParams& p, const ConvGeom& g,
+                            cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(conv_umma_2cta_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv 2cta)");
+    attr_set = true;
+  }
+  const int max_clusters = state().num_sms / 2;
+  const int clusters = p.num_pair_tiles < max_clusters ? p.num_pair_tiles : max_clusters;
+  conv_umma_2cta_kernel<BK><<<2 * clusters, kThreadsTma, g.smem_bytes, st>>>(ta, tb, to, p);
+  return check_cuda(cudaGetLastError(), "conv (cta pair) launch");
+}
+
 template <int A_MODE, int BK>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvParams& p, const ConvGeom& g,
                        cudaStream_t st) {
@@ -616,8 +854,9 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv)");
     attr_set = true;
   }
-  const int grid = p.num_tiles < state().num_sms ? p.num_tiles : state().num_sms;
-  conv_umma_kernel<A_MODE, BK><<<grid, A_MODE == A_TMA ? kThreadsTma : kThreadsGather, g.smem_bytes, st>>>(ta, tb, to, p);
+  const int max_ctas = state().num_sms * g.ctas_per_sm;
+  const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
+  conv_umma_kernel<A_MODE, BK><<<grid, A_MODE == A_TMA ? (p.split_b ? kThreadsTma + 32 : kThreadsTma) : kThreadsGather, g.smem_bytes, st>>>(ta, tb, to, p);
   return check_cuda(cudaGetLastError(), "conv launch");
 }
 
@@ -643,6 +882,7 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   p.chunks_per_tap = g.chunks_per_tap; p.num_k_iters = g.num_k_iters;
   p.bk = g.bk; p.chunks_per_stage = g.chunks_per_stage; p.total_chunks = g.total_chunks;
   p.block_n = g.block_n; p.n_tiles = g.n_tiles; p.m_tiles = g.m_tiles; p.num_tiles = g.m_tiles * g.n_tiles;
+  p.num_pair_tiles = ((g.m_tiles + 1) / 2) * g.n_tiles;
   p.num_stages = g.stages; p.acc_stages = g.acc_stages; p.tmem_cols = g.tmem_cols;
   p.act = d.act; p.res_mode = d.res_mode; p.res_pitch = d.res_pitch; p.out_fp32 = d.out_dtype == VCB_F32 ? 1 : 0;
   p.x = reinterpret_cast<const __half*>(x);
@@ -651,6 +891,12 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   p.out = y;
   p.fault = state().fault_dev;
   p.epi_direct = d.reserved[0] == 1 ? 1 : 0;
+  p.split_b = (d.reserved[0] == 2 && g.a_mode == A_TMA && !g.two_cta && !g.b_resident) ? 1 : 0;
+  p.b_resident = g.b_resident; p.b_res_bytes = g.b_res_bytes;
+  p.dbg_skip_epilogue = d.reserved[0] == 3 ? 1 : 0;
+  if (d.reserved[0] == 4) { p.acc_stages = 1; }
+  p.out_stage_bufs = g.out_bufs;
+  p.out_stage_bytes = g.out_bufs * kStageOutBytes;
   p.c4_wide = (g.a_mode == A_C4 && d.kw % 2 == 0 && d.stride % 2 == 0 && d.pad % 2 == 0 && d.w % 2 == 0 && d.reserved[1] != 1) ? 1 : 0;
 
   const CUtensorMapSwizzle swz = g.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (g.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -671,14 +917,25 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   {   // B: [cout_pad][k_pad] fp16, box = 64 (K) x block_n rows, 128-byte swizzle
     const cuuint64_t dims[2] = {(cuuint64_t)g.k_pad, (cuuint64_t)g.cout_pad};
     const cuuint64_t strides[1] = {(cuuint64_t)g.k_pad * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)g.bk, (cuuint32_t)g.block_n};
+    const cuuint32_t box[2] = {(cuuint32_t)g.bk, (cuuint32_t)(g.two_cta ? g.block_n / 2 : g.block_n)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = state().encode_tiled(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_packed), dims, strides,
                                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   }
-  if (g.a_mode == A_TMA) {
+  p.a_tiled = (g.a_mode == A_TMA && d.kh == 1 && d.kw == 1 && d.stride == 1 && d.pad == 0 && d.reserved[1] != 2) ? 1 : 0;
+  if (p.a_tiled) {
+    // 1x1/s1/p0: A is the [M][cin] matrix itself (row pitch cin_pitch): plain tiled TMA, box = bk channels x 128 rows
+    const cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)g.M};
+    const cuuint64_t strides[1] = {(cuuint64_t)d.cin_pitch * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)g.bk, (cuuint32_t)kBlockM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = state().encode_tiled(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+  } else if (g.a_mode == A_TMA) {
     // A: NHWC activations as a (C, W, H, N) tensor in im2col mode.  Bounding box of base pixels:
     // lower corner = -pad, upper corner = pad - (k - 1); traversal stride = conv stride; one load =
     // 128 consecutive output pixels x 64 channels at filter offset (s, r).
@@ -703,6 +960,11 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   }
   switch (g.a_mode) {
     case A_TMA:
+      if (g.two_cta) {
+        if (g.bk == 64) return launch_conv_2cta<64>(ta, tb, to, p, g, st);
+        if (g.bk == 32) return launch_conv_2cta<32>(ta, tb, to, p, g, st);
+        return launch_conv_2cta<16>(ta, tb, to, p, g, st);
+      }
       if (g.bk == 64) return launch_conv<A_TMA, 64>(ta, tb, to, p, g, st);
       if (g.bk == 32) return launch_conv<A_TMA, 32>(ta, tb, to, p, g, st);
       return launch_conv<A_TMA, 16>(ta, tb, to, p, g, st);

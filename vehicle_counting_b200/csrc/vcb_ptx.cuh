@@ -101,10 +101,19 @@ static __device__ __noinline__ void mbar_fault(KernelFault* f, int code, int inf
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, KernelFault* f, int code, int info) {
   if (mbar_try_wait(bar, parity)) return;
+  // slow path: the %globaltimer read doubles as a short back-off before polling resumes (measured neutral-to-better
+  // than tight polling on B200); a wait that lasts 2 s is a protocol bug -> recorded fault + trap
   const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > 2000000000ull) mbar_fault(f, code, info, (int)parity);
+  }
+}
+// tight polling variant (A/B experiments)
+__device__ __forceinline__ void mbar_wait_tight(uint32_t bar, uint32_t parity, KernelFault* f, int code, int info) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins == (1u << 22)) mbar_fault(f, code, info, (int)parity);
   }
 }
 
