@@ -193,15 +193,22 @@ def run_ours(a) -> dict:
         reid.run(yolo.frames, None, n=ncrops)
         ys.wait_stream(rs)
 
-    def step_e2e(i):
-        """host buffers in, host results out (H2D frames + ROIs, D2H detections + embeddings inside the timed region)"""
-        yolo.upload(host_pool[i % pool_n])
-        yolo.forward()
-        det, cnt = yolo.download()
-        rs.wait_stream(ys)
-        reid.run(yolo.frames, rois_np)
-        feats = reid.download(ncrops)
-        return int(cnt.sum()), feats.shape[0]
+    from vehicle_counting_b200.pipeline import FramePipeline
+    pipe = FramePipeline(yolo, reid)
+
+    def run_e2e(nsteps):
+        """host buffers in, host results out: every step's frames + ROIs are uploaded from pinned memory and its detections +
+        embeddings are read back; uploads of step i+1 overlap the compute of step i (double buffering)"""
+        n_det = n_feat = 0
+        for i in range(nsteps):
+            pipe.submit(host_pool[i % pool_n], rois_np)
+            if pipe.submitted - pipe.collected == 2:
+                det, cnt, feats = pipe.collect()
+                n_det += int(cnt.sum()); n_feat += feats.shape[0]
+        while pipe.collected < pipe.submitted:
+            det, cnt, feats = pipe.collect()
+            n_det += int(cnt.sum()); n_feat += feats.shape[0]
+        return n_det, n_feat
 
     # ROIs resident on the device for the HBM-resident arm
     reid.run(yolo.frames, rois_np)
@@ -218,27 +225,28 @@ def run_ours(a) -> dict:
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    profile_region = os.environ.get("VCB_BENCH_PROFILE", "0") == "1"      # ncu --profile-from-start off: capture only the timed steps
+    if profile_region:
+        torch.cuda.profiler.start()
     e0.record(ys)
     for i in range(a.steps):
         step_device(i)
     e1.record(ys)
     barrier()
+    if profile_region:
+        torch.cuda.profiler.stop()
     ms_dev = e0.elapsed_time(e1) / a.steps
     clocks = sampler.stop()
     det_total = int(yolo.det_count.sum().item())
 
     # end-to-end through host buffers
-    for i in range(max(a.warmup, 1)):
-        step_e2e(i)
+    run_e2e(max(a.warmup, 2))
     barrier()
     t0 = time.perf_counter()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ee0.record(ys)
-    n_det = n_feat = 0
-    for i in range(a.steps):
-        d_, f_ = step_e2e(i)
-        n_det += d_; n_feat += f_
-    ee1.record(rs)
+    ee0.record(pipe.copy_stream)
+    n_det, n_feat = run_e2e(a.steps)
+    ee1.record(ys)
     barrier()
     ms_e2e = max(ee0.elapsed_time(ee1), 1e3 * (time.perf_counter() - t0)) / a.steps
 

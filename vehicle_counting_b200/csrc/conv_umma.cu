@@ -135,40 +135,39 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtenso
       const size_t res_row = (size_t)row * (size_t)p.res_pitch;
       for (int sub = 0; sub < num_sub; ++sub, ++sub_count) {
         const uint32_t stage_buf = out_stage + ((p.out_stage_bufs == 2) ? (sub_count & 1u) : 0u) * kStageOutBytes;
-        if (!p.epi_direct) {
-          if (issuer) {                                    // the store that last used this buffer is drained
-            if (p.out_stage_bufs == 2) tma_store_wait_read<1>();
-            else tma_store_wait_read<0>();
-          }
+        if (!p.epi_direct && p.out_stage_bufs == 1) {          // single staging buffer: drain the previous store first
+          if (issuer) tma_store_wait_read<0>();
           asm volatile("bar.sync 2, 256;" ::: "memory");
         }
         const int col_base = sub * sub_cols + half * my_cols;            // first column (within the N tile) of this thread
+        const int ngroups = (col_base >= p.block_n) ? 0 : ((my_cols == 32 && col_base + 16 < p.block_n) ? 2 : 1);   // warp-uniform
+        // both TMEM loads first, bias (and residual) loads while they are in flight, one wait
+        uint32_t v[2][16];
+        if (ngroups > 0) tmem_ld_x16(t_row + (uint32_t)col_base, v[0]);
+        if (ngroups > 1) tmem_ld_x16(t_row + (uint32_t)(col_base + 16), v[1]);
+        const int n_first = n_tile * p.block_n + col_base;
+        if (ngroups > 0) tmem_ld_wait();
 #pragma unroll
         for (int g16 = 0; g16 < 2; ++g16) {                               // up to two 16-column groups
-          const int col0 = col_base + g16 * 16;
-          if (g16 * 16 >= my_cols || col0 >= p.block_n) continue;         // warp-uniform
-          uint32_t v[16];
-          tmem_ld_x16(t_row + (uint32_t)col0, v);
-          tmem_ld_wait();
-          const int n0 = n_tile * p.block_n + col0;
-          float f[16];
+          if (g16 >= ngroups) continue;
+          const int n0 = n_first + g16 * 16;
+          float fg[16];
           {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 b4 = __ldg(bp + i);
-              f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
-              f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
-              f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
-              f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+              fg[4 * i + 0] = __uint_as_float(v[g16][4 * i + 0]) + b4.x;
+              fg[4 * i + 1] = __uint_as_float(v[g16][4 * i + 1]) + b4.y;
+              fg[4 * i + 2] = __uint_as_float(v[g16][4 * i + 2]) + b4.z;
+              fg[4 * i + 3] = __uint_as_float(v[g16][4 * i + 3]) + b4.w;
             }
           }
-          const bool res_ok = p.res_mode != VCB_RES_NONE && row_ok && n0 < p.cout_store;
-          float rr[16];
-          if (res_ok) {
+          if (p.res_mode != VCB_RES_NONE) {
+            float rr[16];
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              if (n0 + hh * 8 < p.cout_store) {
+              if (row_ok && n0 + hh * 8 < p.cout_store) {
                 const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + res_row + n0 + hh * 8));
                 const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
@@ -182,16 +181,16 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtenso
                 for (int i = 0; i < 8; ++i) rr[hh * 8 + i] = 0.f;
               }
             }
+            if (p.res_mode == VCB_RES_BEFORE_ACT) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) fg[i] = apply_act(fg[i] + rr[i], p.act);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) fg[i] = apply_act(fg[i], p.act) + rr[i];
+            }
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) rr[i] = 0.f;
-          }
-          if (p.res_mode == VCB_RES_BEFORE_ACT) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i] + rr[i], p.act);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.act) + rr[i];
+            for (int i = 0; i < 16; ++i) fg[i] = apply_act(fg[i], p.act);
           }
           if (p.epi_direct) {
             if (row_ok) {
@@ -201,12 +200,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtenso
                 if (nn >= p.cout_store) continue;
                 if (p.out_fp32) {
                   float* o = reinterpret_cast<float*>(p.out) + out_row + nn;
-                  *reinterpret_cast<float4*>(o) = make_float4(f[hh * 8 + 0], f[hh * 8 + 1], f[hh * 8 + 2], f[hh * 8 + 3]);
-                  *reinterpret_cast<float4*>(o + 4) = make_float4(f[hh * 8 + 4], f[hh * 8 + 5], f[hh * 8 + 6], f[hh * 8 + 7]);
+                  *reinterpret_cast<float4*>(o) = make_float4(fg[hh * 8 + 0], fg[hh * 8 + 1], fg[hh * 8 + 2], fg[hh * 8 + 3]);
+                  *reinterpret_cast<float4*>(o + 4) = make_float4(fg[hh * 8 + 4], fg[hh * 8 + 5], fg[hh * 8 + 6], fg[hh * 8 + 7]);
                 } else {
                   __half2 h2[4];
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(f[hh * 8 + 2 * i], f[hh * 8 + 2 * i + 1]);
+                  for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(fg[hh * 8 + 2 * i], fg[hh * 8 + 2 * i + 1]);
                   __half* o = reinterpret_cast<__half*>(p.out) + out_row + nn;
                   *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h2);
                 }
@@ -220,14 +219,14 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtenso
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const uint32_t dst = row_addr + (uint32_t)(((half * 4 + i) ^ sw) << 4);
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(f[4 * i]), "f"(f[4 * i + 1]),
-                             "f"(f[4 * i + 2]), "f"(f[4 * i + 3]) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(fg[4 * i]), "f"(fg[4 * i + 1]),
+                             "f"(fg[4 * i + 2]), "f"(fg[4 * i + 3]) : "memory");
               }
             } else {                     // 16 halves = 2 chunks per 16-column group
               uint32_t h2[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                const __half2 t = __floats2half2_rn(fg[2 * i], fg[2 * i + 1]);
                 h2[i] = *reinterpret_cast<const uint32_t*>(&t);
               }
 #pragma unroll
@@ -241,6 +240,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtenso
         }
         if (!p.epi_direct) {
           fence_proxy_async_smem();                         // staged writes -> visible to the TMA (async proxy)
+          // two buffers: draining every earlier store BEFORE this barrier tells all threads that the other buffer (next
+          // sub-tile's target) is free, so one barrier per sub-tile suffices
+          if (issuer && p.out_stage_bufs == 2) tma_store_wait_read<0>();
           asm volatile("bar.sync 2, 256;" ::: "memory");
           if (issuer) {
             tma_store_2d(&tmap_out, stage_buf, n_tile * p.block_n + sub * sub_cols, m_tile * kBlockM);
@@ -258,7 +260,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtenso
 // Shared-memory carve-up (all offsets from a 1024-byte aligned base):
 //   [num_stages x (A tile 16 KiB | B tile block_n*128 B)] [2 x 16 KiB output staging] [barriers] [tmem slot] [row table]
 template <int A_MODE, int BK>
-__global__ void __launch_bounds__(A_MODE == A_TMA ? kThreadsTma + 32 : kThreadsGather, A_MODE == A_TMA ? 2 : 1)
+__global__ void __launch_bounds__(A_MODE == A_TMA ? kThreadsTma : kThreadsGather, A_MODE == A_TMA ? 2 : 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -856,7 +858,7 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   }
   const int max_ctas = state().num_sms * g.ctas_per_sm;
   const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
-  conv_umma_kernel<A_MODE, BK><<<grid, A_MODE == A_TMA ? (p.split_b ? kThreadsTma + 32 : kThreadsTma) : kThreadsGather, g.smem_bytes, st>>>(ta, tb, to, p);
+  conv_umma_kernel<A_MODE, BK><<<grid, A_MODE == A_TMA ? kThreadsTma : kThreadsGather, g.smem_bytes, st>>>(ta, tb, to, p);
   return check_cuda(cudaGetLastError(), "conv launch");
 }
 
@@ -891,7 +893,7 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   p.out = y;
   p.fault = state().fault_dev;
   p.epi_direct = d.reserved[0] == 1 ? 1 : 0;
-  p.split_b = (d.reserved[0] == 2 && g.a_mode == A_TMA && !g.two_cta && !g.b_resident) ? 1 : 0;
+  p.split_b = 0;   // (a second producer thread for the weight tiles measured no gain; code path kept for experiments only)
   p.b_resident = g.b_resident; p.b_res_bytes = g.b_res_bytes;
   p.dbg_skip_epilogue = d.reserved[0] == 3 ? 1 : 0;
   if (d.reserved[0] == 4) { p.acc_stages = 1; }
