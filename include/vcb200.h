@@ -37,7 +37,9 @@ enum {
   VCB_ERR_FAULT = -4        /* a kernel recorded a pipeline fault (see vcb_last_fault) */
 };
 
-enum { VCB_ACT_NONE = 0, VCB_ACT_SILU = 1, VCB_ACT_RELU = 2 };
+/* VCB_ACT_SILU_TANH: SiLU evaluated as h + h*tanh(h), h = x/2, with tanh.approx.f32 (relative error 2^-11, i.e. the
+ * size of the fp16 rounding of the stored result); half the special-function work of VCB_ACT_SILU (ex2 + rcp) */
+enum { VCB_ACT_NONE = 0, VCB_ACT_SILU = 1, VCB_ACT_RELU = 2, VCB_ACT_SILU_TANH = 3 };
 enum { VCB_RES_NONE = 0, VCB_RES_AFTER_ACT = 1, VCB_RES_BEFORE_ACT = 2 };
 enum { VCB_F16 = 0, VCB_F32 = 1 };
 enum { VCB_A_AUTO = 0, VCB_A_IM2COL_TMA = 1, VCB_A_GATHER = 2, VCB_A_C4 = 3 };
@@ -47,6 +49,15 @@ int vcb_init(int device);                 /* selects device, checks sm_100, reso
 const char* vcb_last_error_string(void);  /* thread-local, never NULL */
 int vcb_last_fault(int32_t out4[4]);      /* host: {code, block, info0, info1} of the last kernel fault */
 int vcb_version(void);
+/* library options (process-wide).  "pdl" = 1: convolution launches carry the programmatic-dependent-launch attribute, so the
+ * set-up of one conv kernel overlaps the tail of the previous kernel on the stream (the kernels order their global-memory
+ * accesses with griddepcontrol.wait); default from $VCB_PDL at vcb_init(), else 0.  Unknown names: VCB_ERR_INVALID / -1. */
+int vcb_set_option(const char* name, int32_t value);
+int vcb_get_option(const char* name);
+/* development aid: "prof" = 1 zeroes and enables per-role cycle counters inside the conv kernel (summed over CTAs: CTA
+ * lifetime, set-up, producer / MMA / epilogue waits and totals, CTAs, tiles); vcb_read_prof synchronises and copies them
+ * to host memory.  Off by default; costs a few clock reads per tile when on. */
+int vcb_read_prof(uint64_t out16[16]);
 
 /* ---- K1: implicit-GEMM convolution on tcgen05 (replaces torch Conv2d+BN+SiLU / ReLU, reference
  *      call sites networks/yolo.py:70 [upstream DetectionModel] and deepsort/deep/model.py:83-95) --- */

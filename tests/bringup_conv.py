@@ -24,7 +24,8 @@ CASES = []
 
 def case(name, **kw):
     base = dict(n=1, h=16, w=16, cin=64, cout=64, k=1, s=1, p=0, act="none", res="none", out="f16", mode="tma",
-                cin_pitch=None, cout_pitch=None, block_n=0, stages=0, epi_direct=False, c4_narrow=False, bk=0, cta_pair=0, a_im2col=False)
+                cin_pitch=None, cout_pitch=None, block_n=0, stages=0, epi_direct=False, c4_narrow=False, bk=0, cta_pair=0, a_im2col=False,
+                pdl=False, one_chain=False, dbg1=0)
     base.update(kw)
     CASES.append((name, base))
 
@@ -104,6 +105,66 @@ case("prof-1x1-96-96-m819k", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=9
 case("prof-3x3-192-192-p4", mode="tma", n=32, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", res="after")
 case("c4-yolo-stem-big", mode="c4", n=4, h=640, w=640, cin=3, cin_pitch=4, cout=48, k=6, s=2, p=2, act="silu")
 
+# specialised-epilogue variants (epi_kind 1..8) on awkward shapes, the generic epilogue forced (epi_direct=6), tanh SiLU, PDL
+case("fast-silu-res-cout40-tail", mode="tma", n=3, h=13, w=13, k=3, p=1, cin=64, cout=40, cout_pitch=48, act="silu", res="after")
+case("fast-tanh-res-cin96-cout192", mode="tma", n=2, h=40, w=40, k=3, p=1, cin=96, cout=192, act="silu_tanh", res="after")
+case("fast-tanh-1x1-cout48", mode="tma", n=2, h=40, w=40, k=1, cin=96, cout=48, cout_pitch=96, act="silu_tanh")
+case("fast-relu-before-2tiles", mode="tma", n=3, h=7, w=7, k=3, p=1, cin=256, cout=512, act="relu", res="before")
+case("fast-none-f16-1x1s2", mode="tma", n=3, h=13, w=13, k=1, s=2, p=0, cin=128, cout=256, act="none")
+case("fast-none-f32-cout255", mode="tma", n=2, h=20, w=20, cin=192, cout=255, cout_pitch=256, out="f32")
+case("generic-silu-res-cin96-cout192", mode="tma", n=2, h=40, w=40, k=3, p=1, cin=96, cout=192, act="silu", res="after", epi_direct=6)
+case("generic-relu-f32", mode="tma", n=3, h=13, w=13, k=3, p=1, cin=64, cout=40, out="f32", act="relu", epi_direct=6)
+case("pdl-3x3-192", mode="tma", n=8, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", res="after", pdl=True)
+case("pdl-1x1-96", mode="tma", n=8, h=80, w=80, k=1, cin=96, cout=96, act="silu", pdl=True)
+case("fast-big-1x1-96", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, act="silu")
+case("fast-big-1x1-96-tanh", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, act="silu_tanh")
+case("fast-big-3x3-192-res", mode="tma", n=64, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", res="after")
+case("fast-big-stem", mode="tma", n=32, h=320, w=320, k=3, p=1, cin=16, cout=48, act="silu")
+case("fast-big-stem-tanh", mode="tma", n=32, h=320, w=320, k=3, p=1, cin=16, cout=48, act="silu_tanh")
+
+# 256-row CTA tiles with two accumulator chains (cta_pair=3 forces them on small shapes; big layers pick them automatically)
+case("m256-3x3-s1", mode="tma", n=2, h=20, w=20, k=3, p=1, cta_pair=3)
+case("m256-3x3-s2-odd", mode="tma", n=3, h=25, w=25, k=3, s=2, p=1, cin=64, cout=128, act="relu", cta_pair=3)
+case("m256-1x1-s2-odd", mode="tma", n=3, h=13, w=13, k=1, s=2, p=0, cin=128, cout=160, cta_pair=3)
+case("m256-cin48-cout48", mode="tma", n=2, h=40, w=40, k=3, p=1, cin=48, cout=48, act="silu", cta_pair=3)
+case("m256-cin96-cout192-res", mode="tma", n=2, h=40, w=40, k=3, p=1, cin=96, cout=192, act="silu", res="after", cta_pair=3)
+case("m256-cout160-f32", mode="tma", n=2, h=20, w=20, cin=128, cout=155, cout_pitch=160, out="f32", cta_pair=3)
+case("m256-cout384-2tiles", mode="tma", n=2, h=20, w=20, k=3, p=1, cin=192, cout=384, act="silu", cta_pair=3)
+case("m256-pitch-slices", mode="tma", n=2, h=20, w=20, k=1, cin=64, cout=64, cin_pitch=128, cout_pitch=192, act="silu", cta_pair=3)
+case("m256-resbefore-relu", mode="tma", n=4, h=13, w=13, k=3, p=1, cin=128, cout=128, act="relu", res="before", cta_pair=3)
+case("m256-bk16-stem", mode="tma", n=2, h=64, w=64, k=3, p=1, cin=16, cout=48, act="silu", cta_pair=3)
+case("m256-bk32-cin96-s2", mode="tma", n=2, h=40, w=40, k=3, s=2, p=1, cin=96, cout=192, act="silu", cta_pair=3)
+case("m256-tiled-1x1-pitch-tail", mode="tma", n=3, h=13, w=13, k=1, cin=64, cout=40, cin_pitch=128, cout_pitch=48, act="relu", cta_pair=3)
+case("m256-tail-272", mode="tma", n=1, h=16, w=17, k=3, p=1, cin=64, cout=96, act="silu_tanh", res="after", cta_pair=3)
+case("m256-reid-l1", mode="tma", n=7, h=25, w=25, k=3, p=1, cin=64, cout=64, act="relu", res="before", cta_pair=3)
+case("m256-stages2", mode="tma", n=2, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=3, stages=2)
+case("auto-big-reid-l1", mode="tma", n=1024, h=25, w=25, k=3, p=1, cin=64, cout=64, act="relu", res="before")
+case("auto-big-reid-l2", mode="tma", n=1024, h=13, w=13, k=3, p=1, cin=128, cout=128, act="relu", res="before")
+case("auto-big-3x3-96", mode="tma", n=32, h=80, w=80, k=3, p=1, cin=96, cout=96, act="silu", res="after")
+case("auto-big-3x3-48", mode="tma", n=16, h=160, w=160, k=3, p=1, cin=48, cout=48, act="silu", res="after")
+case("auto-big-1x1-192", mode="tma", n=64, h=40, w=40, k=1, cin=192, cout=192, act="silu")
+case("m128-big-3x3-192-res", mode="tma", n=64, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", res="after", cta_pair=1)
+case("m128-big-reid-l1", mode="tma", n=1024, h=25, w=25, k=3, p=1, cin=64, cout=64, act="relu", res="before", cta_pair=1)
+case("m128-big-3x3-96", mode="tma", n=32, h=80, w=80, k=3, p=1, cin=96, cout=96, act="silu", res="after", cta_pair=1)
+case("m128-big-1x1-192", mode="tma", n=64, h=40, w=40, k=1, cin=192, cout=192, act="silu", cta_pair=1)
+
+# K-split accumulation chains (auto) against one chain per tile on the small-N layers
+case("kchain-small-n48", mode="tma", n=2, h=40, w=40, k=3, p=1, cin=48, cout=48, act="silu", res="after", dbg1=4)
+case("kchain-small-n64-f32", mode="tma", n=3, h=25, w=25, k=3, p=1, cin=64, cout=64, out="f32", dbg1=4)
+case("kchain-small-n96-1x1", mode="tma", n=2, h=40, w=40, k=1, cin=192, cout=96, act="silu", dbg1=4)
+case("kchain-small-n128-s2", mode="tma", n=3, h=25, w=25, k=3, s=2, p=1, cin=64, cout=128, act="relu", dbg1=4)
+case("kchain-tiny-k", mode="tma", n=2, h=40, w=40, k=1, cin=32, cout=48, act="silu", dbg1=4)
+
+# experiment: CTA pairs (cta_group::2) with two co-resident clusters per SM pair, mainloop only (epi_direct=3 skips the epilogue)
+case("xp-pair2-noepi-192", mode="tma", n=128, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=2, dbg1=5, epi_direct=3)
+case("xp-pair1-noepi-192", mode="tma", n=128, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=2, epi_direct=3)
+case("xp-single-noepi-192", mode="tma", n=128, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=1, epi_direct=3)
+case("xp-pair2-noepi-256", mode="tma", n=512, h=7, w=7, k=3, p=1, cin=256, cout=256, act="relu", cta_pair=2, dbg1=5, epi_direct=3)
+case("xp-single-noepi-256", mode="tma", n=512, h=7, w=7, k=3, p=1, cin=256, cout=256, act="relu", cta_pair=1, epi_direct=3)
+case("xp-pair2-noepi-64", mode="tma", n=1024, h=25, w=25, k=3, p=1, cin=64, cout=64, act="relu", cta_pair=2, dbg1=5, epi_direct=3)
+case("xp-single-noepi-64", mode="tma", n=1024, h=25, w=25, k=3, p=1, cin=64, cout=64, act="relu", cta_pair=1, epi_direct=3)
+case("xp-pair2-192", mode="tma", n=128, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=2, dbg1=5)
+
 
 def run_case(idx: int) -> dict:
     import torch
@@ -117,7 +178,9 @@ def run_case(idx: int) -> dict:
     n, h, w, cin, cout, k, s, p = (c[x] for x in ("n", "h", "w", "cin", "cout", "k", "s", "p"))
     cin_pitch = c["cin_pitch"] or cin
     mode = {"tma": L.A_IM2COL_TMA, "gather": L.A_GATHER, "c4": L.A_C4}[c["mode"]]
-    act = {"none": L.ACT_NONE, "silu": L.ACT_SILU, "relu": L.ACT_RELU}[c["act"]]
+    act = {"none": L.ACT_NONE, "silu": L.ACT_SILU, "relu": L.ACT_RELU, "silu_tanh": L.ACT_SILU_TANH}[c["act"]]
+    if c.get("pdl"):
+        L.check(L.load().vcb_set_option(b"pdl", 1), "set_option")
     res_mode = {"none": L.RES_NONE, "after": L.RES_AFTER_ACT, "before": L.RES_BEFORE_ACT}[c["res"]]
     cout_store = (cout + 7) // 8 * 8
     cout_pitch = c["cout_pitch"] or cout_store
@@ -130,7 +193,7 @@ def run_case(idx: int) -> dict:
     d = ops.make_conv_desc(n, h, w, cin, cout, k, s, p, cin_pitch=cin_pitch, cout_pitch=cout_pitch, act=act,
                            res_mode=res_mode, res_pitch=cout_pitch if res_mode else 0,
                            out_dtype=L.F32 if c["out"] == "f32" else L.F16, a_mode=mode, block_n=c["block_n"], stages=c["stages"],
-                           epi_direct=c["epi_direct"], c4_narrow=c["c4_narrow"], bk=c["bk"], cta_pair=c["cta_pair"], a_im2col=c["a_im2col"])
+                           epi_direct=c["epi_direct"], c4_narrow=c["c4_narrow"], bk=c["bk"], cta_pair=c["cta_pair"], a_im2col=c["a_im2col"], one_chain=c["one_chain"], dbg1=c["dbg1"])
     ho, wo = ops.conv_out_hw(d)
     res_full = (torch.randn(n, ho, wo, cout_pitch, generator=g)).half() if res_mode else None
 
@@ -139,7 +202,7 @@ def run_case(idx: int) -> dict:
     ref = F.conv2d(xr, wt, bias, s, p)
     if res_mode == L.RES_BEFORE_ACT:
         ref = ref + res_full[..., :cout].float().permute(0, 3, 1, 2)
-    if act == L.ACT_SILU:
+    if act in (L.ACT_SILU, L.ACT_SILU_TANH):
         ref = F.silu(ref)
     elif act == L.ACT_RELU:
         ref = F.relu(ref)
@@ -157,6 +220,9 @@ def run_case(idx: int) -> dict:
     ops.conv2d(d, xd, wp, bp, y, residual=resd)
     torch.cuda.synchronize()
     dt = time.time() - t0
+    prof_on = os.environ.get("VCB_PROF", "0") == "1"
+    if prof_on:
+        L.check(L.load().vcb_set_option(b"prof", 1), "set_option(prof)")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
@@ -164,6 +230,19 @@ def run_case(idx: int) -> dict:
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 5 * 1e3
+    prof = None
+    if prof_on:
+        import ctypes
+        buf = (ctypes.c_uint64 * 16)()
+        L.check(L.load().vcb_read_prof(buf), "read_prof")
+        L.load().vcb_set_option(b"prof", 0)
+        names = ["cta_total", "setup", "prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_tmem", "mma_total",
+                 "epi_wait_tmem", "epi_sync_store", "epi_total", "ctas", "tiles"]
+        v = dict(zip(names, [int(x) for x in buf]))
+        ctas = max(v["ctas"], 1)
+        prof = {"ctas_per_launch": ctas / 5, "tiles_per_cta": v["tiles"] / ctas, "cta_cycles": v["cta_total"] / ctas}
+        for nm in names[1:10]:
+            prof[nm + "_frac"] = round(v[nm] / max(v["cta_total"], 1), 3)
     got = y.float().cpu()
     err = (got[..., :cout] - ref).abs()
     scale = ref.abs().max().item()
@@ -186,6 +265,8 @@ def run_case(idx: int) -> dict:
         out["sample_got"] = got.reshape(-1, cout_pitch)[r0, :8].tolist()
         out["sample_ref"] = ref.reshape(-1, cout)[r0, :8].tolist()
     out["fault"] = list(L.last_fault())
+    if prof is not None:
+        out["prof"] = prof
     return out
 
 

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvcb200.so")
 
 VCB_OK = 0
-ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_RELU, ACT_SILU_TANH = 0, 1, 2, 3
 RES_NONE, RES_AFTER_ACT, RES_BEFORE_ACT = 0, 1, 2
 F16, F32 = 0, 1
 A_AUTO, A_IM2COL_TMA, A_GATHER, A_C4 = 0, 1, 2, 3
@@ -78,6 +78,9 @@ _SIGNATURES = {
     "vcb_last_error_string": ([], C.c_char_p),
     "vcb_last_fault": ([C.POINTER(_I32)], _I32),
     "vcb_version": ([], _I32),
+    "vcb_set_option": ([C.c_char_p, _I32], _I32),
+    "vcb_get_option": ([C.c_char_p], _I32),
+    "vcb_read_prof": ([C.POINTER(C.c_uint64)], _I32),
     "vcb_conv_packed_sizes": ([C.POINTER(ConvDesc), C.POINTER(_I64), C.POINTER(_I64)], _I32),
     "vcb_conv_pack_weights": ([C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP], _I32),
     "vcb_conv2d_fwd": ([C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP], _I32),

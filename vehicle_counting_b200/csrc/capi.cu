@@ -1,6 +1,7 @@
 // extern "C" surface of libvcb200.so (declared in include/vcb200.h) + library state + CUDA-graph capture.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -94,7 +95,34 @@ int vcb_init(int device) {
   }
   s.device = device;
   s.initialised = true;
+  if (const char* e_pdl = getenv("VCB_PDL")) s.pdl = atoi(e_pdl) != 0 ? 1 : 0;
   return VCB_OK;
+}
+
+int vcb_set_option(const char* name, int32_t value) {
+  if (!name) return set_error(VCB_ERR_INVALID, "null option name");
+  if (strcmp(name, "pdl") == 0) { state().pdl = value != 0 ? 1 : 0; return VCB_OK; }
+  if (strcmp(name, "prof") == 0) {
+    State& s = state();
+    if (value && s.prof_dev == nullptr) {
+      const cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s.prof_dev), 16 * sizeof(unsigned long long));
+      if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(prof)");
+    }
+    if (s.prof_dev) cudaMemset(s.prof_dev, 0, 16 * sizeof(unsigned long long));
+    s.prof_on = value != 0 ? 1 : 0;
+    return VCB_OK;
+  }
+  return set_error(VCB_ERR_INVALID, "unknown option '%s'", name);
+}
+int vcb_read_prof(uint64_t out16[16]) {
+  State& s = state();
+  if (!out16) return set_error(VCB_ERR_INVALID, "null output");
+  if (!s.prof_dev) { memset(out16, 0, 16 * sizeof(uint64_t)); return VCB_OK; }
+  return check_cuda(cudaMemcpy(out16, s.prof_dev, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost), "cudaMemcpy(prof)");
+}
+int vcb_get_option(const char* name) {
+  if (name && strcmp(name, "pdl") == 0) return state().pdl;
+  return -1;
 }
 
 int vcb_last_fault(int32_t out4[4]) {

@@ -71,12 +71,25 @@ struct ConvParams {
   int b_res_bytes;     // bytes of the resident weight region (multiple of 1024)
   int split_b;         // A_TMA single-CTA: weight tiles are issued by a second producer warp
   int a_tiled;         // A_TMA, 1x1/s1/p0: A is the plain [M][C] matrix -> tiled-mode TMA instead of im2col mode
+  int epi_kind;        // 0: generic epilogue; 1..8: specialised instance (epi_kind_of)
+  int kchains;         // 1, 2 or 4 accumulators per tile: K steps are dealt round-robin to independent accumulation chains
+                       // (dependent tcgen05.mma on ONE accumulator issue ~200 clk apart), the epilogue sums them
+  int cout_pad;        // n_tiles * block_n = length of the packed bias
   const __half* x;
   const float* bias;
   const __half* residual;
   void* out;
   KernelFault* fault;
+  unsigned long long* prof;   // optional role timers (vcb_set_option("prof", 1)): cycles summed over CTAs, see PROF_* below
 };
+
+// role timers (development aid, off unless p.prof != nullptr): where each warp role of the conv kernel waits
+enum { PROF_CTA_TOTAL = 0, PROF_SETUP, PROF_PROD_WAIT_EMPTY, PROF_PROD_TOTAL, PROF_MMA_WAIT_FULL, PROF_MMA_WAIT_TMEM, PROF_MMA_TOTAL,
+       PROF_EPI_WAIT_TMEM, PROF_EPI_SYNC_STORE, PROF_EPI_TOTAL, PROF_CTAS, PROF_TILES, PROF_N };
+__device__ __forceinline__ long long prof_clock(const unsigned long long* prof) { return prof ? clock64() : 0; }
+__device__ __forceinline__ void prof_add(unsigned long long* prof, int slot, long long v) {
+  if (prof) atomicAdd(prof + slot, (unsigned long long)v);
+}
 
 struct RowInfo {     // one output pixel of the current M tile (gather modes)
   int img_base;      // n * H * W
@@ -85,6 +98,12 @@ struct RowInfo {     // one output pixel of the current M tile (gather modes)
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == VCB_ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));   // ex2.approx + rcp.approx: ~1e-6 relative
+  if (act == VCB_ACT_SILU_TANH) {      // x*sigmoid(x) = h + h*tanh(h), h = x/2: ONE MUFU op per element instead of two
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+  }
   if (act == VCB_ACT_RELU) return fmaxf(v, 0.0f);
   return v;
 }
@@ -168,7 +187,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtenso
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               if (row_ok && n0 + hh * 8 < p.cout_store) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + res_row + n0 + hh * 8));
+                const uint4 rv = __ldcg(reinterpret_cast<const uint4*>(p.residual + res_row + n0 + hh * 8));
                 const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -257,16 +276,248 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtenso
     if (!p.epi_direct && issuer) tma_store_wait_all<0>();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Specialised epilogue (single-CTA TMA kernel, staged TMA store): activation / residual mode / output type are
+// template parameters, the bias comes from shared memory (broadcast reads), SiLU is 5 (ex2 + rcp) or 3 (tanh)
+// instructions per element with no range fix-ups -- ~6 thread instructions per output instead of ~23 in the generic
+// epilogue (ncu, profiles/r01_ncu_*): small-K layers (1x1 convs, stems) are bound by this loop, not by the MMAs.
+// ---------------------------------------------------------------------------------------------------------------
+template <int ACT>
+__device__ __forceinline__ float act_fast(float v) {
+  if (ACT == VCB_ACT_SILU) {             // v * 1/(1 + 2^(-v*log2e)); 1+e is in [1, inf] so rcp needs no scaling
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return v * r;
+  }
+  if (ACT == VCB_ACT_SILU_TANH) {
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+  }
+  if (ACT == VCB_ACT_RELU) return fmaxf(v, 0.0f);
+  return v;
+}
+
+template <int ACT, int RES, bool F32OUT, bool M256>
+__device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CUtensorMap* tmap_out_ptr, const CUtensorMap* tmap_res_ptr,
+                                                   uint32_t tmem_base, uint32_t out_stage, uint32_t bias_smem, uint32_t res_bar0,
+                                                   uint32_t tmem_full0, uint32_t tmem_empty0) {
+  // Residual (RES != NONE): the residual sub-tile is fetched by TMA INTO the staging buffer (same 128-byte-swizzled layout
+  // as the output sub-tile), every thread reads its own 16-byte chunks, adds, and writes the result back in place.  Per-thread
+  // global loads of a row-per-lane layout touch 32 lines per request and, with no L1 left beside ~220 KiB of shared memory,
+  // cost ~17k cycles per 128x192 tile (role timers, profiles/r01_role_timers.md); the TMA fetch is coalesced and asynchronous.
+  // M256 = false: the CTA tile is 128 rows; warp (q = warp & 3, half = warp >> 2) drains rows [32q, 32q+32) and one
+  //               half of the columns of each staged sub-tile.
+  // M256 = true:  the CTA tile is 256 rows in two accumulators (chains); warps 0-3 drain chain 0 (rows 0-127), warps 4-7
+  //               chain 1 (rows 128-255), every thread all columns of the sub-tile in two passes of 32 (fp16) / 16 (fp32).
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q = warp & 3;                      // TMEM lane quarter this warp may read
+  const int hi = warp >> 2;                    // column half (M256 = false) or accumulator chain (M256 = true)
+  constexpr int TILE_M = M256 ? 256 : 128;
+  const int row_in_tile = (M256 ? hi * 128 : 0) + q * 32 + lane;
+  constexpr int SUB_COLS = F32OUT ? 32 : 64;   // columns per staged sub-tile (128 bytes per row)
+  constexpr int MY_COLS = SUB_COLS / 2;        // columns per thread per pass: 32 (fp16) or 16 (fp32)
+  constexpr int NG = MY_COLS / 16;             // 16-column groups per pass
+  constexpr int PASSES = M256 ? 2 : 1;
+  constexpr uint32_t STAGE_BYTES = (uint32_t)TILE_M * 128u;
+  const int num_sub = (p.block_n + SUB_COLS - 1) / SUB_COLS;
+  const bool issuer = threadIdx.x == 0;
+  const uint32_t row_off = (uint32_t)row_in_tile * 128u;
+  const int sw = row_in_tile & 7;
+  const bool two_bufs = p.out_stage_bufs == 2;
+  const uint32_t acc_stride = (uint32_t)p.block_n * (M256 ? 2u : (uint32_t)p.kchains);
+  const int kchains = M256 ? 1 : p.kchains;
+  uint32_t tile_iter = 0, sub_count = 0;
+  long long t_wait = 0, t_sync = 0;
+  const long long t_begin = prof_clock(issuer ? p.prof : nullptr);
+  if (RES != VCB_RES_NONE && issuer && (int)blockIdx.x < p.num_tiles) {      // residual of the first sub-tile
+    const int mt0 = (int)blockIdx.x / p.n_tiles, nt0 = (int)blockIdx.x - mt0 * p.n_tiles;
+    mbar_arrive_expect_tx(res_bar0, STAGE_BYTES);
+    tma_load_2d(tmap_res_ptr, res_bar0, out_stage, nt0 * p.block_n, mt0 * TILE_M);
+  }
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
+    const int m_tile = tile / p.n_tiles;
+    const int n_tile = tile - m_tile * p.n_tiles;
+    const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
+    const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
+    const long long tw0 = prof_clock(issuer ? p.prof : nullptr);
+    mbar_wait(tmem_full0 + 8u * acc, acc_ph, p.fault, FAULT_TMEM_FULL_WAIT, (int)acc);
+    t_wait += prof_clock(issuer ? p.prof : nullptr) - tw0;
+    tcgen05_fence_after();
+    const int row = m_tile * TILE_M + row_in_tile;
+    const bool row_ok = row < p.M;
+    const uint32_t t_row = tmem_base + acc * acc_stride + (M256 ? (uint32_t)(hi * p.block_n) : 0u) + ((uint32_t)(q * 32) << 16);
+    const int n_base = n_tile * p.block_n;
+    (void)row; (void)row_ok;
+    for (int sub = 0; sub < num_sub; ++sub, ++sub_count) {
+      const uint32_t buf_idx = two_bufs ? (sub_count & 1u) : 0u;
+      const uint32_t stage_buf = out_stage + buf_idx * STAGE_BYTES;
+      if (RES != VCB_RES_NONE) {
+        // the residual sub-tile was requested one sub-tile ago (the request waited for the buffer's previous store)
+        mbar_wait(res_bar0 + 8u * buf_idx, (two_bufs ? (sub_count >> 1) : sub_count) & 1u, p.fault, FAULT_FULL_WAIT, 400 + (int)buf_idx);
+      } else if (!two_bufs) {                            // single staging buffer: drain the previous store first
+        if (issuer) tma_store_wait_read<0>();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+#pragma unroll
+      for (int pass = 0; pass < PASSES; ++pass) {
+        const int colhalf = M256 ? pass : hi;
+        const int col_base = sub * SUB_COLS + colhalf * MY_COLS;         // first column (within the N tile) of this pass
+        const int ngroups = (col_base >= p.block_n) ? 0 : ((NG == 2 && col_base + 16 < p.block_n) ? 2 : 1);   // warp-uniform
+        uint32_t v[NG][16];
+        if (ngroups > 0) tmem_ld_x16(t_row + (uint32_t)col_base, v[0]);
+        if (NG == 2 && ngroups > 1) tmem_ld_x16(t_row + (uint32_t)(col_base + 16), v[NG - 1]);
+        if (kchains > 1 && ngroups > 0) {                  // sum the K chains (fp32)
+          for (int c = 1; c < kchains; ++c) {
+            uint32_t w[NG][16];
+            tmem_ld_x16(t_row + (uint32_t)(c * p.block_n + col_base), w[0]);
+            if (NG == 2 && ngroups > 1) tmem_ld_x16(t_row + (uint32_t)(c * p.block_n + col_base + 16), w[NG - 1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+              if (g < ngroups) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[g][i] = __float_as_uint(__uint_as_float(v[g][i]) + __uint_as_float(w[g][i]));
+              }
+          }
+        }
+        uint4 rv[NG][2];
+        if (RES != VCB_RES_NONE) {                         // this thread's own chunks of the staged residual sub-tile
+#pragma unroll
+          for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t src = stage_buf + row_off + (uint32_t)(((colhalf * 4 + g * 2 + hh) ^ sw) << 4);
+              if (g < ngroups)
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv[g][hh].x), "=r"(rv[g][hh].y), "=r"(rv[g][hh].z), "=r"(rv[g][hh].w) : "r"(src));
+              else
+                rv[g][hh] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        if (ngroups > 0) tmem_ld_wait();
+        if (sub == num_sub - 1 && pass == PASSES - 1) {    // accumulator fully read: hand it back before the math / stores
+          tcgen05_fence_before();
+          mbar_arrive(tmem_empty0 + 8u * acc);
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          if (g >= ngroups) continue;
+          const uint32_t b_addr = bias_smem + (uint32_t)(n_base + col_base + g * 16) * 4u;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float b0, b1, b2, b3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(b_addr + 16u * i));
+            f[4 * i + 0] = __uint_as_float(v[g][4 * i + 0]) + b0;
+            f[4 * i + 1] = __uint_as_float(v[g][4 * i + 1]) + b1;
+            f[4 * i + 2] = __uint_as_float(v[g][4 * i + 2]) + b2;
+            f[4 * i + 3] = __uint_as_float(v[g][4 * i + 3]) + b3;
+          }
+          if (RES != VCB_RES_NONE) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv[g][hh]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 t = __half22float2(rh[i]);
+                if (RES == VCB_RES_BEFORE_ACT) {
+                  f[hh * 8 + 2 * i] = act_fast<ACT>(f[hh * 8 + 2 * i] + t.x);
+                  f[hh * 8 + 2 * i + 1] = act_fast<ACT>(f[hh * 8 + 2 * i + 1] + t.y);
+                } else {
+                  f[hh * 8 + 2 * i] = act_fast<ACT>(f[hh * 8 + 2 * i]) + t.x;
+                  f[hh * 8 + 2 * i + 1] = act_fast<ACT>(f[hh * 8 + 2 * i + 1]) + t.y;
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = act_fast<ACT>(f[i]);
+          }
+          // staged row = 128 bytes; this pass owns 16-byte chunks [colhalf*4, colhalf*4+4); 128-byte swizzle
+          const uint32_t row_addr = stage_buf + row_off;
+          if (F32OUT) {            // 16 floats = 4 chunks
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t dst = row_addr + (uint32_t)(((colhalf * 4 + i) ^ sw) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(f[4 * i]), "f"(f[4 * i + 1]), "f"(f[4 * i + 2]),
+                           "f"(f[4 * i + 3]) : "memory");
+            }
+          } else {                 // 16 halves = 2 chunks per 16-column group
+            uint32_t h2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+              h2[i] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint32_t dst = row_addr + (uint32_t)(((colhalf * 4 + g * 2 + i) ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(h2[4 * i]), "r"(h2[4 * i + 1]), "r"(h2[4 * i + 2]),
+                           "r"(h2[4 * i + 3]) : "memory");
+            }
+          }
+        }
+      }
+      fence_proxy_async_smem();                         // staged writes -> visible to the TMA (async proxy)
+      const long long ts0 = prof_clock(issuer ? p.prof : nullptr);
+      if (issuer && two_bufs) tma_store_wait_read<0>();   // the other buffer (next sub-tile's target) is free after the barrier
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (issuer) {
+        tma_store_2d(tmap_out_ptr, stage_buf, n_base + sub * SUB_COLS, m_tile * TILE_M);
+        tma_store_commit();
+        if (RES != VCB_RES_NONE) {                        // request the residual of the next sub-tile (maybe of the next tile)
+          int nt = tile, nsub = sub + 1;
+          if (nsub == num_sub) { nsub = 0; nt = tile + (int)gridDim.x; }
+          if (nt < p.num_tiles) {
+            if (!two_bufs) tma_store_wait_read<0>();        // same buffer: the store just issued must have read it
+            const int nm = nt / p.n_tiles, nn = nt - nm * p.n_tiles;
+            const uint32_t nb = two_bufs ? ((sub_count + 1u) & 1u) : 0u;
+            mbar_arrive_expect_tx(res_bar0 + 8u * nb, STAGE_BYTES);
+            tma_load_2d(tmap_res_ptr, res_bar0 + 8u * nb, out_stage + nb * STAGE_BYTES, nn * p.block_n + nsub * SUB_COLS, nm * TILE_M);
+          }
+        }
+      }
+      t_sync += prof_clock(issuer ? p.prof : nullptr) - ts0;
+    }
+  }
+  if (issuer) tma_store_wait_all<0>();
+  if (issuer && p.prof) {
+    prof_add(p.prof, PROF_EPI_WAIT_TMEM, t_wait);
+    prof_add(p.prof, PROF_EPI_SYNC_STORE, t_sync);
+    prof_add(p.prof, PROF_EPI_TOTAL, clock64() - t_begin);
+    prof_add(p.prof, PROF_TILES, tile_iter);
+  }
+}
+
+// epilogue variants with a specialised instance; anything else runs the generic conv_epilogue
+__host__ __device__ constexpr int epi_kind_of(int act, int res, int f32) {
+  return f32 ? ((act == VCB_ACT_NONE && res == VCB_RES_NONE) ? 7 : 0)
+             : (act == VCB_ACT_SILU ? (res == VCB_RES_NONE ? 1 : (res == VCB_RES_AFTER_ACT ? 2 : 0))
+                : act == VCB_ACT_SILU_TANH ? (res == VCB_RES_NONE ? 3 : (res == VCB_RES_AFTER_ACT ? 4 : 0))
+                : act == VCB_ACT_RELU ? (res == VCB_RES_NONE ? 5 : (res == VCB_RES_BEFORE_ACT ? 6 : 0))
+                : (res == VCB_RES_NONE ? 8 : 0));
+}
+
 // Shared-memory carve-up (all offsets from a 1024-byte aligned base):
 //   [num_stages x (A tile 16 KiB | B tile block_n*128 B)] [2 x 16 KiB output staging] [barriers] [tmem slot] [row table]
-template <int A_MODE, int BK>
-__global__ void __launch_bounds__(A_MODE == A_TMA ? kThreadsTma : kThreadsGather, A_MODE == A_TMA ? 2 : 1)
+// M256 (A_TMA only): the CTA tile is 256 output pixels x N held in TWO accumulators ("chains": rows 0-127 and 128-255).
+// Every weight tile that reaches shared memory feeds both chains, so the L2 -> SM weight traffic per output is halved
+// (the whole path is bound by the ~6300 B/clk chip-wide L2 throughput), and the two independent
+// accumulation chains keep the tensor pipe busy from ONE resident CTA that owns all of the SM's shared memory.
+template <int A_MODE, int BK, bool M256>
+__global__ void __launch_bounds__(A_MODE == A_TMA ? kThreadsTma : kThreadsGather, (A_MODE == A_TMA && !M256) ? 2 : 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, const ConvParams p) {
+  static_assert(!M256 || A_MODE == A_TMA, "256-row tiles exist for the TMA path only");
+  constexpr int kTileM = M256 ? 2 * kBlockM : kBlockM;
+  constexpr uint32_t kATile = (uint32_t)kTileM * kBlockK * 2;        // bytes of A per pipeline stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
-  const uint32_t stage_bytes = kATileBytes + (p.b_resident ? 0u : b_tile_bytes);
+  const uint32_t stage_bytes = kATile + (p.b_resident ? 0u : b_tile_bytes);
   const uint32_t b_res = smem_base + (uint32_t)p.num_stages * stage_bytes;              // resident weights (may be empty)
   const uint32_t out_stage = b_res + (uint32_t)p.b_res_bytes;                             // 1024-aligned
   const uint32_t bars = out_stage + (uint32_t)p.out_stage_bytes;                          // 8-byte aligned
@@ -276,14 +527,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   auto tmem_empty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
   const uint32_t bres_bar = tmem_slot + 8u;          // second half of the 16-byte slot region
+  const uint32_t res_bar0 = tmem_slot + 16u;         // 2 residual-arrival barriers (TMA path: the gather row table is unused)
   // generic pointers to the same locations (for plain loads/stores)
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   uint8_t* tail_gen = smem_gen + (size_t)p.num_stages * stage_bytes + p.b_res_bytes + p.out_stage_bytes + 8 * (2 * kMaxStages + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_gen);
   RowInfo* rows = reinterpret_cast<RowInfo*>(tail_gen + 16);
+  const uint32_t bias_smem = tmem_slot + 16u + (uint32_t)(kBlockM * sizeof(RowInfo));    // fp32 [cout_pad], 16-byte aligned
+  float* bias_gen = reinterpret_cast<float*>(tail_gen + 16 + kBlockM * sizeof(RowInfo));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (p.epi_kind != 0)        // the packed bias is a constant of the layer: staged once, read as smem broadcasts
+    for (int i = threadIdx.x; i < p.cout_pad; i += blockDim.x) bias_gen[i] = __ldg(p.bias + i);
+
+  // Programmatic dependent launch: the next kernel of the stream may start its own set-up (barrier init, TMEM
+  // allocation, tensor-map prefetch) on SMs this grid no longer fills; it blocks in griddep_wait() until this grid
+  // has completed and flushed.  Both instructions are no-ops for a normally serialised launch.
+  griddep_launch_dependents();
+  const long long t_cta0 = prof_clock(p.prof);
 
   if (threadIdx.x == 0) {
     const uint32_t full_count = (A_MODE == A_TMA) ? (p.split_b ? 2u : 1u) : (1u + kGatherThreads);
@@ -296,12 +558,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(tmem_empty_bar(a), kNumEpilogueThreads);
     }
     mbar_init(bres_bar, 1);
+    if (A_MODE == A_TMA) { mbar_init(res_bar0, 1); mbar_init(res_bar0 + 8u, 1); }
     fence_mbar_init();
   }
   if (warp == kProducerWarp && lane == 0) {
     if (A_MODE == A_TMA) tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (!p.epi_direct) tma_prefetch_desc(&tmap_out);
+    if (A_MODE == A_TMA && p.epi_kind != 0 && p.res_mode != VCB_RES_NONE) tma_prefetch_desc(&tmap_res);
   }
   if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -311,10 +575,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_wait();      // everything below may read what earlier kernels of the stream wrote (and overwrite what they read)
+  if (threadIdx.x == 0 && p.prof) { prof_add(p.prof, PROF_SETUP, clock64() - t_cta0); prof_add(p.prof, PROF_CTAS, 1); }
 
   if (warp == kProducerWarp) {
     // ======================= TMA producer (one thread) =======================
     if (lane == 0) {
+      long long t_w = 0;
+      const long long t_b = prof_clock(p.prof);
       uint32_t it = 0;
       if (A_MODE == A_TMA && p.b_resident && (int)blockIdx.x < p.num_tiles) {
         // small layers: every packed weight chunk is loaded once per CTA and stays put
@@ -326,7 +594,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         int cw = 0, ch = 0, cn = 0;
         if (A_MODE == A_TMA) {
-          const int m0 = m_tile * kBlockM;
+          const int m0 = m_tile * kTileM;
           cn = m0 / p.PQ;
           const int rem = m0 - cn * p.PQ;
           const int p0 = rem / p.Q, q0 = rem - p0 * p.Q;
@@ -334,20 +602,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ch = p0 * p.stride - p.pad;
         }
         int r = 0, s = 0, c = 0, kidx = 0;
-        constexpr uint32_t a_chunk = (uint32_t)(kBlockM * BK * 2);
+        constexpr uint32_t a_chunk = (uint32_t)(kTileM * BK * 2);
         const uint32_t b_chunk = (uint32_t)(p.block_n * BK * 2);
         constexpr int G = kBlockK / BK;
         for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
           const int st = it % p.num_stages;
           const uint32_t ph = (it / p.num_stages) & 1u;
+          const long long tw = prof_clock(p.prof);
           mbar_wait(empty_bar(st), ph ^ 1u, p.fault, FAULT_EMPTY_WAIT, st);
+          t_w += prof_clock(p.prof) - tw;
           const uint32_t a_dst = smem_base + (uint32_t)st * stage_bytes;
-          const uint32_t b_dst = a_dst + kATileBytes;
+          const uint32_t b_dst = a_dst + kATile;
           const int nch = (G == 1) ? 1 : min(G, p.total_chunks - kit * G);
           if (A_MODE == A_TMA) {
             mbar_arrive_expect_tx(full_bar(st), (uint32_t)nch * ((p.split_b || p.b_resident) ? a_chunk : a_chunk + b_chunk));
             for (int g = 0; g < nch; ++g, ++kidx) {
-              if (p.a_tiled) tma_load_2d(&tmap_a, full_bar(st), a_dst + (uint32_t)g * a_chunk, c * BK, m_tile * kBlockM);
+              if (p.a_tiled) tma_load_2d(&tmap_a, full_bar(st), a_dst + (uint32_t)g * a_chunk, c * BK, m_tile * kTileM);
               else tma_load_im2col_4d(&tmap_a, full_bar(st), a_dst + (uint32_t)g * a_chunk, c * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
               if (!p.split_b && !p.b_resident)
                 tma_load_2d(&tmap_b, full_bar(st), b_dst + (uint32_t)g * b_chunk, kidx * BK, n_tile * p.block_n);
@@ -359,12 +629,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
       }
+      if (p.prof) { prof_add(p.prof, PROF_PROD_WAIT_EMPTY, t_w); prof_add(p.prof, PROF_PROD_TOTAL, clock64() - t_b); }
     }
   } else if (warp == kMmaWarp) {
     // ======================= MMA issuer (one thread) =======================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16((uint32_t)p.block_n);
-      constexpr uint32_t a_chunk = (uint32_t)(kBlockM * BK * 2);
+      constexpr uint32_t a_chunk = (uint32_t)(kTileM * BK * 2);
+      constexpr uint32_t a_chain = (uint32_t)(kBlockM * BK * 2);                     // chain 1 = rows 128..255 of each chunk
       const uint32_t b_chunk = (uint32_t)(p.block_n * BK * 2);
       constexpr uint32_t sbo = (uint32_t)(8 * BK * 2);                               // 8 rows of one swizzle row each
       constexpr uint32_t layout_type = BK == 64 ? 2u : (BK == 32 ? 4u : 6u);       // SWIZZLE_128B / 64B / 32B
@@ -373,17 +645,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // descriptor high words are loop invariants; only the 14-bit start-address field changes
       const uint64_t desc_hi = umma_desc_kmajor(0, sbo, layout_type);
       uint32_t it = 0, tile_iter = 0;
+      long long t_wf = 0, t_wt = 0;
+      const long long t_b = prof_clock(p.prof);
       if (p.b_resident && (int)blockIdx.x < p.num_tiles) mbar_wait(bres_bar, 0u, p.fault, FAULT_FULL_WAIT, 300);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
         const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
         const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
+        const long long tw1 = prof_clock(p.prof);
         mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u, p.fault, FAULT_TMEM_EMPTY_WAIT, (int)acc);
+        t_wt += prof_clock(p.prof) - tw1;
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.block_n;
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.block_n * (M256 ? 2u : (uint32_t)p.kchains);
+        uint32_t ks = 0;                                  // K=16 steps issued for this tile
+        const uint32_t chain_mask = (uint32_t)p.kchains - 1u;
         for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
           const int st = it % p.num_stages;
           const uint32_t ph = (it / p.num_stages) & 1u;
+          const long long tw2 = prof_clock(p.prof);
           mbar_wait(full_bar(st), ph, p.fault, FAULT_FULL_WAIT, st);
+          t_wf += prof_clock(p.prof) - tw2;
           tcgen05_fence_after();
           const uint32_t a_addr = smem_base + (uint32_t)st * stage_bytes;
           const int nch = (G == 1) ? 1 : min(G, p.total_chunks - kit * G);
@@ -391,12 +671,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int g = 0; g < G; ++g) {
             if (g < nch) {
               const uint64_t a_desc = desc_hi | (uint64_t)(((a_addr + (uint32_t)g * a_chunk) & 0x3FFFF) >> 4);
-              const uint32_t b_addr = p.b_resident ? b_res + (uint32_t)(kit * G + g) * b_chunk : a_addr + kATileBytes + (uint32_t)g * b_chunk;
+              const uint32_t b_addr = p.b_resident ? b_res + (uint32_t)(kit * G + g) * b_chunk : a_addr + kATile + (uint32_t)g * b_chunk;
               const uint64_t b_desc = desc_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
 #pragma unroll
               for (int k = 0; k < ksteps; ++k) {
                 // +32 bytes per UMMA_K step inside the swizzle row: +2 in the (addr >> 4) field
-                umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kit | g | k) != 0 ? 1u : 0u);
+                if (M256) {    // two row chains: rows 0..127 and 128..255 of the same chunk against the same weight tile
+                  umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kit | g | k) != 0 ? 1u : 0u);
+                  umma_f16(d_tmem + (uint32_t)p.block_n, a_desc + (uint64_t)((a_chain >> 4) + 2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                           (kit | g | k) != 0 ? 1u : 0u);
+                } else {       // K chains: step ks accumulates into accumulator ks % kchains
+                  umma_f16(d_tmem + (ks & chain_mask) * (uint32_t)p.block_n, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                           ks > chain_mask ? 1u : 0u);
+                  ++ks;
+                }
               }
             }
           }
@@ -404,12 +692,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (kit == p.num_k_iters - 1) umma_commit(tmem_full_bar(acc));
         }
       }
+      if (p.prof) { prof_add(p.prof, PROF_MMA_WAIT_FULL, t_wf); prof_add(p.prof, PROF_MMA_WAIT_TMEM, t_wt); prof_add(p.prof, PROF_MMA_TOTAL, clock64() - t_b); }
     }
   } else if (warp < kEpilogueWarps) {
-    conv_epilogue<false>(p, &tmap_out, tmem_base, out_stage, tmem_full_bar(0), tmem_empty_bar(0), blockIdx.x, gridDim.x, 0);
+#define VCB_EPI_CASE(K, ACT, RES, F32) \
+    case K: conv_epilogue_fast<ACT, RES, F32, M256>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), tmem_empty_bar(0)); break;
+    switch (A_MODE == A_TMA ? p.epi_kind : 0) {
+      VCB_EPI_CASE(1, VCB_ACT_SILU, VCB_RES_NONE, false)
+      VCB_EPI_CASE(2, VCB_ACT_SILU, VCB_RES_AFTER_ACT, false)
+      VCB_EPI_CASE(3, VCB_ACT_SILU_TANH, VCB_RES_NONE, false)
+      VCB_EPI_CASE(4, VCB_ACT_SILU_TANH, VCB_RES_AFTER_ACT, false)
+      VCB_EPI_CASE(5, VCB_ACT_RELU, VCB_RES_NONE, false)
+      VCB_EPI_CASE(6, VCB_ACT_RELU, VCB_RES_BEFORE_ACT, false)
+      VCB_EPI_CASE(7, VCB_ACT_NONE, VCB_RES_NONE, true)
+      VCB_EPI_CASE(8, VCB_ACT_NONE, VCB_RES_NONE, false)
+      default:
+        if (!M256) conv_epilogue<false>(p, &tmap_out, tmem_base, out_stage, tmem_full_bar(0), tmem_empty_bar(0), blockIdx.x, gridDim.x, 0);
+    }
+#undef VCB_EPI_CASE
   } else if (A_MODE == A_TMA) {
     // ======================= optional second TMA producer (warp 10): weight tiles =======================
-    if (p.split_b && warp == kGatherWarp0 && lane == 0) {
+    if (!M256 && p.split_b && warp == kGatherWarp0 && lane == 0) {
       const uint32_t b_chunk = (uint32_t)(p.block_n * BK * 2);
       constexpr int G = kBlockK / BK;
       uint32_t it = 0;
@@ -521,6 +824,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tcgen05_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (threadIdx.x == 0 && p.prof) prof_add(p.prof, PROF_CTA_TOTAL, clock64() - t_cta0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -532,7 +836,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // accumulator on the leader's tmem_empty barrier.  A operand: im2col TMA only.
 // ---------------------------------------------------------------------------------------------------------------
 template <int BK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTma, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTma, 2)
 conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -556,6 +860,7 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
+  griddep_launch_dependents();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
@@ -581,6 +886,7 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   cluster_sync_all();                                   // peers' barriers exist before any remote arrive / TMA signal
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_wait();
 
   if (warp == kProducerWarp) {
     if (lane == 0) {
@@ -700,6 +1006,10 @@ struct ConvGeom {
   int out_bufs;         // staged output sub-tiles in flight (1 or 2)
   int ctas_per_sm;      // 1, or 2 co-resident persistent CTAs for narrow-N layers (each <= 110 KiB smem, <= 256 TMEM columns)
   int two_cta;          // CTA-pair kernel (cta_group::2)
+  int m256;             // 256-row CTA tiles, two accumulator chains, one CTA per SM
+  int tile_m;           // 128 or 256
+  int epi_kind;         // specialised epilogue instance (0 = generic)
+  int kchains;          // K-split accumulation chains per tile (1, 2, 4)
   int b_resident, b_res_bytes;
   size_t smem_bytes;
 };
@@ -766,19 +1076,57 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
   // opt-in (reserved[3] == 2); reserved[3] == 1 forces the single-CTA kernel.
   g.two_cta = (g.a_mode == A_TMA && g.m_tiles >= 2 && d.reserved[3] == 2) ? 1 : 0;
   if (d.reserved[3] == 2 && !g.two_cta) return set_error(VCB_ERR_INVALID, "conv: the CTA-pair kernel needs the TMA path and >= 2 M tiles");
+  // specialised epilogue: single-CTA TMA kernel with the staged TMA store (any debug value in reserved[0] forces the generic one)
+  g.epi_kind = (g.a_mode == A_TMA && !g.two_cta && d.reserved[0] == 0) ? epi_kind_of(d.act, d.res_mode, d.out_dtype == VCB_F32 ? 1 : 0) : 0;
+  const size_t b_total = (size_t)g.total_chunks * g.block_n * g.bk * 2;
+  const size_t tail0 = 1024 /*align slack*/ + 8 * (2 * kMaxStages + 4) + 16 + kBlockM * sizeof(RowInfo) + (size_t)g.cout_pad * 4 + 64;
+  g.m256 = 0; g.tile_m = kBlockM; g.b_resident = 0; g.b_res_bytes = 0; g.kchains = 1;
+  int chosen = 0;
+  // ---- 256-row tiles (two accumulator chains, one CTA per SM): halves the weight bytes each SM pulls from L2 per output.
+  // Needs the specialised epilogue, N <= 192 (three 56 KiB stages must fit) and at least two waves of 256-row tiles
+  // (reserved[3] == 3 forces it, == 1 forbids it).
+  {
+    const bool want = g.a_mode == A_TMA && !g.two_cta && g.epi_kind != 0 && g.block_n <= 192 && d.reserved[3] != 1 &&
+                      d.reserved[3] == 3;     // opt-in: measured at or below the two-CTA 128-row mode on every layer shape
+    if (d.reserved[3] == 3 && !want) return set_error(VCB_ERR_INVALID, "conv: 256-row tiles need the TMA path, a specialised epilogue and N <= 192");
+    if (want) {
+      const size_t budget = 227 * 1024;
+      const size_t stage_out = 2 * (size_t)kStageOutBytes;                  // 256 rows x 128 B
+      for (int res = 1; res >= 0 && !chosen; --res) {
+        // resident weights (one N tile): the packed B is loaded once per CTA and no weight tile travels with the stages
+        if (res && !(g.n_tiles == 1 && b_total <= 112 * 1024)) continue;
+        const size_t b_res = res ? (b_total + 1023) / 1024 * 1024 : 0;
+        const size_t stage_bytes = 2 * (size_t)kATileBytes + (res ? 0 : (size_t)g.block_n * 128);
+        for (int bufs = 2; bufs >= 1 && !chosen; --bufs) {
+          const size_t fixed = tail0 + b_res + (size_t)bufs * stage_out;
+          if (budget < fixed + 3 * stage_bytes) continue;
+          int stages = (int)((budget - fixed) / stage_bytes);
+          if (stages > kMaxStages) stages = kMaxStages;
+          if (d.stages != 0 && d.stages < stages) stages = d.stages;
+          if (stages < 2) continue;
+          if (bufs == 2 && stages < 4 && budget >= tail0 + b_res + stage_out + (size_t)(stages + 1) * stage_bytes) continue;   // prefer one more stage
+          const int acc = (4 * g.block_n <= 512) ? 2 : 1;
+          int pow2 = 32;
+          while (pow2 < acc * 2 * g.block_n) pow2 <<= 1;
+          g.m256 = 1; g.tile_m = 2 * kBlockM; g.ctas_per_sm = 1; g.acc_stages = acc; g.tmem_cols = pow2; g.stages = stages; g.out_bufs = bufs;
+          g.b_resident = res; g.b_res_bytes = (int)b_res;
+          g.smem_bytes = fixed + (size_t)stages * stage_bytes;
+          chosen = 1;
+        }
+      }
+    }
+  }
+  if (!chosen) {
   // resident weights: one N tile and a packed B of at most 48 KiB stay in shared memory for the whole kernel
   // (measured: pays off together with two CTAs per SM because it shrinks the per-stage footprint to the A tile)
-  const size_t b_total = (size_t)g.total_chunks * g.block_n * g.bk * 2;
   g.b_resident = (g.a_mode == A_TMA && !g.two_cta && g.n_tiles == 1 && b_total <= 48 * 1024 && g.m_tiles > 148 && d.reserved[0] != 5) ? 1 : 0;
   g.b_res_bytes = g.b_resident ? (int)((b_total + 1023) / 1024 * 1024) : 0;
   const size_t stage_bytes = (size_t)kATileBytes + (g.b_resident ? 0 : (size_t)g.block_n * (g.two_cta ? 64 : 128));
-  const size_t tail = 1024 /*align slack*/ + g.b_res_bytes + 8 * (2 * kMaxStages + 4) + 16 + kBlockM * sizeof(RowInfo) + 64;
+  const size_t tail = tail0 + g.b_res_bytes;
   const int min_stages = (g.a_mode == A_TMA) ? 2 : kGatherLag + 2;
-  // Dependent tcgen05.mma on one accumulator issue ~200 cycles apart (measured), so one CTA cannot keep the tensor pipe
-  // busy; two co-resident persistent CTAs per SM give it two independent accumulator chains.  Try 2 CTAs/SM first
-  // (half the shared memory and half the TMEM each), fall back to 1.
-  const bool allow2 = g.a_mode == A_TMA && !g.two_cta && d.reserved[0] != 7 && (long long)g.m_tiles * g.n_tiles > 2 * 148;
-  int chosen = 0;
+  // Two co-resident persistent CTAs per SM give the tensor pipe two independent accumulator chains (half the shared
+  // memory and half the TMEM each); fall back to 1.
+  const bool allow2 = g.a_mode == A_TMA && (!g.two_cta || d.reserved[1] == 5) && d.reserved[0] != 7 && (long long)g.m_tiles * g.n_tiles > 2 * 148;
   for (int ctas = allow2 ? 2 : 1; ctas >= 1 && !chosen; --ctas) {
     const size_t budget = (size_t)(227 * 1024) / ctas;
     const int tmem_budget = 512 / ctas;
@@ -796,8 +1144,26 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
       if (ctas == 2 && bufs == 2 && stages < 3) continue;     // prefer a third stage over a second staging buffer
       g.ctas_per_sm = ctas; g.acc_stages = acc; g.tmem_cols = pow2; g.stages = stages; g.out_bufs = bufs;
       g.smem_bytes = fixed + (size_t)stages * stage_bytes;
+      // K chains: one tcgen05.mma of this N occupies the tensor pipe for block_n/2 clk but dependent ones issue ~200 clk apart,
+      // so the SM wants ~400/block_n independent accumulators; they share this CTA's TMEM budget (single-buffered if need be)
+      g.kchains = 1;
+      if (g.epi_kind != 0 && d.reserved[1] == 4) {     // opt-in (reserved[1] == 4): measured slower than one chain on every shape
+        const int total_ksteps = g.total_chunks * (g.bk / 16);
+        int want = (400 + g.block_n - 1) / g.block_n;            // chains per SM
+        want = (want + ctas - 1) / ctas;                         // per CTA
+        int kc = want >= 3 ? 4 : (want >= 2 ? 2 : 1);
+        while (kc > 1 && (kc * g.block_n > tmem_budget || total_ksteps < 2 * kc)) kc >>= 1;
+        if (kc > 1) {
+          g.kchains = kc;
+          g.acc_stages = (2 * kc * g.block_n <= tmem_budget) ? 2 : 1;
+          int p2 = 32;
+          while (p2 < g.acc_stages * kc * g.block_n) p2 <<= 1;
+          g.tmem_cols = p2;
+        }
+      }
       chosen = 1;
     }
+  }
   }
   if (!chosen) return set_error(VCB_ERR_INVALID, "conv: not enough shared memory for the pipeline");
   return VCB_OK;
@@ -832,6 +1198,23 @@ int conv_pack_weights(const VcbConvDesc& d, const float* w, const float* bias, v
   return check_cuda(cudaGetLastError(), "pack_weights launch");
 }
 
+// Launch configuration shared by the conv kernels; with state().pdl the launch carries the programmatic stream
+// serialisation attribute (the kernels call griddepcontrol.wait before they touch global memory).
+static void fill_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int block, size_t smem, cudaStream_t st) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (state().pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
+  }
+}
+
 template <int BK>
 static int launch_conv_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvParams& p, const ConvGeom& g,
                             cudaStream_t st) {
@@ -841,25 +1224,29 @@ static int launch_conv_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv 2cta)");
     attr_set = true;
   }
-  const int max_clusters = state().num_sms / 2;
+  const int max_clusters = state().num_sms / 2 * g.ctas_per_sm;
   const int clusters = p.num_pair_tiles < max_clusters ? p.num_pair_tiles : max_clusters;
-  conv_umma_2cta_kernel<BK><<<2 * clusters, kThreadsTma, g.smem_bytes, st>>>(ta, tb, to, p);
-  return check_cuda(cudaGetLastError(), "conv (cta pair) launch");
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  fill_launch_config(cfg, attr, 2 * clusters, kThreadsTma, g.smem_bytes, st);
+  return check_cuda(cudaLaunchKernelEx(&cfg, conv_umma_2cta_kernel<BK>, ta, tb, to, p), "conv (cta pair) launch");
 }
 
-template <int A_MODE, int BK>
-static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvParams& p, const ConvGeom& g,
-                       cudaStream_t st) {
+template <int A_MODE, int BK, bool M256 = false>
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const ConvParams& p,
+                       const ConvGeom& g, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<A_MODE, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<A_MODE, BK, M256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv)");
     attr_set = true;
   }
   const int max_ctas = state().num_sms * g.ctas_per_sm;
   const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
-  conv_umma_kernel<A_MODE, BK><<<grid, A_MODE == A_TMA ? kThreadsTma : kThreadsGather, g.smem_bytes, st>>>(ta, tb, to, p);
-  return check_cuda(cudaGetLastError(), "conv launch");
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  fill_launch_config(cfg, attr, grid, A_MODE == A_TMA ? kThreadsTma : kThreadsGather, g.smem_bytes, st);
+  return check_cuda(cudaLaunchKernelEx(&cfg, conv_umma_kernel<A_MODE, BK, M256>, ta, tb, to, tr, p), "conv launch");
 }
 
 int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const float* bias_packed, const void* residual,
@@ -883,7 +1270,8 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   p.Cout = d.cout; p.cout_store = (d.cout + 7) / 8 * 8; p.out_pitch = d.cout_pitch;
   p.chunks_per_tap = g.chunks_per_tap; p.num_k_iters = g.num_k_iters;
   p.bk = g.bk; p.chunks_per_stage = g.chunks_per_stage; p.total_chunks = g.total_chunks;
-  p.block_n = g.block_n; p.n_tiles = g.n_tiles; p.m_tiles = g.m_tiles; p.num_tiles = g.m_tiles * g.n_tiles;
+  p.block_n = g.block_n; p.n_tiles = g.n_tiles;
+  p.m_tiles = (g.M + g.tile_m - 1) / g.tile_m; p.num_tiles = p.m_tiles * g.n_tiles;
   p.num_pair_tiles = ((g.m_tiles + 1) / 2) * g.n_tiles;
   p.num_stages = g.stages; p.acc_stages = g.acc_stages; p.tmem_cols = g.tmem_cols;
   p.act = d.act; p.res_mode = d.res_mode; p.res_pitch = d.res_pitch; p.out_fp32 = d.out_dtype == VCB_F32 ? 1 : 0;
@@ -892,24 +1280,39 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   p.residual = reinterpret_cast<const __half*>(residual);
   p.out = y;
   p.fault = state().fault_dev;
+  p.prof = state().prof_on ? state().prof_dev : nullptr;
   p.epi_direct = d.reserved[0] == 1 ? 1 : 0;
   p.split_b = 0;   // (a second producer thread for the weight tiles measured no gain; code path kept for experiments only)
   p.b_resident = g.b_resident; p.b_res_bytes = g.b_res_bytes;
   p.dbg_skip_epilogue = d.reserved[0] == 3 ? 1 : 0;
+  p.cout_pad = g.cout_pad;
+  p.epi_kind = g.epi_kind;
+  p.kchains = g.kchains;
   if (d.reserved[0] == 4) { p.acc_stages = 1; }
   p.out_stage_bufs = g.out_bufs;
-  p.out_stage_bytes = g.out_bufs * kStageOutBytes;
+  p.out_stage_bytes = g.out_bufs * (g.tile_m * 128);
   p.c4_wide = (g.a_mode == A_C4 && d.kw % 2 == 0 && d.stride % 2 == 0 && d.pad % 2 == 0 && d.w % 2 == 0 && d.reserved[1] != 1) ? 1 : 0;
 
   const CUtensorMapSwizzle swz = g.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (g.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  alignas(64) CUtensorMap ta, tb, to;
+  alignas(64) CUtensorMap ta, tb, to, tr;
   memset(&ta, 0, sizeof(ta));
   memset(&to, 0, sizeof(to));
+  memset(&tr, 0, sizeof(tr));
+  if (p.epi_kind != 0 && d.res_mode != VCB_RES_NONE) {   // residual: [M][cout] fp16 view with row pitch res_pitch, same boxes as the output
+    const cuuint64_t dims[2] = {(cuuint64_t)d.cout, (cuuint64_t)g.M};
+    const cuuint64_t strides[1] = {(cuuint64_t)d.res_pitch * 2};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)g.tile_m};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = state().encode_tiled(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(residual), dims, strides, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(residual) failed: %d", (int)r);
+  }
   if (!p.epi_direct) {   // output: [M][cout] slice of an NHWC buffer with row pitch cout_pitch; box = 128 bytes x 128 rows
     const bool f32 = d.out_dtype == VCB_F32;
     const cuuint64_t dims[2] = {(cuuint64_t)d.cout, (cuuint64_t)g.M};
     const cuuint64_t strides[1] = {(cuuint64_t)d.cout_pitch * (f32 ? 4 : 2)};
-    const cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : 64), (cuuint32_t)kBlockM};
+    const cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : 64), (cuuint32_t)g.tile_m};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = state().encode_tiled(&to, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, y, dims,
                                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -931,7 +1334,7 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
     // 1x1/s1/p0: A is the [M][cin] matrix itself (row pitch cin_pitch): plain tiled TMA, box = bk channels x 128 rows
     const cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)g.M};
     const cuuint64_t strides[1] = {(cuuint64_t)d.cin_pitch * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)g.bk, (cuuint32_t)kBlockM};
+    const cuuint32_t box[2] = {(cuuint32_t)g.bk, (cuuint32_t)g.tile_m};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = state().encode_tiled(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -948,7 +1351,7 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
     const int upper[2] = {d.pad - (d.kw - 1), d.pad - (d.kh - 1)};
     const cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
     const CUresult r = state().encode_im2col(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, lower,
-                                             upper, (cuuint32_t)g.bk, (cuuint32_t)kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                             upper, (cuuint32_t)g.bk, (cuuint32_t)g.tile_m, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                              swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeIm2col failed: %d", (int)r);
@@ -967,11 +1370,16 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
         if (g.bk == 32) return launch_conv_2cta<32>(ta, tb, to, p, g, st);
         return launch_conv_2cta<16>(ta, tb, to, p, g, st);
       }
-      if (g.bk == 64) return launch_conv<A_TMA, 64>(ta, tb, to, p, g, st);
-      if (g.bk == 32) return launch_conv<A_TMA, 32>(ta, tb, to, p, g, st);
-      return launch_conv<A_TMA, 16>(ta, tb, to, p, g, st);
-    case A_GATHER: return launch_conv<A_GATHER, 64>(ta, tb, to, p, g, st);
-    default: return launch_conv<A_C4, 64>(ta, tb, to, p, g, st);
+      if (g.m256) {
+        if (g.bk == 64) return launch_conv<A_TMA, 64, true>(ta, tb, to, tr, p, g, st);
+        if (g.bk == 32) return launch_conv<A_TMA, 32, true>(ta, tb, to, tr, p, g, st);
+        return launch_conv<A_TMA, 16, true>(ta, tb, to, tr, p, g, st);
+      }
+      if (g.bk == 64) return launch_conv<A_TMA, 64>(ta, tb, to, tr, p, g, st);
+      if (g.bk == 32) return launch_conv<A_TMA, 32>(ta, tb, to, tr, p, g, st);
+      return launch_conv<A_TMA, 16>(ta, tb, to, tr, p, g, st);
+    case A_GATHER: return launch_conv<A_GATHER, 64>(ta, tb, to, tr, p, g, st);
+    default: return launch_conv<A_C4, 64>(ta, tb, to, tr, p, g, st);
   }
 }
 

@@ -22,10 +22,13 @@ struct State {
   int device = -1;
   int num_sms = 0;
   int driver_version = 0;
+  int pdl = 0;                         // conv launches carry the programmatic-dependent-launch attribute ($VCB_PDL / vcb_set_option)
   EncodeTiledFn encode_tiled = nullptr;
   EncodeIm2colFn encode_im2col = nullptr;
   KernelFault* fault_host = nullptr;   // pinned + mapped: still readable after a trapped kernel
   KernelFault* fault_dev = nullptr;
+  int prof_on = 0;                     // conv role timers (development aid)
+  unsigned long long* prof_dev = nullptr;   // 16 counters in device memory
 };
 State& state();
 

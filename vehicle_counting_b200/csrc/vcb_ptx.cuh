@@ -117,6 +117,10 @@ __device__ __forceinline__ void mbar_wait_tight(uint32_t bar, uint32_t parity, K
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -15,6 +15,7 @@ torch elementwise ops once at load time, never per frame.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -263,7 +264,8 @@ class YoloEngine:
         def src_of(i, f) -> TRef:
             return TRef(self.x_s2d, 0, 16) if (i == 0 and f == -1) else home[i - 1 if f == -1 else f]
 
-        SILU = L.ACT_SILU
+        # $VCB_SILU=tanh: one-MUFU SiLU (h + h*tanh(h)); default: ex2 + rcp
+        SILU = L.ACT_SILU_TANH if os.environ.get("VCB_SILU", "exp") == "tanh" else L.ACT_SILU
         for i, (f, n, kind, args) in enumerate(LAYERS_V6):
             pre = f"model.{i}"
             if kind == "Conv":
