@@ -165,6 +165,28 @@ case("xp-pair2-noepi-64", mode="tma", n=1024, h=25, w=25, k=3, p=1, cin=64, cout
 case("xp-single-noepi-64", mode="tma", n=1024, h=25, w=25, k=3, p=1, cin=64, cout=64, act="relu", cta_pair=1, epi_direct=3)
 case("xp-pair2-192", mode="tma", n=128, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", cta_pair=2, dbg1=5)
 
+# CTA pairs, two co-resident clusters per SM pair (cta_pair=4), specialised epilogue: parity on awkward shapes + timing vs auto
+case("pair2-odd-mtiles", mode="tma", n=5, h=13, w=13, k=3, p=1, cin=128, cout=128, act="relu", res="before", cta_pair=4)
+case("pair2-cout384-bk32", mode="tma", n=3, h=20, w=20, k=3, p=1, cin=96, cout=384, act="silu", cta_pair=4)
+case("pair2-cout255-f32", mode="tma", n=2, h=20, w=20, cin=128, cout=255, cout_pitch=256, out="f32", cta_pair=4)
+case("pair2-bk16-stem", mode="tma", n=2, h=64, w=64, k=3, p=1, cin=16, cout=48, act="silu", cta_pair=4)
+case("pair2-res-after-slices", mode="tma", n=2, h=40, w=40, k=3, p=1, cin=96, cout=192, cout_pitch=384, act="silu", res="after", cta_pair=4)
+case("pair2-1x1-tail", mode="tma", n=3, h=13, w=13, k=1, cin=64, cout=40, cin_pitch=128, cout_pitch=48, act="relu", cta_pair=4)
+case("pair1-res-before", mode="tma", n=4, h=13, w=13, k=3, p=1, cin=128, cout=128, act="relu", res="before", cta_pair=2)
+case("pair2-big-3x3-192-res", mode="tma", n=64, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", res="after", cta_pair=4)
+case("pair2-big-3x3-96", mode="tma", n=32, h=80, w=80, k=3, p=1, cin=96, cout=96, act="silu", res="after", cta_pair=4)
+case("pair2-big-reid-l1", mode="tma", n=1024, h=25, w=25, k=3, p=1, cin=64, cout=64, act="relu", res="before", cta_pair=4)
+case("pair2-big-reid-l2", mode="tma", n=1024, h=13, w=13, k=3, p=1, cin=128, cout=128, act="relu", res="before", cta_pair=4)
+case("pair2-big-reid-l3", mode="tma", n=2048, h=7, w=7, k=3, p=1, cin=256, cout=256, act="relu", res="before", cta_pair=4)
+case("auto-big-reid-l3", mode="tma", n=2048, h=7, w=7, k=3, p=1, cin=256, cout=256, act="relu", res="before")
+case("pair2-big-reid-l4", mode="tma", n=4096, h=4, w=4, k=3, p=1, cin=512, cout=512, act="relu", res="before", cta_pair=4)
+case("auto-big-reid-l4", mode="tma", n=4096, h=4, w=4, k=3, p=1, cin=512, cout=512, act="relu", res="before")
+case("pair2-big-1x1-192", mode="tma", n=64, h=40, w=40, k=1, cin=192, cout=192, act="silu", cta_pair=4)
+case("pair2-big-s2-192-384", mode="tma", n=64, h=40, w=40, k=3, s=2, p=1, cin=192, cout=384, act="silu", cta_pair=4)
+case("auto-big-s2-192-384", mode="tma", n=64, h=40, w=40, k=3, s=2, p=1, cin=192, cout=384, act="silu")
+case("pair2-big-1x1-768-384", mode="tma", n=64, h=20, w=20, k=1, cin=768, cout=384, act="silu", cta_pair=4)
+case("auto-big-1x1-768-384", mode="tma", n=64, h=20, w=20, k=1, cin=768, cout=384, act="silu")
+
 
 def run_case(idx: int) -> dict:
     import torch

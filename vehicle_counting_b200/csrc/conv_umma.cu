@@ -300,10 +300,14 @@ __device__ __forceinline__ float act_fast(float v) {
   return v;
 }
 
-template <int ACT, int RES, bool F32OUT, bool M256>
+template <int ACT, int RES, bool F32OUT, bool M256, bool TWO_CTA = false>
 __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CUtensorMap* tmap_out_ptr, const CUtensorMap* tmap_res_ptr,
                                                    uint32_t tmem_base, uint32_t out_stage, uint32_t bias_smem, uint32_t res_bar0,
-                                                   uint32_t tmem_full0, uint32_t tmem_empty0) {
+                                                   uint32_t tmem_full0, uint32_t tmem_empty0, int first_tile = (int)blockIdx.x,
+                                                   int tile_step = (int)gridDim.x, int cta_rank = 0) {
+  // TWO_CTA: this CTA is one half of a cta_group::2 pair; it drains its own 128 accumulator rows of the 256-row pair tile
+  // (tiles are numbered per cluster) and releases the accumulator on the LEADER's tmem_empty barrier.
+  const int total_tiles = TWO_CTA ? p.num_pair_tiles : p.num_tiles;
   // Residual (RES != NONE): the residual sub-tile is fetched by TMA INTO the staging buffer (same 128-byte-swizzled layout
   // as the output sub-tile), every thread reads its own 16-byte chunks, adds, and writes the result back in place.  Per-thread
   // global loads of a row-per-lane layout touch 32 lines per request and, with no L1 left beside ~220 KiB of shared memory,
@@ -333,14 +337,16 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
   uint32_t tile_iter = 0, sub_count = 0;
   long long t_wait = 0, t_sync = 0;
   const long long t_begin = prof_clock(issuer ? p.prof : nullptr);
-  if (RES != VCB_RES_NONE && issuer && (int)blockIdx.x < p.num_tiles) {      // residual of the first sub-tile
-    const int mt0 = (int)blockIdx.x / p.n_tiles, nt0 = (int)blockIdx.x - mt0 * p.n_tiles;
+  if (RES != VCB_RES_NONE && issuer && first_tile < total_tiles) {      // residual of the first sub-tile
+    const int pm0 = first_tile / p.n_tiles, nt0 = first_tile - pm0 * p.n_tiles;
+    const int mt0 = TWO_CTA ? 2 * pm0 + cta_rank : pm0;
     mbar_arrive_expect_tx(res_bar0, STAGE_BYTES);
     tma_load_2d(tmap_res_ptr, res_bar0, out_stage, nt0 * p.block_n, mt0 * TILE_M);
   }
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
-    const int m_tile = tile / p.n_tiles;
-    const int n_tile = tile - m_tile * p.n_tiles;
+  for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++tile_iter) {
+    const int pm_tile = tile / p.n_tiles;
+    const int n_tile = tile - pm_tile * p.n_tiles;
+    const int m_tile = TWO_CTA ? 2 * pm_tile + cta_rank : pm_tile;
     const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
     const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
     const long long tw0 = prof_clock(issuer ? p.prof : nullptr);
@@ -400,7 +406,8 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
         if (ngroups > 0) tmem_ld_wait();
         if (sub == num_sub - 1 && pass == PASSES - 1) {    // accumulator fully read: hand it back before the math / stores
           tcgen05_fence_before();
-          mbar_arrive(tmem_empty0 + 8u * acc);
+          if (TWO_CTA && cta_rank != 0) mbar_arrive_remote(tmem_empty0 + 8u * acc, 0);
+          else mbar_arrive(tmem_empty0 + 8u * acc);
         }
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -470,10 +477,11 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
         tma_store_commit();
         if (RES != VCB_RES_NONE) {                        // request the residual of the next sub-tile (maybe of the next tile)
           int nt = tile, nsub = sub + 1;
-          if (nsub == num_sub) { nsub = 0; nt = tile + (int)gridDim.x; }
-          if (nt < p.num_tiles) {
+          if (nsub == num_sub) { nsub = 0; nt = tile + tile_step; }
+          if (nt < total_tiles) {
             if (!two_bufs) tma_store_wait_read<0>();        // same buffer: the store just issued must have read it
-            const int nm = nt / p.n_tiles, nn = nt - nm * p.n_tiles;
+            const int npm = nt / p.n_tiles, nn = nt - npm * p.n_tiles;
+            const int nm = TWO_CTA ? 2 * npm + cta_rank : npm;
             const uint32_t nb = two_bufs ? ((sub_count + 1u) & 1u) : 0u;
             mbar_arrive_expect_tx(res_bar0 + 8u * nb, STAGE_BYTES);
             tma_load_2d(tmap_res_ptr, res_bar0 + 8u * nb, out_stage + nb * STAGE_BYTES, nn * p.block_n + nsub * SUB_COLS, nm * TILE_M);
@@ -838,7 +846,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 template <int BK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTma, 2)
 conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                      const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
+                      const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_tile_bytes = (uint32_t)p.block_n * 64u;                 // this CTA's half: N/2 rows x 128 B
@@ -851,11 +859,16 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   auto tmem_empty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * kMaxStages + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-      smem_gen + (size_t)p.num_stages * stage_bytes + p.out_stage_bytes + 8 * (2 * kMaxStages + 4));
+  uint8_t* tail_gen = smem_gen + (size_t)p.num_stages * stage_bytes + p.out_stage_bytes + 8 * (2 * kMaxStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_gen);
+  const uint32_t res_bar0 = tmem_slot + 16u;         // same tail layout as the single-CTA kernel: slot, (row table ->) 2 residual barriers, bias
+  const uint32_t bias_smem = tmem_slot + 16u + (uint32_t)(kBlockM * sizeof(RowInfo));
+  float* bias_gen = reinterpret_cast<float*>(tail_gen + 16 + kBlockM * sizeof(RowInfo));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (p.epi_kind != 0)
+    for (int i = threadIdx.x; i < p.cout_pad; i += blockDim.x) bias_gen[i] = __ldg(p.bias + i);
   const int rank = (int)cluster_ctarank();
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1;
@@ -871,12 +884,15 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_init(tmem_full_bar(a), 1);
       mbar_init(tmem_empty_bar(a), 2 * kNumEpilogueThreads);   // both CTAs' epilogues (leader's copy is the live one)
     }
+    mbar_init(res_bar0, 1);
+    mbar_init(res_bar0 + 8u, 1);
     fence_mbar_init();
   }
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_out);
+    if (p.epi_kind != 0 && p.res_mode != VCB_RES_NONE) tma_prefetch_desc(&tmap_res);
   }
   if (warp == kMmaWarp) {
     tmem_alloc_2cta(tmem_slot, (uint32_t)p.tmem_cols);
@@ -962,7 +978,22 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       }
     }
   } else if (warp < kEpilogueWarps) {
-    conv_epilogue<true>(p, &tmap_out, tmem_base, out_stage, tmem_full_bar(0), tmem_empty_bar(0), cluster_id, num_clusters, rank);
+#define VCB_EPI_CASE(K, ACT, RES, F32) \
+    case K: conv_epilogue_fast<ACT, RES, F32, false, true>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), \
+                                                           tmem_empty_bar(0), cluster_id, num_clusters, rank); break;
+    switch (p.epi_kind) {
+      VCB_EPI_CASE(1, VCB_ACT_SILU, VCB_RES_NONE, false)
+      VCB_EPI_CASE(2, VCB_ACT_SILU, VCB_RES_AFTER_ACT, false)
+      VCB_EPI_CASE(3, VCB_ACT_SILU_TANH, VCB_RES_NONE, false)
+      VCB_EPI_CASE(4, VCB_ACT_SILU_TANH, VCB_RES_AFTER_ACT, false)
+      VCB_EPI_CASE(5, VCB_ACT_RELU, VCB_RES_NONE, false)
+      VCB_EPI_CASE(6, VCB_ACT_RELU, VCB_RES_BEFORE_ACT, false)
+      VCB_EPI_CASE(7, VCB_ACT_NONE, VCB_RES_NONE, true)
+      VCB_EPI_CASE(8, VCB_ACT_NONE, VCB_RES_NONE, false)
+      default:
+        conv_epilogue<true>(p, &tmap_out, tmem_base, out_stage, tmem_full_bar(0), tmem_empty_bar(0), cluster_id, num_clusters, rank);
+    }
+#undef VCB_EPI_CASE
   }
 
   tcgen05_fence_before();
@@ -1074,10 +1105,17 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
     return set_error(VCB_ERR_INVALID, "conv: bad residual pitch");
   // CTA pairs (cta_group::2): measured on B200 at parity with the single-CTA kernel for these layer shapes, so they are
   // opt-in (reserved[3] == 2); reserved[3] == 1 forces the single-CTA kernel.
-  g.two_cta = (g.a_mode == A_TMA && g.m_tiles >= 2 && d.reserved[3] == 2) ? 1 : 0;
-  if (d.reserved[3] == 2 && !g.two_cta) return set_error(VCB_ERR_INVALID, "conv: the CTA-pair kernel needs the TMA path and >= 2 M tiles");
+  // CTA pairs (cta_group::2, each CTA loads half of every weight tile), two co-resident clusters per SM pair: measured 3-9 %
+  // faster than two independent 128-row CTAs per SM on 3x3 layers with N >= 128 and at least two waves of pair tiles, at
+  // parity elsewhere (profiles/r01_layer_modes.md).  reserved[3]: 1 = never, 2 = pair kernel with one cluster per SM pair,
+  // 4 = pair kernel with two.
+  const int epi0 = (d.reserved[0] == 0) ? epi_kind_of(d.act, d.res_mode, d.out_dtype == VCB_F32 ? 1 : 0) : 0;
+  const bool auto_pair = d.reserved[3] == 0 && g.a_mode == A_TMA && epi0 != 0 && d.kh * d.kw > 1 && g.block_n >= 128 &&
+                         (long long)((g.m_tiles + 1) / 2) * g.n_tiles >= 2 * 148;
+  g.two_cta = (g.a_mode == A_TMA && g.m_tiles >= 2 && (d.reserved[3] == 2 || d.reserved[3] == 4 || auto_pair)) ? 1 : 0;
+  if ((d.reserved[3] == 2 || d.reserved[3] == 4) && !g.two_cta) return set_error(VCB_ERR_INVALID, "conv: the CTA-pair kernel needs the TMA path and >= 2 M tiles");
   // specialised epilogue: single-CTA TMA kernel with the staged TMA store (any debug value in reserved[0] forces the generic one)
-  g.epi_kind = (g.a_mode == A_TMA && !g.two_cta && d.reserved[0] == 0) ? epi_kind_of(d.act, d.res_mode, d.out_dtype == VCB_F32 ? 1 : 0) : 0;
+  g.epi_kind = (g.a_mode == A_TMA && d.reserved[0] == 0) ? epi_kind_of(d.act, d.res_mode, d.out_dtype == VCB_F32 ? 1 : 0) : 0;
   const size_t b_total = (size_t)g.total_chunks * g.block_n * g.bk * 2;
   const size_t tail0 = 1024 /*align slack*/ + 8 * (2 * kMaxStages + 4) + 16 + kBlockM * sizeof(RowInfo) + (size_t)g.cout_pad * 4 + 64;
   g.m256 = 0; g.tile_m = kBlockM; g.b_resident = 0; g.b_res_bytes = 0; g.kchains = 1;
@@ -1126,7 +1164,7 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
   const int min_stages = (g.a_mode == A_TMA) ? 2 : kGatherLag + 2;
   // Two co-resident persistent CTAs per SM give the tensor pipe two independent accumulator chains (half the shared
   // memory and half the TMEM each); fall back to 1.
-  const bool allow2 = g.a_mode == A_TMA && (!g.two_cta || d.reserved[1] == 5) && d.reserved[0] != 7 && (long long)g.m_tiles * g.n_tiles > 2 * 148;
+  const bool allow2 = g.a_mode == A_TMA && (!g.two_cta || d.reserved[1] == 5 || d.reserved[3] == 4 || auto_pair) && d.reserved[0] != 7 && (long long)g.m_tiles * g.n_tiles > 2 * 148;
   for (int ctas = allow2 ? 2 : 1; ctas >= 1 && !chosen; --ctas) {
     const size_t budget = (size_t)(227 * 1024) / ctas;
     const int tmem_budget = 512 / ctas;
@@ -1147,7 +1185,7 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
       // K chains: one tcgen05.mma of this N occupies the tensor pipe for block_n/2 clk but dependent ones issue ~200 clk apart,
       // so the SM wants ~400/block_n independent accumulators; they share this CTA's TMEM budget (single-buffered if need be)
       g.kchains = 1;
-      if (g.epi_kind != 0 && d.reserved[1] == 4) {     // opt-in (reserved[1] == 4): measured slower than one chain on every shape
+      if (g.epi_kind != 0 && !g.two_cta && d.reserved[1] == 4) {     // opt-in (reserved[1] == 4): measured slower than one chain on every shape
         const int total_ksteps = g.total_chunks * (g.bk / 16);
         int want = (400 + g.block_n - 1) / g.block_n;            // chains per SM
         want = (want + ctas - 1) / ctas;                         // per CTA
@@ -1216,8 +1254,8 @@ static void fill_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* att
 }
 
 template <int BK>
-static int launch_conv_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ConvParams& p, const ConvGeom& g,
-                            cudaStream_t st) {
+static int launch_conv_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const ConvParams& p,
+                            const ConvGeom& g, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     const cudaError_t e = cudaFuncSetAttribute(conv_umma_2cta_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1229,7 +1267,7 @@ static int launch_conv_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   fill_launch_config(cfg, attr, 2 * clusters, kThreadsTma, g.smem_bytes, st);
-  return check_cuda(cudaLaunchKernelEx(&cfg, conv_umma_2cta_kernel<BK>, ta, tb, to, p), "conv (cta pair) launch");
+  return check_cuda(cudaLaunchKernelEx(&cfg, conv_umma_2cta_kernel<BK>, ta, tb, to, tr, p), "conv (cta pair) launch");
 }
 
 template <int A_MODE, int BK, bool M256 = false>
@@ -1366,9 +1404,9 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   switch (g.a_mode) {
     case A_TMA:
       if (g.two_cta) {
-        if (g.bk == 64) return launch_conv_2cta<64>(ta, tb, to, p, g, st);
-        if (g.bk == 32) return launch_conv_2cta<32>(ta, tb, to, p, g, st);
-        return launch_conv_2cta<16>(ta, tb, to, p, g, st);
+        if (g.bk == 64) return launch_conv_2cta<64>(ta, tb, to, tr, p, g, st);
+        if (g.bk == 32) return launch_conv_2cta<32>(ta, tb, to, tr, p, g, st);
+        return launch_conv_2cta<16>(ta, tb, to, tr, p, g, st);
       }
       if (g.m256) {
         if (g.bk == 64) return launch_conv<A_TMA, 64, true>(ta, tb, to, tr, p, g, st);
