@@ -166,6 +166,17 @@ typedef struct VcbRoiDesc {
  * clipped, end exclusive); out: fp16 [num_rois][out][out][out_channels] */
 int vcb_roi_resize_norm(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, int32_t fw, const int32_t* rois,
                         void* out, vcb_stream_t stream);
+/* Fused ReID stem for the folded-BN path (feature_extractor.py:26-39 + model.py:52-60: crop preprocessing, Conv3x3(3->64)+BN+ReLU,
+ * MaxPool2d(3, 2, padding=1)) in two launches:
+ *   vcb_roi_stem_patches: same crop/resize/normalise arithmetic as vcb_roi_resize_norm (out_size must be 50), written as the
+ *     stem's im2col operand: patches fp16 [num_rois][25 blocks][128 rows][32], block (by, bx) = 5x5 pooled pixels, row
+ *     ti*11+tj = conv output (10*by-1+ti, 10*bx-1+tj), element (r*3+s)*3+c = input (y+r-1, x+s-1, c); padding zero.
+ *   vcb_reid_stem_pool: w_packed fp16 [64][32] (same K order, BN folded, zero padded), bias fp32 [64] ->
+ *     out fp16 [num_rois][25][25][64] = maxpool3x3s2p1(relu(conv + bias)); tcgen05 GEMM + pooling in shared memory. */
+int vcb_roi_stem_patches(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, int32_t fw, const int32_t* rois,
+                         void* patches, vcb_stream_t stream);
+int vcb_reid_stem_pool(const void* patches, const void* w_packed, const float* bias, void* out, int32_t num_rois,
+                       vcb_stream_t stream);
 /* float64 xyxy boxes -> the reference's integer crop rectangle (deep_sort.py:78-95), on device.
  * boxes: double [num][4]; frame_of: int32 [num]; rois out: int32 [num][5] */
 int vcb_boxes_to_rois(const double* boxes_xyxy, const int32_t* frame_of, int32_t num, int32_t fw, int32_t fh,

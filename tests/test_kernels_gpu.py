@@ -258,3 +258,58 @@ def test_roi_resize_norm_matches_oracle(lib):
         got = out.float().cpu()
         assert (got[..., 3:] == 0).all()
         assert (got[..., :3] - ref).abs().max().item() < 2.5e-3    # fp16 storage of values up to ~2.7
+
+
+def test_reid_fused_stem_matches_unfused_reference(lib):
+    """roi_stem_patches + reid_stem_pool (crop -> conv3x3 3->64 + bias -> ReLU -> maxpool 3/2/1 in one pass, tcgen05) against
+    the same arithmetic spelled out with torch on the fp16 crop that vcb_roi_resize_norm produces
+    (/root/reference/networks/deepsort/deep/model.py:52-60)."""
+    import torch.nn.functional as F
+    from oracle import reid as R
+    from vehicle_counting_b200 import ops, _lib as L
+    rng = np.random.default_rng(5)
+    fh, fw = 240, 320
+    frames = torch.from_numpy(rng.integers(0, 256, (2, fh, fw, 3), dtype=np.uint8)).to(DEV)
+    n = 37                                                     # not a multiple of anything: exercises the tile tail
+    wh = rng.uniform(8, 200, (n, 2)); tl = rng.uniform(0, 1, (n, 2)) * (np.array([fw, fh]) - wh)
+    rois_np = np.concatenate([rng.integers(0, 2, (n, 1)), tl, tl + wh], 1).astype(np.int32)
+    rois_np[5] = (0, 10, 10, 10, 30)                           # zero-width crop: the unfused kernel writes zeros, so must this one
+    rois = torch.from_numpy(rois_np).to(DEV)
+    rd = L.RoiDesc()
+    rd.num_rois, rd.out_size, rd.out_channels = n, 50, 4
+    for c in range(3):
+        rd.mean[c] = R.NORM_MEAN[c]; rd.inv_std[c] = 1.0 / R.NORM_STD[c]
+    x = torch.zeros(n, 50, 50, 4, dtype=torch.float16, device=DEV)
+    ops.roi_resize_norm(rd, frames, fh, fw, rois, x)
+    g = torch.Generator().manual_seed(3)
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.3)
+    b = torch.randn(64, generator=g) * 0.2
+    wp, bp = ops.pack_reid_stem_weights(w.to(DEV), b.to(DEV))
+    patches = torch.full((n, 25, 128, 32), 7.0, dtype=torch.float16, device=DEV)
+    out = torch.full((n, 25, 25, 64), -5.0, dtype=torch.float16, device=DEV)
+    ops.roi_stem_patches(rd, frames, fh, fw, rois, patches)
+    ops.reid_stem_pool(patches, wp, bp, out, n)
+    torch.cuda.synchronize()
+    assert tuple(lib_fault()) == (0, 0, 0, 0)
+    # the im2col operand itself is integer-exact: element (r*3+s)*3+c of row ti*11+tj of block (by,bx) = crop[y+r-1, x+s-1, c]
+    xc = F.pad(x[..., :3].float().cpu().permute(0, 3, 1, 2), (1, 1, 1, 1))                     # [n,3,52,52]
+    cols = F.unfold(xc, 3).view(n, 3, 9, 50, 50).permute(0, 3, 4, 2, 1).reshape(n, 50, 50, 27)   # k = tap*3 + c
+    pt = patches.float().cpu()
+    for blk in (0, 7, 24):
+        by, bx = divmod(blk, 5)
+        for row in (0, 12, 60, 120):
+            ti, tj = divmod(row, 11)
+            cy, cx = 10 * by - 1 + ti, 10 * bx - 1 + tj
+            want = cols[:, cy, cx] if (cy >= 0 and cx >= 0) else torch.zeros(n, 27)
+            assert torch.equal(pt[:, blk, row, :27], want), (blk, row)
+    assert (pt[:, :, 121:, :] == 0).all() and (pt[..., 27:] == 0).all()
+    # conv + bias + ReLU (fp32 accumulate on the fp16 operands), fp16 rounding, max-pool
+    conv = F.conv2d(x[..., :3].float().cpu().permute(0, 3, 1, 2), wp[:, :27].float().cpu().view(64, 3, 3, 3).permute(0, 3, 1, 2), b, 1, 1)
+    ref = F.max_pool2d(F.relu(conv).half().float(), 3, 2, 1).permute(0, 2, 3, 1)
+    got = out.float().cpu()
+    assert (got - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
+def lib_fault():
+    from vehicle_counting_b200 import _lib as L
+    return L.last_fault()

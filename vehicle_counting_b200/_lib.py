@@ -95,6 +95,8 @@ _SIGNATURES = {
     "vcb_nms": ([C.POINTER(NmsDesc), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP], _I32),
     "vcb_roi_resize_norm": ([C.POINTER(RoiDesc), _VP, _I32, _I32, _VP, _VP, _VP], _I32),
     "vcb_boxes_to_rois": ([_VP, _VP, _I32, _I32, _I32, _VP, _VP], _I32),
+    "vcb_roi_stem_patches": ([C.POINTER(RoiDesc), _VP, _I32, _I32, _VP, _VP, _VP], _I32),
+    "vcb_reid_stem_pool": ([_VP, _VP, _VP, _VP, _I32, _VP], _I32),
     "vcb_avgpool_l2norm": ([_VP, _I32, _I32, _I32, _I32, _VP, _VP], _I32),
     "vcb_bn_train_stats": ([_VP, _I32, _VP, _I32, _VP, _VP, _F, _VP, _VP, _VP], _I32),
     "vcb_bn_apply": ([_VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _I32, _VP], _I32),

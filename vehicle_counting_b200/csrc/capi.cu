@@ -24,6 +24,8 @@ int nms(const VcbNmsDesc&, const float*, const float*, const int*, const int*, c
 long long nms_workspace_bytes(int n, int max_candidates);
 int roi_resize_norm(const VcbRoiDesc&, const uint8_t*, int, int, const int*, void*, cudaStream_t);
 int boxes_to_rois(const double*, const int*, int, int, int, int*, cudaStream_t);
+int roi_stem_patches(const VcbRoiDesc&, const uint8_t*, int, int, const int*, void*, cudaStream_t);
+int reid_stem_pool(const void*, const void*, const float*, void*, int, cudaStream_t);
 
 static thread_local char g_err[512] = "";
 
@@ -187,6 +189,14 @@ int vcb_roi_resize_norm(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, 
                         vcb_stream_t st) {
   VCB_GUARD(d);
   return roi_resize_norm(*d, frames, fh, fw, rois, out, (cudaStream_t)st);
+}
+int vcb_roi_stem_patches(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, int32_t fw, const int32_t* rois, void* patches,
+                         vcb_stream_t st) {
+  VCB_GUARD(d);
+  return roi_stem_patches(*d, frames, fh, fw, rois, patches, (cudaStream_t)st);
+}
+int vcb_reid_stem_pool(const void* patches, const void* w_packed, const float* bias, void* out, int32_t num_rois, vcb_stream_t st) {
+  return reid_stem_pool(patches, w_packed, bias, out, num_rois, (cudaStream_t)st);
 }
 int vcb_boxes_to_rois(const double* boxes, const int32_t* frame_of, int32_t num, int32_t fw, int32_t fh, int32_t* rois, vcb_stream_t st) {
   const int rc = require_init(); if (rc) return rc;

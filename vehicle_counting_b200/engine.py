@@ -451,6 +451,8 @@ class ReidEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], capacity: int = 64, *, device="cuda:0", bn_mode: str = "eval",
                  a_mode: int = L.A_AUTO):
         assert bn_mode in ("eval", "train")
+        # folded-BN path: fused crop -> stem conv -> ReLU -> max-pool ($VCB_REID_FUSED_STEM=0 keeps the three separate kernels)
+        self.fused_stem = os.environ.get("VCB_REID_FUSED_STEM", "1") != "0"
         self.device = torch.device(device)
         L.init(self.device.index or 0)
         self.sd = {k: v for k, v in state_dict.items() if not k.startswith("classifier")}
@@ -489,16 +491,28 @@ class ReidEngine:
         rd.num_rois, rd.out_size, rd.out_channels = nb, REID_SIZE, 16
         for c in range(3):
             rd.mean[c] = REID_MEAN[c]; rd.inv_std[c] = 1.0 / REID_STD[c]
-        x0 = buf(REID_SIZE, 16)          # 3 real + 13 zero channels: one 32-byte TMA box per tap (bk = 16)
         plan.keep += [rd, frames]
-        plan.add(lambda st: ops.roi_resize_norm(rd, frames, fh, fw, self.rois, x0, stream=st), "roi crop+resize+norm")
         RELU = L.ACT_RELU
         w_, b_ = _fold_plain(sd["conv.0.weight"], sd["conv.0.bias"], self._bn("conv.1"), REID_BN_EPS, dev)
-        s0 = buf(50, 64)
-        plan.conv(TRef(x0, 0, 16), nb, _pad_cin(w_, 16), b_, TRef(s0, 0, 64), 3, 1, 1, RELU, a_mode=self.a_mode,
-                  flops=2.0 * nb * 2500 * 64 * 27)
         cur = TRef(buf(25, 64), 0, 64)
-        plan.add(lambda st, s0=s0, cur=cur: ops.maxpool(s0, 64, cur.buf, 64, nb, 50, 50, 64, 3, 2, 1, stream=st), "maxpool3x3s2")
+        stem_flops = 2.0 * nb * 2500 * 64 * 27
+        if self.fused_stem:
+            # crop -> im2col patches of the stem (K = 27 -> 32), then ONE kernel: tcgen05 GEMM + bias + ReLU + 3x3/s2 max-pool
+            # (csrc/reid_stem.cu): the 50x50x64 stem map never reaches HBM
+            patches = torch.zeros(nb, 25, 128, 32, dtype=torch.float16, device=dev)
+            wp, bp = ops.pack_reid_stem_weights(w_, b_)
+            plan.keep += [patches, wp, bp]
+            plan.add(lambda st: ops.roi_stem_patches(rd, frames, fh, fw, self.rois, patches, stream=st), "roi crop+resize+norm -> stem patches")
+            plan.conv_flops += stem_flops
+            plan.num_convs += 1
+            plan.add(lambda st, cur=cur: ops.reid_stem_pool(patches, wp, bp, cur.buf, nb, stream=st),
+                     f"stem conv3x3 3->64 + maxpool3x3s2 (fused) M={nb * 2500}", stem_flops)
+        else:
+            x0 = buf(REID_SIZE, 16)          # 3 real + 13 zero channels: one 32-byte TMA box per tap (bk = 16)
+            plan.add(lambda st: ops.roi_resize_norm(rd, frames, fh, fw, self.rois, x0, stream=st), "roi crop+resize+norm")
+            s0 = buf(50, 64)
+            plan.conv(TRef(x0, 0, 16), nb, _pad_cin(w_, 16), b_, TRef(s0, 0, 64), 3, 1, 1, RELU, a_mode=self.a_mode, flops=stem_flops)
+            plan.add(lambda st, s0=s0, cur=cur: ops.maxpool(s0, 64, cur.buf, 64, nb, 50, 50, 64, 3, 2, 1, stream=st), "maxpool3x3s2")
         size = 25
         for prefix, ci, co, down in REID_BLOCKS:
             s = 2 if down else 1

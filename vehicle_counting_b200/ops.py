@@ -135,6 +135,27 @@ def roi_resize_norm(desc: L.RoiDesc, frames_u8, fh, fw, rois, out, stream=None) 
             "vcb_roi_resize_norm")
 
 
+def roi_stem_patches(desc: L.RoiDesc, frames_u8, fh, fw, rois, patches, stream=None) -> None:
+    """crop/resize/normalise as roi_resize_norm, written as the fused stem's im2col operand [n][25][128][32] fp16"""
+    L.check(L.load().vcb_roi_stem_patches(C.byref(desc), L.ptr(frames_u8), fh, fw, L.ptr(rois), L.ptr(patches), _st(stream)),
+            "vcb_roi_stem_patches")
+
+
+def reid_stem_pool(patches, w_packed, bias, out, num_rois, stream=None) -> None:
+    """maxpool3x3s2p1(relu(conv3x3(crop) + bias)) -> out fp16 [n][25][25][64] (tcgen05 GEMM + pooling in shared memory)"""
+    L.check(L.load().vcb_reid_stem_pool(L.ptr(patches), L.ptr(w_packed), L.ptr(bias), L.ptr(out), num_rois, _st(stream)),
+            "vcb_reid_stem_pool")
+
+
+def pack_reid_stem_weights(w_oihw: torch.Tensor, bias: torch.Tensor):
+    """[64, 3, 3, 3] fp32 (BN folded) -> fp16 [64][32], k = (r*3+s)*3 + c, zero padded; bias fp32 [64]"""
+    assert tuple(w_oihw.shape) == (64, 3, 3, 3)
+    wk = w_oihw.permute(0, 2, 3, 1).reshape(64, 27)
+    wp = torch.zeros(64, 32, dtype=torch.float16, device=w_oihw.device)
+    wp[:, :27] = wk.to(torch.float16)
+    return wp.contiguous(), bias.to(torch.float32).contiguous()
+
+
 def boxes_to_rois(boxes_f64, frame_of, num, fw, fh, rois, stream=None) -> None:
     L.check(L.load().vcb_boxes_to_rois(L.ptr(boxes_f64), L.ptr(frame_of), num, fw, fh, L.ptr(rois), _st(stream)),
             "vcb_boxes_to_rois")
