@@ -187,6 +187,32 @@ case("auto-big-s2-192-384", mode="tma", n=64, h=40, w=40, k=3, s=2, p=1, cin=192
 case("pair2-big-1x1-768-384", mode="tma", n=64, h=20, w=20, k=1, cin=768, cout=384, act="silu", cta_pair=4)
 case("auto-big-1x1-768-384", mode="tma", n=64, h=20, w=20, k=1, cin=768, cout=384, act="silu")
 
+# patch mode (cta_pair=5): one input patch per 64-channel chunk in shared memory, nine taps through shifted descriptors
+case("patch-3x3-64", mode="tma", n=2, h=20, w=20, k=3, p=1, cin=64, cout=64, cta_pair=5)
+case("patch-reid-l1", mode="tma", n=7, h=25, w=25, k=3, p=1, cin=64, cout=64, act="relu", res="before", cta_pair=5)
+case("patch-reid-l2", mode="tma", n=5, h=13, w=13, k=3, p=1, cin=128, cout=128, act="relu", res="before", cta_pair=5)
+case("patch-cin48-res", mode="tma", n=2, h=40, w=40, k=3, p=1, cin=48, cout=48, act="silu", res="after", cta_pair=5)
+case("patch-cin192-res-slices", mode="tma", n=2, h=40, w=40, k=3, p=1, cin=192, cout=192, cin_pitch=384, cout_pitch=384, act="silu", res="after", cta_pair=5)
+case("patch-cin96-bk64", mode="tma", n=2, h=80, w=80, k=3, p=1, cin=96, cout=96, act="silu", res="after", bk=64, cta_pair=5)
+case("patch-cout384-2tiles", mode="tma", n=2, h=20, w=20, k=3, p=1, cin=192, cout=384, act="silu", cta_pair=5)
+case("patch-cout40-f32", mode="tma", n=3, h=13, w=13, k=3, p=1, cin=64, cout=40, out="f32", cta_pair=5)
+case("patch-w160-4segs", mode="tma", n=2, h=64, w=160, k=3, p=1, cin=48, cout=48, act="silu_tanh", cta_pair=5)
+case("patch-odd-23x37", mode="tma", n=3, h=23, w=37, k=3, p=1, cin=64, cout=96, act="silu", res="after", cta_pair=5)
+case("patch-tiny-4x4", mode="tma", n=9, h=4, w=4, k=3, p=1, cin=128, cout=128, act="relu", cta_pair=5)
+case("patch-big-reid-l1", mode="tma", n=1024, h=25, w=25, k=3, p=1, cin=64, cout=64, act="relu", res="before", cta_pair=5)
+case("patch-big-reid-l2", mode="tma", n=1024, h=13, w=13, k=3, p=1, cin=128, cout=128, act="relu", res="before", cta_pair=5)
+case("patch-big-3x3-192-res", mode="tma", n=64, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", res="after", cta_pair=5)
+case("patch-big-3x3-96", mode="tma", n=32, h=80, w=80, k=3, p=1, cin=96, cout=96, act="silu", res="after", bk=64, cta_pair=5)
+case("patch-big-3x3-48", mode="tma", n=16, h=160, w=160, k=3, p=1, cin=48, cout=48, act="silu", res="after", cta_pair=5)
+case("patch-big-3x3-384", mode="tma", n=64, h=20, w=20, k=3, p=1, cin=384, cout=384, act="silu", res="after", cta_pair=5)
+case("auto-big-3x3-384", mode="tma", n=64, h=20, w=20, k=3, p=1, cin=384, cout=384, act="silu", res="after")
+
+case("patchk1-big-reid-l1", mode="tma", n=1024, h=25, w=25, k=3, p=1, cin=64, cout=64, act="relu", res="before", cta_pair=5, one_chain=True)
+case("patchk1-big-3x3-48", mode="tma", n=16, h=160, w=160, k=3, p=1, cin=48, cout=48, act="silu", res="after", cta_pair=5, one_chain=True)
+case("auto-big-yolos-32", mode="tma", n=32, h=160, w=160, k=3, p=1, cin=32, cout=32, act="silu", res="after")
+case("patch-big-yolos-64", mode="tma", n=32, h=80, w=80, k=3, p=1, cin=64, cout=64, act="silu", res="after", cta_pair=5)
+case("auto-big-yolos-64", mode="tma", n=32, h=80, w=80, k=3, p=1, cin=64, cout=64, act="silu", res="after")
+
 
 def run_case(idx: int) -> dict:
     import torch

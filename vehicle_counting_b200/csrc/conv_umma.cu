@@ -72,6 +72,13 @@ struct ConvParams {
   int split_b;         // A_TMA single-CTA: weight tiles are issued by a second producer warp
   int a_tiled;         // A_TMA, 1x1/s1/p0: A is the plain [M][C] matrix -> tiled-mode TMA instead of im2col mode
   int epi_kind;        // 0: generic epilogue; 1..8: specialised instance (epi_kind_of)
+  // patch mode (3x3/s1/p1): an M tile is R output rows x Xs output columns of one image; its input patch of (R+2) x (Xs+2)
+  // pixels sits in shared memory once per 64-channel chunk and the nine taps read it through shifted descriptors
+  int patch_R, patch_Xs, patch_Lp, patch_xsegs, patch_ytiles;
+  int patch_box_bytes;   // bytes one patch TMA box delivers = (R+2) * Lp * 128
+  int patch_stage_bytes; // shared memory per patch stage (>= (128 + 2*Lp + 2) rows, multiple of 1024)
+  int patch_out_bytes;   // bytes of one output / residual box = R * Xs * 128
+  int a_stages, b_stages;
   int kchains;         // 1, 2 or 4 accumulators per tile: K steps are dealt round-robin to independent accumulation chains
                        // (dependent tcgen05.mma on ONE accumulator issue ~200 clk apart), the epilogue sums them
   int cout_pad;        // n_tiles * block_n = length of the packed bias
@@ -300,7 +307,7 @@ __device__ __forceinline__ float act_fast(float v) {
   return v;
 }
 
-template <int ACT, int RES, bool F32OUT, bool M256, bool TWO_CTA = false>
+template <int ACT, int RES, bool F32OUT, bool M256, bool TWO_CTA = false, bool PATCH = false>
 __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CUtensorMap* tmap_out_ptr, const CUtensorMap* tmap_res_ptr,
                                                    uint32_t tmem_base, uint32_t out_stage, uint32_t bias_smem, uint32_t res_bar0,
                                                    uint32_t tmem_full0, uint32_t tmem_empty0, int first_tile = (int)blockIdx.x,
@@ -329,19 +336,48 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
   constexpr uint32_t STAGE_BYTES = (uint32_t)TILE_M * 128u;
   const int num_sub = (p.block_n + SUB_COLS - 1) / SUB_COLS;
   const bool issuer = threadIdx.x == 0;
-  const uint32_t row_off = (uint32_t)row_in_tile * 128u;
-  const int sw = row_in_tile & 7;
+  // PATCH: accumulator row m is lattice point (i, j) = (m / Lp, m % Lp) of the R x (Xs+2) output lattice; columns j >= Xs and
+  // rows i >= R are junk.  Valid points are staged densely (row i*Xs + j) so that one 4-D TMA box {64, Xs, R, 1} stores them.
+  const int lat_i = PATCH ? row_in_tile / p.patch_Lp : 0;
+  const int lat_j = PATCH ? row_in_tile - lat_i * p.patch_Lp : 0;
+  const bool lat_ok = !PATCH || (lat_i < p.patch_R && lat_j < p.patch_Xs);
+  const int stage_row = PATCH ? lat_i * p.patch_Xs + lat_j : row_in_tile;
+  const uint32_t row_off = (uint32_t)stage_row * 128u;
+  const int sw = stage_row & 7;
+  const uint32_t res_bytes = PATCH ? (uint32_t)p.patch_out_bytes : STAGE_BYTES;
+  auto issue_res_load = [&](uint32_t bar, uint32_t dst, int c0, int mt) {
+    mbar_arrive_expect_tx(bar, res_bytes);
+    if (PATCH) {
+      const int per_img = p.patch_ytiles * p.patch_xsegs;
+      const int ni = mt / per_img, rem = mt - ni * per_img;
+      const int yt = rem / p.patch_xsegs, xs = rem - yt * p.patch_xsegs;
+      tma_load_4d(tmap_res_ptr, bar, dst, c0, xs * p.patch_Xs, yt * p.patch_R, ni);
+    } else {
+      tma_load_2d(tmap_res_ptr, bar, dst, c0, mt * TILE_M);
+    }
+  };
+  auto issue_store = [&](uint32_t src, int c0, int mt) {
+    if (PATCH) {
+      const int per_img = p.patch_ytiles * p.patch_xsegs;
+      const int ni = mt / per_img, rem = mt - ni * per_img;
+      const int yt = rem / p.patch_xsegs, xs = rem - yt * p.patch_xsegs;
+      tma_store_4d(tmap_out_ptr, src, c0, xs * p.patch_Xs, yt * p.patch_R, ni);
+    } else {
+      tma_store_2d(tmap_out_ptr, src, c0, mt * TILE_M);
+    }
+  };
   const bool two_bufs = p.out_stage_bufs == 2;
-  const uint32_t acc_stride = (uint32_t)p.block_n * (M256 ? 2u : (uint32_t)p.kchains);
-  const int kchains = M256 ? 1 : p.kchains;
+  // TMEM layout of one accumulator stage: [K chain][row chain (M256 only)][block_n columns]
+  const uint32_t kstride = (uint32_t)p.block_n * (M256 ? 2u : 1u);
+  const int kchains = p.kchains;
+  const uint32_t acc_stride = kstride * (uint32_t)kchains;
   uint32_t tile_iter = 0, sub_count = 0;
   long long t_wait = 0, t_sync = 0;
   const long long t_begin = prof_clock(issuer ? p.prof : nullptr);
   if (RES != VCB_RES_NONE && issuer && first_tile < total_tiles) {      // residual of the first sub-tile
     const int pm0 = first_tile / p.n_tiles, nt0 = first_tile - pm0 * p.n_tiles;
     const int mt0 = TWO_CTA ? 2 * pm0 + cta_rank : pm0;
-    mbar_arrive_expect_tx(res_bar0, STAGE_BYTES);
-    tma_load_2d(tmap_res_ptr, res_bar0, out_stage, nt0 * p.block_n, mt0 * TILE_M);
+    issue_res_load(res_bar0, out_stage, nt0 * p.block_n, mt0);
   }
   for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++tile_iter) {
     const int pm_tile = tile / p.n_tiles;
@@ -379,8 +415,8 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
         if (kchains > 1 && ngroups > 0) {                  // sum the K chains (fp32)
           for (int c = 1; c < kchains; ++c) {
             uint32_t w[NG][16];
-            tmem_ld_x16(t_row + (uint32_t)(c * p.block_n + col_base), w[0]);
-            if (NG == 2 && ngroups > 1) tmem_ld_x16(t_row + (uint32_t)(c * p.block_n + col_base + 16), w[NG - 1]);
+            tmem_ld_x16(t_row + (uint32_t)c * kstride + (uint32_t)col_base, w[0]);
+            if (NG == 2 && ngroups > 1) tmem_ld_x16(t_row + (uint32_t)c * kstride + (uint32_t)(col_base + 16), w[NG - 1]);
             tmem_ld_wait();
 #pragma unroll
             for (int g = 0; g < NG; ++g)
@@ -397,7 +433,7 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const uint32_t src = stage_buf + row_off + (uint32_t)(((colhalf * 4 + g * 2 + hh) ^ sw) << 4);
-              if (g < ngroups)
+              if (g < ngroups && lat_ok)
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv[g][hh].x), "=r"(rv[g][hh].y), "=r"(rv[g][hh].z), "=r"(rv[g][hh].w) : "r"(src));
               else
                 rv[g][hh] = make_uint4(0u, 0u, 0u, 0u);
@@ -445,7 +481,9 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
           }
           // staged row = 128 bytes; this pass owns 16-byte chunks [colhalf*4, colhalf*4+4); 128-byte swizzle
           const uint32_t row_addr = stage_buf + row_off;
-          if (F32OUT) {            // 16 floats = 4 chunks
+          if (!lat_ok) {
+            // junk lattice point (patch mode): nothing to stage
+          } else if (F32OUT) {            // 16 floats = 4 chunks
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint32_t dst = row_addr + (uint32_t)(((colhalf * 4 + i) ^ sw) << 4);
@@ -473,7 +511,7 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
       if (issuer && two_bufs) tma_store_wait_read<0>();   // the other buffer (next sub-tile's target) is free after the barrier
       asm volatile("bar.sync 2, 256;" ::: "memory");
       if (issuer) {
-        tma_store_2d(tmap_out_ptr, stage_buf, n_base + sub * SUB_COLS, m_tile * TILE_M);
+        issue_store(stage_buf, n_base + sub * SUB_COLS, m_tile);
         tma_store_commit();
         if (RES != VCB_RES_NONE) {                        // request the residual of the next sub-tile (maybe of the next tile)
           int nt = tile, nsub = sub + 1;
@@ -483,8 +521,7 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
             const int npm = nt / p.n_tiles, nn = nt - npm * p.n_tiles;
             const int nm = TWO_CTA ? 2 * npm + cta_rank : npm;
             const uint32_t nb = two_bufs ? ((sub_count + 1u) & 1u) : 0u;
-            mbar_arrive_expect_tx(res_bar0 + 8u * nb, STAGE_BYTES);
-            tma_load_2d(tmap_res_ptr, res_bar0 + 8u * nb, out_stage + nb * STAGE_BYTES, nn * p.block_n + nsub * SUB_COLS, nm * TILE_M);
+            issue_res_load(res_bar0 + 8u * nb, out_stage + nb * STAGE_BYTES, nn * p.block_n + nsub * SUB_COLS, nm);
           }
         }
       }
@@ -1001,6 +1038,190 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   if (warp == kMmaWarp) tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Patch mode (3x3 / stride 1 / pad 1, TMA path): the input of an M tile is loaded ONCE per 64-channel chunk.
+// An M tile is R output rows x Xs output columns of one image.  Its input patch, (R+2) x (Xs+2) pixels x 64 channels, arrives
+// by one tiled 4-D TMA box (borders and image edges zero-filled by the TMA unit) and sits in shared memory as consecutive
+// 128-byte rows, pixel (py, px) at row py*Lp + px, Lp = Xs+2.  Accumulator row m = i*Lp + j is output pixel (y0+i, x0+j); for
+// filter tap (r, s) its operand row is m + r*Lp + s, so the tap's A operand is the SAME shared-memory patch read through a
+// descriptor whose start address is shifted by (r*Lp + s) rows.  tcgen05.mma applies the 128-byte swizzle to absolute
+// shared-memory address bits, so any 128-byte-aligned start is legal with base_offset = 0 (tools/umma_shift_probe.cu,
+// profiles/r01_umma_shift_probe.txt).  Lattice columns j >= Xs (and rows i >= R) are junk: they are computed and dropped.
+// Versus one im2col box per tap this cuts the L2 -> shared-memory traffic of A by 9 / ((1+2/R)(1+2/Xs)) (3.5-5x); the weight
+// tiles stream through their own ring (own producer warp) or stay resident when the packed B fits.
+// The lattice of a tile has up to 256 rows: rows 0-127 and 128-255 are two accumulators (two independent MMA chains -- dependent
+// tcgen05.mma on one accumulator issue ~190 clk apart) that share every weight tile.
+// Warps: 0-7 epilogue (0-3 chain 0, 4-7 chain 1), 8 patch producer, 9 MMA issuer (+ TMEM), 10 weight producer.  One CTA per SM.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kThreadsPatch = 352;
+constexpr int kPatchMaxA = 4, kPatchMaxB = 8;
+
+__global__ void __launch_bounds__(kThreadsPatch, 1)
+conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t a_region = smem_base;
+  const uint32_t b_region = a_region + (uint32_t)(p.a_stages * p.patch_stage_bytes);
+  const uint32_t b_bytes = p.b_resident ? (uint32_t)p.b_res_bytes : (uint32_t)p.b_stages * b_tile_bytes;
+  const uint32_t out_stage = b_region + b_bytes;
+  const uint32_t bars = out_stage + (uint32_t)p.out_stage_bytes;
+  auto afull = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto aempty = [&](int s) { return bars + 8u * (uint32_t)(kPatchMaxA + s); };
+  auto bfull = [&](int s) { return bars + 8u * (uint32_t)(2 * kPatchMaxA + s); };
+  auto bempty = [&](int s) { return bars + 8u * (uint32_t)(2 * kPatchMaxA + kPatchMaxB + s); };
+  const uint32_t tfull0 = bars + 8u * (2 * kPatchMaxA + 2 * kPatchMaxB);
+  const uint32_t tempty0 = tfull0 + 16u;
+  const uint32_t tmem_slot = tempty0 + 16u;
+  const uint32_t bres_bar = tmem_slot + 8u;
+  const uint32_t res_bar0 = tmem_slot + 16u;
+  const uint32_t bias_smem = tmem_slot + 32u;
+  uint8_t* tail_gen = smem_raw + (tmem_slot - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_gen);
+  float* bias_gen = reinterpret_cast<float*>(tail_gen + 32);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.cout_pad; i += blockDim.x) bias_gen[i] = __ldg(p.bias + i);
+  griddep_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPatchMaxA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < kPatchMaxB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8u * a, 1); mbar_init(tempty0 + 8u * a, kNumEpilogueThreads); }
+    mbar_init(bres_bar, 1);
+    mbar_init(res_bar0, 1);
+    mbar_init(res_bar0 + 8u, 1);
+    fence_mbar_init();
+  }
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    if (p.res_mode != VCB_RES_NONE) tma_prefetch_desc(&tmap_res);
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_wait();
+
+  const int chunks = p.chunks_per_tap;
+  const int per_img = p.patch_ytiles * p.patch_xsegs;
+  const uint32_t bc = (uint32_t)(p.block_n * kBlockK * 2);                     // one (tap, chunk) weight tile
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {         // ---- patch producer: one 4-D box per (tile, channel chunk)
+      uint32_t ita = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles;
+        const int ni = mt / per_img, rem = mt - ni * per_img;
+        const int yt = rem / p.patch_xsegs, xs = rem - yt * p.patch_xsegs;
+        for (int c = 0; c < chunks; ++c, ++ita) {
+          const int sa = ita % p.a_stages;
+          mbar_wait(aempty(sa), ((ita / p.a_stages) & 1u) ^ 1u, p.fault, FAULT_EMPTY_WAIT, 600 + sa);
+          mbar_arrive_expect_tx(afull(sa), (uint32_t)p.patch_box_bytes);
+          tma_load_4d(&tmap_a, afull(sa), a_region + (uint32_t)(sa * p.patch_stage_bytes), c * kBlockK, xs * p.patch_Xs - 1,
+                      yt * p.patch_R - 1, ni);
+        }
+      }
+    }
+  } else if (warp == kGatherWarp0) {
+    if (lane == 0) {         // ---- weight producer
+      if (p.b_resident) {
+        if ((int)blockIdx.x < p.num_tiles) {
+          mbar_arrive_expect_tx(bres_bar, (uint32_t)p.total_chunks * bc);
+          for (int kc = 0; kc < p.total_chunks; ++kc) tma_load_2d(&tmap_b, bres_bar, b_region + (uint32_t)kc * bc, kc * kBlockK, 0);
+        }
+      } else {
+        uint32_t itb = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          const int nt = tile % p.n_tiles;
+          for (int c = 0; c < chunks; ++c)
+            for (int t = 0; t < 9; ++t, ++itb) {
+              const int sb = itb % p.b_stages;
+              mbar_wait(bempty(sb), ((itb / p.b_stages) & 1u) ^ 1u, p.fault, FAULT_EMPTY_WAIT, 620 + sb);
+              mbar_arrive_expect_tx(bfull(sb), b_tile_bytes);
+              tma_load_2d(&tmap_b, bfull(sb), b_region + (uint32_t)sb * b_tile_bytes, (t * chunks + c) * kBlockK, nt * p.block_n);
+            }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {         // ---- MMA issuer
+      const uint32_t idesc = umma_idesc_f16((uint32_t)p.block_n);
+      const uint64_t desc_hi = umma_desc_kmajor(0, 1024u, 2u);      // SWIZZLE_128B, 8-row groups 1024 B apart, base_offset 0
+      uint32_t ita = 0, itb = 0, tile_iter = 0;
+      if (p.b_resident && (int)blockIdx.x < p.num_tiles) mbar_wait(bres_bar, 0u, p.fault, FAULT_FULL_WAIT, 640);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
+        const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
+        const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
+        mbar_wait(tempty0 + 8u * acc, acc_ph ^ 1u, p.fault, FAULT_TMEM_EMPTY_WAIT, (int)acc);
+        tcgen05_fence_after();
+        // accumulators of a stage: [K chain kc][row chain: lattice rows 0-127 | 128-255][block_n]
+        const uint32_t d_tmem = tmem_base + acc * 2u * (uint32_t)(p.block_n * p.kchains);
+        uint32_t ks = 0;
+        const uint32_t kmask = (uint32_t)p.kchains - 1u;
+        for (int c = 0; c < chunks; ++c, ++ita) {
+          const int sa = ita % p.a_stages;
+          mbar_wait(afull(sa), (ita / p.a_stages) & 1u, p.fault, FAULT_FULL_WAIT, 650 + sa);
+          tcgen05_fence_after();
+          const uint32_t a_base = a_region + (uint32_t)(sa * p.patch_stage_bytes);
+#pragma unroll 1
+          for (int t = 0; t < 9; ++t) {
+            const int r = t / 3, sx = t - r * 3;
+            const uint32_t a_addr = a_base + (uint32_t)(r * p.patch_Lp + sx) * 128u;
+            uint32_t b_addr;
+            int sb = 0;
+            if (p.b_resident) {
+              b_addr = b_region + (uint32_t)(t * chunks + c) * bc;
+            } else {
+              sb = itb % p.b_stages;
+              mbar_wait(bfull(sb), (itb / p.b_stages) & 1u, p.fault, FAULT_FULL_WAIT, 660 + sb);
+              tcgen05_fence_after();
+              b_addr = b_region + (uint32_t)sb * b_tile_bytes;
+            }
+            const uint64_t a_desc = desc_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+            const uint64_t b_desc = desc_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k, ++ks) {      // 2 row chains x kchains K chains: independent accumulators sharing every weight tile
+              const uint32_t d = d_tmem + (ks & kmask) * 2u * (uint32_t)p.block_n;
+              const uint32_t accumulate = ks > kmask ? 1u : 0u;
+              umma_f16(d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
+              umma_f16(d + (uint32_t)p.block_n, a_desc + (uint64_t)(1024 + 2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
+            }
+            if (!p.b_resident) { umma_commit(bempty(sb)); ++itb; }
+          }
+          umma_commit(aempty(sa));
+        }
+        umma_commit(tfull0 + 8u * acc);
+      }
+    }
+  } else if (warp < kEpilogueWarps) {
+#define VCB_EPI_CASE(K, ACT, RES, F32) \
+    case K: conv_epilogue_fast<ACT, RES, F32, true, false, true>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tfull0, tempty0); break;
+    switch (p.epi_kind) {
+      VCB_EPI_CASE(1, VCB_ACT_SILU, VCB_RES_NONE, false)
+      VCB_EPI_CASE(2, VCB_ACT_SILU, VCB_RES_AFTER_ACT, false)
+      VCB_EPI_CASE(3, VCB_ACT_SILU_TANH, VCB_RES_NONE, false)
+      VCB_EPI_CASE(4, VCB_ACT_SILU_TANH, VCB_RES_AFTER_ACT, false)
+      VCB_EPI_CASE(5, VCB_ACT_RELU, VCB_RES_NONE, false)
+      VCB_EPI_CASE(6, VCB_ACT_RELU, VCB_RES_BEFORE_ACT, false)
+      VCB_EPI_CASE(7, VCB_ACT_NONE, VCB_RES_NONE, true)
+      VCB_EPI_CASE(8, VCB_ACT_NONE, VCB_RES_NONE, false)
+      default: break;
+    }
+#undef VCB_EPI_CASE
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight packing: OIHW fp32 (BN folded) -> [cout_pad][K_pad] fp16, K index = (tap * cin_pad + c) for
 // the 64-channel-chunk modes and (tap * 4 + c) for A_C4
@@ -1041,6 +1262,8 @@ struct ConvGeom {
   int tile_m;           // 128 or 256
   int epi_kind;         // specialised epilogue instance (0 = generic)
   int kchains;          // K-split accumulation chains per tile (1, 2, 4)
+  int patch;            // patch mode (conv_patch_kernel)
+  int patch_R, patch_Xs, patch_Lp, patch_xsegs, patch_ytiles, patch_stage_bytes, a_stages, b_stages;
   int b_resident, b_res_bytes;
   size_t smem_bytes;
 };
@@ -1118,8 +1341,55 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
   g.epi_kind = (g.a_mode == A_TMA && d.reserved[0] == 0) ? epi_kind_of(d.act, d.res_mode, d.out_dtype == VCB_F32 ? 1 : 0) : 0;
   const size_t b_total = (size_t)g.total_chunks * g.block_n * g.bk * 2;
   const size_t tail0 = 1024 /*align slack*/ + 8 * (2 * kMaxStages + 4) + 16 + kBlockM * sizeof(RowInfo) + (size_t)g.cout_pad * 4 + 64;
-  g.m256 = 0; g.tile_m = kBlockM; g.b_resident = 0; g.b_res_bytes = 0; g.kchains = 1;
+  g.m256 = 0; g.tile_m = kBlockM; g.b_resident = 0; g.b_res_bytes = 0; g.kchains = 1; g.patch = 0;
   int chosen = 0;
+  // ---- patch mode: 3x3/s1/p1 with 64-channel chunks; reserved[3] == 5 forces it, == 1 (or any other forced mode) forbids it
+  {
+    const bool can = g.a_mode == A_TMA && !g.two_cta && g.epi_kind != 0 && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.pad == 1 && g.bk == 64;
+    const bool want = can && (d.reserved[3] == 5);
+    if (d.reserved[3] == 5 && !can) return set_error(VCB_ERR_INVALID, "conv: patch mode needs a 3x3/s1/p1 layer on the TMA path with 64-channel chunks");
+    if (want) {
+      // tile shape: R rows x Xs columns with R * (Xs + 2) <= 128, maximising useful rows per 128-row tile over the image
+      double best = 0.0;
+      for (int nseg = 1; nseg <= 16; ++nseg) {
+        const int xs = (d.w + nseg - 1) / nseg;
+        if (xs + 2 > 128) continue;
+        int r = 256 / (xs + 2);
+        if (r > d.h) r = d.h;
+        if (r < 1) continue;
+        const int yt = (d.h + r - 1) / r;
+        const double util = (double)d.h * d.w / ((double)yt * nseg * 256.0);
+        if (util > best + 1e-9) { best = util; g.patch_R = r; g.patch_Xs = xs; g.patch_xsegs = nseg; g.patch_ytiles = yt; }
+      }
+      g.patch_Lp = g.patch_Xs + 2;
+      g.patch_stage_bytes = ((256 + 2 * g.patch_Lp + 2) * 128 + 1023) / 1024 * 1024;
+      const size_t budget = 227 * 1024;
+      const size_t tailp = 1024 + 8 * (2 * 4 + 2 * 8) + 32 + 16 + 16 + (size_t)g.cout_pad * 4 + 64;
+      for (int res = 1; res >= 0 && !chosen; --res) {
+        if (res && !(g.n_tiles == 1 && b_total <= 112 * 1024)) continue;
+        const size_t b_res = res ? (b_total + 1023) / 1024 * 1024 : 0;
+        for (int bufs = 2; bufs >= 1 && !chosen; --bufs)
+          for (int as = 3; as >= 2 && !chosen; --as) {
+            const size_t fixed = tailp + b_res + (size_t)bufs * 2 * kStageOutBytes + (size_t)as * g.patch_stage_bytes;
+            if (fixed > budget) continue;
+            int bs = res ? 0 : (int)((budget - fixed) / ((size_t)g.block_n * 128));
+            if (bs > 8) bs = 8;
+            if (!res && bs < 3) continue;
+            g.patch = 1; g.a_stages = as; g.b_stages = bs; g.b_resident = res; g.b_res_bytes = (int)b_res; g.out_bufs = bufs;
+            // narrow N: the two row chains do not cover the ~190 clk dependent-issue interval -> split K over two more accumulators
+            g.kchains = (g.block_n <= 64 && d.reserved[1] != 3) ? 2 : 1;
+            g.ctas_per_sm = 1; g.acc_stages = (4 * g.kchains * g.block_n <= 512) ? 2 : 1;
+            g.tile_m = 2 * kBlockM;
+            int pow2 = 32;
+            while (pow2 < g.acc_stages * 2 * g.kchains * g.block_n) pow2 <<= 1;
+            g.tmem_cols = pow2; g.stages = as;
+            g.smem_bytes = fixed + (size_t)bs * g.block_n * 128;
+            chosen = 1;
+          }
+      }
+      if (!chosen && d.reserved[3] == 5) return set_error(VCB_ERR_INVALID, "conv: patch mode does not fit in shared memory");
+    }
+  }
   // ---- 256-row tiles (two accumulator chains, one CTA per SM): halves the weight bytes each SM pulls from L2 per output.
   // Needs the specialised epilogue, N <= 192 (three 56 KiB stages must fit) and at least two waves of 256-row tiles
   // (reserved[3] == 3 forces it, == 1 forbids it).
@@ -1127,7 +1397,7 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
     const bool want = g.a_mode == A_TMA && !g.two_cta && g.epi_kind != 0 && g.block_n <= 192 && d.reserved[3] != 1 &&
                       d.reserved[3] == 3;     // opt-in: measured at or below the two-CTA 128-row mode on every layer shape
     if (d.reserved[3] == 3 && !want) return set_error(VCB_ERR_INVALID, "conv: 256-row tiles need the TMA path, a specialised epilogue and N <= 192");
-    if (want) {
+    if (want && !chosen) {
       const size_t budget = 227 * 1024;
       const size_t stage_out = 2 * (size_t)kStageOutBytes;                  // 256 rows x 128 B
       for (int res = 1; res >= 0 && !chosen; --res) {
@@ -1326,6 +1596,15 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   p.cout_pad = g.cout_pad;
   p.epi_kind = g.epi_kind;
   p.kchains = g.kchains;
+  if (g.patch) {
+    p.patch_R = g.patch_R; p.patch_Xs = g.patch_Xs; p.patch_Lp = g.patch_Lp; p.patch_xsegs = g.patch_xsegs; p.patch_ytiles = g.patch_ytiles;
+    p.patch_box_bytes = (g.patch_R + 2) * g.patch_Lp * 128;
+    p.patch_stage_bytes = g.patch_stage_bytes;
+    p.patch_out_bytes = g.patch_R * g.patch_Xs * 128;
+    p.a_stages = g.a_stages; p.b_stages = g.b_stages;
+    p.m_tiles = d.n * g.patch_ytiles * g.patch_xsegs;
+    p.num_tiles = p.m_tiles * g.n_tiles;
+  }
   if (d.reserved[0] == 4) { p.acc_stages = 1; }
   p.out_stage_bufs = g.out_bufs;
   p.out_stage_bytes = g.out_bufs * (g.tile_m * 128);
@@ -1336,6 +1615,60 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   memset(&ta, 0, sizeof(ta));
   memset(&to, 0, sizeof(to));
   memset(&tr, 0, sizeof(tr));
+  if (g.patch) {
+    // 4-D views (C, W, H, N): input patch box {64, Xs+2, R+2, 1}; output / residual box {64 | 32, Xs, R, 1}; weights as usual
+    const cuuint32_t estr4[4] = {1, 1, 1, 1};
+    {
+      const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
+      const cuuint64_t strides[3] = {(cuuint64_t)d.cin_pitch * 2, (cuuint64_t)d.w * d.cin_pitch * 2, (cuuint64_t)d.h * d.w * d.cin_pitch * 2};
+      const cuuint32_t box[4] = {64u, (cuuint32_t)g.patch_Lp, (cuuint32_t)(g.patch_R + 2), 1u};
+      const CUresult r = state().encode_tiled(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr4,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(patch input) failed: %d", (int)r);
+    }
+    {
+      const bool f32 = d.out_dtype == VCB_F32;
+      const cuuint64_t es = f32 ? 4 : 2;
+      const cuuint64_t dims[4] = {(cuuint64_t)d.cout, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
+      const cuuint64_t strides[3] = {(cuuint64_t)d.cout_pitch * es, (cuuint64_t)d.w * d.cout_pitch * es, (cuuint64_t)d.h * d.w * d.cout_pitch * es};
+      const cuuint32_t box[4] = {(cuuint32_t)(f32 ? 32 : 64), (cuuint32_t)g.patch_Xs, (cuuint32_t)g.patch_R, 1u};
+      const CUresult r = state().encode_tiled(&to, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, y, dims, strides, box,
+                                              estr4, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(patch output) failed: %d", (int)r);
+    }
+    if (d.res_mode != VCB_RES_NONE) {
+      const cuuint64_t dims[4] = {(cuuint64_t)d.cout, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
+      const cuuint64_t strides[3] = {(cuuint64_t)d.res_pitch * 2, (cuuint64_t)d.w * d.res_pitch * 2, (cuuint64_t)d.h * d.w * d.res_pitch * 2};
+      const cuuint32_t box[4] = {64u, (cuuint32_t)g.patch_Xs, (cuuint32_t)g.patch_R, 1u};
+      const CUresult r = state().encode_tiled(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(residual), dims, strides, box, estr4,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(patch residual) failed: %d", (int)r);
+    }
+    {
+      const cuuint64_t dims[2] = {(cuuint64_t)g.k_pad, (cuuint64_t)g.cout_pad};
+      const cuuint64_t strides[1] = {(cuuint64_t)g.k_pad * 2};
+      const cuuint32_t box[2] = {64u, (cuuint32_t)g.block_n};
+      const cuuint32_t estr[2] = {1, 1};
+      const CUresult r = state().encode_tiled(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+      const cudaError_t e = cudaFuncSetAttribute(conv_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv patch)");
+      attr_set = true;
+    }
+    const int grid = p.num_tiles < state().num_sms ? p.num_tiles : state().num_sms;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    fill_launch_config(cfg, attr, grid, kThreadsPatch, g.smem_bytes, st);
+    return check_cuda(cudaLaunchKernelEx(&cfg, conv_patch_kernel, ta, tb, to, tr, p), "conv (patch) launch");
+  }
   if (p.epi_kind != 0 && d.res_mode != VCB_RES_NONE) {   // residual: [M][cout] fp16 view with row pitch res_pitch, same boxes as the output
     const cuuint64_t dims[2] = {(cuuint64_t)d.cout, (cuuint64_t)g.M};
     const cuuint64_t strides[1] = {(cuuint64_t)d.res_pitch * 2};

@@ -143,6 +143,19 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint32_t bar, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 4-D tiled load (c0 innermost); out-of-range coordinates (negative included) are zero-filled
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// 4-D tiled store smem -> global (bulk async group); elements outside the tensor are not written
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // 4-D im2col load over an NHWC tensor: base pixel (c, w, h, n) + filter offsets (s, r)
 __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c, int w,
                                                    int h, int n, uint16_t off_w, uint16_t off_h) {
