@@ -279,6 +279,17 @@ def run_ours(a) -> dict:
     totals = [sum(c[i] for c in per_rank) for i in range(3)]
 
     peaks = _peaks()
+    # DRAM bytes of the conv launches of one step, from the committed ncu launch list of this very command at the default workload
+    # (profiles/r01_launch_summary.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the conv kernels of a step)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_launch_summary.json")) as f:
+            ls = json.load(f)
+        if (a.model, a.size, B, R_) == ("yolov5m", 640, 64, 64):
+            traffic = int(ls["conv_kernels"]["dram_bytes_per_step"])
+            traffic_src = "profiles/r01_launch_summary.json (ncu, batch 64)"
+    except Exception:
+        pass
     out = None
     if rank == 0:
         fps = world * B / (ms_dev / 1e3)
@@ -293,7 +304,7 @@ def run_ours(a) -> dict:
                "gpu_launches": int(launches * a.steps),
                "roofline": {"kernel": "conv_umma_kernel (all conv launches of one step)", "bound": "tensor", "achieved": ach,
                             "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"],
-                            "frac_of_burst": ach / peaks["tflops_burst"], "peak_source": peaks["source"], "traffic": None,
+                            "frac_of_burst": ach / peaks["tflops_burst"], "peak_source": peaks["source"], "traffic": traffic, "traffic_source": traffic_src,
                             "conv_gflop_per_step": conv_flops / 1e9, "conv_ms_per_step": conv_ms, "other_kernels_ms_per_step": other_ms,
                             "whole_step_tensor_frac": conv_flops / (ms_dev / 1e3) / 1e12 / peaks["tflops_sustained"]},
                "counters": {"frames": totals[0], "detections": totals[1], "crops": totals[2], "detections_last_step_rank0": det_total},
@@ -312,7 +323,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="yolov5m")
     ap.add_argument("--size", type=int, default=640)
-    ap.add_argument("--batch", type=int, default=32, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
     ap.add_argument("--rois", type=int, default=64, help="ReID crops per frame")
     ap.add_argument("--obj-bias", type=float, default=-3.0, help="synthetic Detect objectness bias (controls #candidates)")
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the CPU reference arm (bounded sample)")

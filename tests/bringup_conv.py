@@ -213,6 +213,15 @@ case("auto-big-yolos-32", mode="tma", n=32, h=160, w=160, k=3, p=1, cin=32, cout
 case("patch-big-yolos-64", mode="tma", n=32, h=80, w=80, k=3, p=1, cin=64, cout=64, act="silu", res="after", cta_pair=5)
 case("auto-big-yolos-64", mode="tma", n=32, h=80, w=80, k=3, p=1, cin=64, cout=64, act="silu", res="after")
 
+# experiment: mainloop only (no epilogue, results garbage) of 256-pixel tiles: two chained M=128 x N=cout MMAs per K step (dbg1=6)
+# against ONE swapped MMA, weights as A (M=128), 256 pixels as N (dbg1=7); and the production 128-row two-CTA mode (epi_direct=3)
+for _nm, _kw in (("reid-l1", dict(n=1024, h=25, w=25, k=3, p=1, cin=64, cout=64)), ("reid-l2", dict(n=1024, h=13, w=13, k=3, p=1, cin=128, cout=128)),
+                 ("yolo-48", dict(n=16, h=160, w=160, k=3, p=1, cin=48, cout=48)), ("yolo-96", dict(n=32, h=80, w=80, k=3, p=1, cin=96, cout=96)),
+                 ("yolo-1x1-96", dict(n=32, h=160, w=160, k=1, cin=96, cout=96))):
+    case(f"xq-m256-noepi-{_nm}", mode="tma", act="relu", cta_pair=3, dbg1=6, **_kw)
+    case(f"xq-swap-noepi-{_nm}", mode="tma", act="relu", cta_pair=3, dbg1=7, **_kw)
+    case(f"xq-m128-noepi-{_nm}", mode="tma", act="relu", cta_pair=1, epi_direct=3, **_kw)
+
 
 def run_case(idx: int) -> dict:
     import torch

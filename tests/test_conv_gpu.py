@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import bringup_conv as B   # noqa: E402
 
-_SKIP = ("sweep-", "prof-", "-big", "im2col-1x1-96", "xp-")          # timing sweeps / large tensors: run by bringup_conv.py itself
+_SKIP = ("sweep-", "prof-", "-big", "im2col-1x1-96", "xp-", "xq-")          # timing sweeps / large tensors: run by bringup_conv.py itself
 _CASES = [(i, n) for i, (n, _) in enumerate(B.CASES) if not any(k in n for k in _SKIP)]
 # the one-MUFU SiLU (tanh.approx.f32, 2^-11 relative) is allowed twice the bar
 _TOL = {"default": 1e-3, "silu_tanh": 2e-3}

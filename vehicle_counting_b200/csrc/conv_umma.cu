@@ -67,6 +67,7 @@ struct ConvParams {
   int epi_direct;      // 1: per-thread 16-byte global stores (debug / cross-check); 0: staged TMA store
   int c4_wide;         // A_C4: 16-byte granules (two taps) instead of 8-byte ones
   int dbg_skip_epilogue;   // timing experiment: epilogue only hands the accumulator back (results are garbage)
+  int dbg_swap;            // timing experiment (256-row tiles): ONE tcgen05.mma with the weights as A (M=128) and 256 pixels as N
   int b_resident;      // A_TMA single-CTA, one N tile, small weights: the whole packed B stays in shared memory
   int b_res_bytes;     // bytes of the resident weight region (multiple of 1024)
   int split_b;         // A_TMA single-CTA: weight tiles are issued by a second producer warp
@@ -389,6 +390,11 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
     mbar_wait(tmem_full0 + 8u * acc, acc_ph, p.fault, FAULT_TMEM_FULL_WAIT, (int)acc);
     t_wait += prof_clock(issuer ? p.prof : nullptr) - tw0;
     tcgen05_fence_after();
+    if (p.dbg_skip_epilogue) {
+      tcgen05_fence_before();
+      mbar_arrive(tmem_empty0 + 8u * acc);
+      continue;
+    }
     const int row = m_tile * TILE_M + row_in_tile;
     const bool row_ok = row < p.M;
     const uint32_t t_row = tmem_base + acc * acc_stride + (M256 ? (uint32_t)(hi * p.block_n) : 0u) + ((uint32_t)(q * 32) << 16);
@@ -721,7 +727,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
               for (int k = 0; k < ksteps; ++k) {
                 // +32 bytes per UMMA_K step inside the swizzle row: +2 in the (addr >> 4) field
-                if (M256) {    // two row chains: rows 0..127 and 128..255 of the same chunk against the same weight tile
+                if (M256 && p.dbg_swap) {   // experiment: D^T[128 x 256 pixels] = W[128 x 16] * X[256 x 16]^T, one instruction per K step
+                  umma_f16(tmem_base + acc * 256u, b_desc + (uint64_t)(2 * k), a_desc + (uint64_t)(2 * k), umma_idesc_f16(256u), (kit | g | k) != 0 ? 1u : 0u);
+                } else if (M256) {    // two row chains: rows 0..127 and 128..255 of the same chunk against the same weight tile
                   umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kit | g | k) != 0 ? 1u : 0u);
                   umma_f16(d_tmem + (uint32_t)p.block_n, a_desc + (uint64_t)((a_chain >> 4) + 2 * k), b_desc + (uint64_t)(2 * k), idesc,
                            (kit | g | k) != 0 ? 1u : 0u);
@@ -1592,7 +1600,9 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   p.epi_direct = d.reserved[0] == 1 ? 1 : 0;
   p.split_b = 0;   // (a second producer thread for the weight tiles measured no gain; code path kept for experiments only)
   p.b_resident = g.b_resident; p.b_res_bytes = g.b_res_bytes;
-  p.dbg_skip_epilogue = d.reserved[0] == 3 ? 1 : 0;
+  p.dbg_skip_epilogue = (d.reserved[0] == 3 || d.reserved[1] == 6 || d.reserved[1] == 7) ? 1 : 0;
+  p.dbg_swap = d.reserved[1] == 7 ? 1 : 0;
+  if (p.dbg_swap) { p.tmem_cols = 512; p.acc_stages = 2; }
   p.cout_pad = g.cout_pad;
   p.epi_kind = g.epi_kind;
   p.kchains = g.kchains;
