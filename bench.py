@@ -162,6 +162,9 @@ def run_ours(a) -> dict:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        # rank 0's stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
