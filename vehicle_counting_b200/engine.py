@@ -192,6 +192,7 @@ class YoloEngine:
         self.name = model_name or infer_model_name(state_dict)
         self.fp32_logits = fp32_logits
         self.a_mode = a_mode
+        self.fuse_c3 = os.environ.get("VCB_C3_FUSE", "1") != "0"      # C3: cv1|cv2 as one GEMM, bottlenecks in place
         gd, gw = MODEL_SCALES[self.name]
         det_w = state_dict["model.24.m.0.weight"]
         self.nc = det_w.shape[0] // 3 - 5
@@ -285,23 +286,39 @@ class YoloEngine:
                 hh, ww = hw[i]
                 cat = self._buf(hh, ww, 2 * c_)
                 nrep = reps[i]
-                # cv2 -> right half of the concat buffer
-                w_, b_ = fold_conv_bn(sd, pre + ".cv2", YOLO_BN_EPS, dev)
-                plan.conv(x, B, w_, b_, TRef(cat, c_, c_), 1, 1, 0, SILU, a_mode=self.a_mode)
-                # cv1 -> chain of bottlenecks -> left half
-                ping = [TRef(self._buf(hh, ww, c_), 0, c_), TRef(self._buf(hh, ww, c_), 0, c_)]
                 tmp = TRef(self._buf(hh, ww, c_), 0, c_)
-                cur = ping[0]
-                w_, b_ = fold_conv_bn(sd, pre + ".cv1", YOLO_BN_EPS, dev)
-                plan.conv(x, B, w_, b_, cur, 1, 1, 0, SILU, a_mode=self.a_mode)
-                for j in range(nrep):
-                    dst = TRef(cat, 0, c_) if j == nrep - 1 else ping[(j + 1) & 1]
-                    w1, b1 = fold_conv_bn(sd, f"{pre}.m.{j}.cv1", YOLO_BN_EPS, dev)
-                    plan.conv(cur, B, w1, b1, tmp, 1, 1, 0, SILU, a_mode=self.a_mode)
-                    w2, b2 = fold_conv_bn(sd, f"{pre}.m.{j}.cv2", YOLO_BN_EPS, dev)
-                    plan.conv(tmp, B, w2, b2, dst, 3, 1, 1, SILU, residual=cur if shortcut else None,
-                              res_mode=L.RES_AFTER_ACT, a_mode=self.a_mode)
-                    cur = dst
+                if self.fuse_c3:
+                    # cv1 and cv2 are 1x1 convolutions of the SAME input: one GEMM with N = 2*c_ (concatenated weights) writes both
+                    # halves of the concat buffer, so the input is read once.  The bottleneck chain then runs IN PLACE on the left
+                    # half: y <- y + cv2'(cv1'(y)) reads y only through the 1x1 (into tmp) and as the residual of the very tile it
+                    # overwrites (the epilogue stages the residual tile before it stores the result).
+                    wa, ba = fold_conv_bn(sd, pre + ".cv1", YOLO_BN_EPS, dev)
+                    wb, bb = fold_conv_bn(sd, pre + ".cv2", YOLO_BN_EPS, dev)
+                    plan.conv(x, B, torch.cat([wa, wb], 0), torch.cat([ba, bb], 0), TRef(cat, 0, 2 * c_), 1, 1, 0, SILU, a_mode=self.a_mode)
+                    cur = TRef(cat, 0, c_)
+                    for j in range(nrep):
+                        w1, b1 = fold_conv_bn(sd, f"{pre}.m.{j}.cv1", YOLO_BN_EPS, dev)
+                        plan.conv(cur, B, w1, b1, tmp, 1, 1, 0, SILU, a_mode=self.a_mode)
+                        w2, b2 = fold_conv_bn(sd, f"{pre}.m.{j}.cv2", YOLO_BN_EPS, dev)
+                        plan.conv(tmp, B, w2, b2, cur, 3, 1, 1, SILU, residual=cur if shortcut else None,
+                                  res_mode=L.RES_AFTER_ACT, a_mode=self.a_mode)
+                else:
+                    # cv2 -> right half of the concat buffer
+                    w_, b_ = fold_conv_bn(sd, pre + ".cv2", YOLO_BN_EPS, dev)
+                    plan.conv(x, B, w_, b_, TRef(cat, c_, c_), 1, 1, 0, SILU, a_mode=self.a_mode)
+                    # cv1 -> chain of bottlenecks -> left half
+                    ping = [TRef(self._buf(hh, ww, c_), 0, c_), TRef(self._buf(hh, ww, c_), 0, c_)]
+                    cur = ping[0]
+                    w_, b_ = fold_conv_bn(sd, pre + ".cv1", YOLO_BN_EPS, dev)
+                    plan.conv(x, B, w_, b_, cur, 1, 1, 0, SILU, a_mode=self.a_mode)
+                    for j in range(nrep):
+                        dst = TRef(cat, 0, c_) if j == nrep - 1 else ping[(j + 1) & 1]
+                        w1, b1 = fold_conv_bn(sd, f"{pre}.m.{j}.cv1", YOLO_BN_EPS, dev)
+                        plan.conv(cur, B, w1, b1, tmp, 1, 1, 0, SILU, a_mode=self.a_mode)
+                        w2, b2 = fold_conv_bn(sd, f"{pre}.m.{j}.cv2", YOLO_BN_EPS, dev)
+                        plan.conv(tmp, B, w2, b2, dst, 3, 1, 1, SILU, residual=cur if shortcut else None,
+                                  res_mode=L.RES_AFTER_ACT, a_mode=self.a_mode)
+                        cur = dst
                 w_, b_ = fold_conv_bn(sd, pre + ".cv3", YOLO_BN_EPS, dev)
                 plan.conv(TRef(cat, 0, 2 * c_), B, w_, b_, home[i], 1, 1, 0, SILU, a_mode=self.a_mode)
             elif kind == "SPPF":
