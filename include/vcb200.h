@@ -94,6 +94,11 @@ int vcb_frames_to_f16c4(const uint8_t* frames, void* out, int32_t n, int32_t h, 
 /* uint8 HWC3 frames -> fp16 space-to-depth NHWC16: out[n][y/2][x/2][(dy*2+dx)*3+c] = in/255, channels 12..15 zero
  * (h, w even).  Turns the 6x6/s2/p2 YOLOv5 stem into a 3x3/s1/p1 convolution that the im2col TMA can feed. */
 int vcb_frames_to_f16_s2d(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t stream);
+/* letterbox with an exact 2x reduction ([upstream] AutoShape: cv2.resize(INTER_LINEAR) + copyMakeBorder(114), reached from
+ * networks/yolo.py:70): dst uint8 [n][h1][w1][3] = 2x2 box mean with round-half-up of src uint8 [n][h0][w0][3] (h0, w0 even)
+ * placed at (top, left), pad_value elsewhere; bit-identical to cv2 for this ratio (1280x720 -> 640x360 inside 384x640) */
+int vcb_letterbox_half_u8(const uint8_t* src, int32_t n, int32_t h0, int32_t w0, uint8_t* dst, int32_t h1, int32_t w1,
+                          int32_t top, int32_t left, int32_t pad_value, vcb_stream_t stream);
 /* nearest x2 upsample of a channel slice into a channel slice (nn.Upsample(None, 2, 'nearest')) */
 int vcb_upsample2x(const void* src, int32_t src_pitch, void* dst, int32_t dst_pitch, int32_t n, int32_t h,
                    int32_t w, int32_t c, vcb_stream_t stream);

@@ -313,3 +313,39 @@ def test_reid_fused_stem_matches_unfused_reference(lib):
 def lib_fault():
     from vehicle_counting_b200 import _lib as L
     return L.last_fault()
+
+
+def test_letterbox_half_is_bit_identical_to_cv2(lib):
+    """vcb_letterbox_half_u8 against upstream's host letterbox (cv2.resize INTER_LINEAR + copyMakeBorder 114) for the exact 2x
+    ratio the reference hits on 1280x720 video (AutoShape size=640 -> 384x640), and through the YoloBackbone adapter."""
+    from oracle import yolov5 as Y
+    from vehicle_counting_b200 import ops
+    rng = np.random.default_rng(12)
+    for (h0, w0, h1, w1) in ((720, 1280, 384, 640), (96, 160, 64, 80), (64, 64, 32, 32)):
+        frames = rng.integers(0, 256, (3, h0, w0, 3), dtype=np.uint8)
+        want = np.stack([Y.letterbox(f, (h1, w1)) for f in frames])
+        dh, dw = (h1 - h0 // 2) / 2, (w1 - w0 // 2) / 2
+        top, left = int(round(dh - 0.1)), int(round(dw - 0.1))
+        dst = torch.full((3, h1, w1, 3), 7, dtype=torch.uint8, device=DEV)
+        ops.letterbox_half(torch.from_numpy(frames).to(DEV), 3, h0, w0, dst, h1, w1, top, left, 114)
+        np.testing.assert_array_equal(dst.cpu().numpy(), want)
+
+
+def test_adapter_device_letterbox_matches_host_letterbox(lib):
+    """YoloBackbone.detect on 1280x720 frames: the device letterbox path and the host (cv2) path give identical rows."""
+    from vehicle_counting_b200.networks import yolo as NY
+    from vehicle_counting_b200.weights import synth_yolov5_state_dict
+    rng = np.random.default_rng(13)
+    imgs = [rng.integers(0, 256, (720, 1280, 3), dtype=np.uint8) for _ in range(2)]
+    net = NY.YoloBackbone(None, 0.45, 0.25, 300, state_dict=synth_yolov5_state_dict("yolov5n", seed=0, obj_bias=1.0))
+    det_dev, cnt_dev = net.detect_raw(imgs)
+    det_dev, cnt_dev = det_dev.copy(), cnt_dev.copy()
+    eng = net._engine(2, 384, 640)
+    frames_dev = eng.frames.clone()
+    lb = [NY._letterbox(im, (384, 640)) for im in imgs]           # host path: already at the inference shape, no resize left
+    eng.set_scale([(720, 1280)] * 2)
+    eng.upload(torch.from_numpy(np.stack(lb)).pin_memory()); eng.forward()
+    det_host, cnt_host = eng.download()
+    assert torch.equal(eng.frames, frames_dev)                    # the network saw the same bytes on both paths
+    np.testing.assert_array_equal(cnt_dev, cnt_host)
+    np.testing.assert_array_equal(det_dev, det_host)

@@ -87,6 +87,7 @@ _SIGNATURES = {
     "vcb_conv_out_hw": ([C.POINTER(ConvDesc), C.POINTER(_I32), C.POINTER(_I32)], _I32),
     "vcb_frames_to_f16c4": ([_VP, _VP, _I32, _I32, _I32, _VP], _I32),
     "vcb_frames_to_f16_s2d": ([_VP, _VP, _I32, _I32, _I32, _VP], _I32),
+    "vcb_letterbox_half_u8": ([_VP, _I32, _I32, _I32, _VP, _I32, _I32, _I32, _I32, _I32, _VP], _I32),
     "vcb_upsample2x": ([_VP, _I32, _VP, _I32, _I32, _I32, _I32, _I32, _VP], _I32),
     "vcb_sppf_pool": ([_VP, _I32, _I32, _I32, _I32, _I32, _VP], _I32),
     "vcb_maxpool": ([_VP, _I32, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP], _I32),

@@ -12,6 +12,7 @@ namespace vcb {
 // other translation units
 int frames_to_f16c4(const uint8_t*, void*, int, int, int, cudaStream_t);
 int frames_to_f16_s2d(const uint8_t*, void*, int, int, int, cudaStream_t);
+int letterbox_half(const uint8_t*, int, int, int, uint8_t*, int, int, int, int, int, cudaStream_t);
 int upsample2x(const void*, int, void*, int, int, int, int, int, cudaStream_t);
 int sppf_pool(void*, int, int, int, int, int, cudaStream_t);
 int maxpool(const void*, int, void*, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -161,6 +162,11 @@ int vcb_frames_to_f16c4(const uint8_t* frames, void* out, int32_t n, int32_t h, 
 int vcb_frames_to_f16_s2d(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t st) {
   const int rc = require_init(); if (rc) return rc;
   return frames_to_f16_s2d(frames, out, n, h, w, (cudaStream_t)st);
+}
+int vcb_letterbox_half_u8(const uint8_t* src, int32_t n, int32_t h0, int32_t w0, uint8_t* dst, int32_t h1, int32_t w1, int32_t top,
+                          int32_t left, int32_t pad_value, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return letterbox_half(src, n, h0, w0, dst, h1, w1, top, left, pad_value, (cudaStream_t)st);
 }
 int vcb_upsample2x(const void* src, int32_t sp, void* dst, int32_t dp, int32_t n, int32_t h, int32_t w, int32_t c, vcb_stream_t st) {
   const int rc = require_init(); if (rc) return rc;

@@ -91,6 +91,42 @@ int frames_to_f16_s2d(const uint8_t* frames, void* out, int n, int h, int w, cud
   return check_cuda(cudaGetLastError(), "frames_to_f16_s2d launch");
 }
 
+// ---------------------------------------------------------------- letterbox, exact 2x reduction
+// upstream AutoShape letterboxes on the host: cv2.resize(INTER_LINEAR) + copyMakeBorder(114) (reached from
+// /root/reference/networks/yolo.py:70).  For an exact 2x reduction of uint8 data cv2's fixed-point bilinear equals the 2x2
+// box mean with round-half-up, (a+b+c+d+2)>>2 (checked bit for bit in tests/test_kernels_gpu.py), so a
+// 1280x720 frame becomes its 640x360 image inside the 384x640 inference frame on the device; one thread per output pixel.
+__global__ void letterbox_half_kernel(const uint8_t* __restrict__ src, int n, int h0, int w0, uint8_t* __restrict__ dst, int h1, int w1,
+                                      int top, int left, int pad) {
+  const int hh = h0 >> 1, wh = w0 >> 1;
+  const long long total = (long long)n * h1 * w1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w1);
+    long long t = i / w1;
+    const int y = (int)(t % h1);
+    const int b = (int)(t / h1);
+    const int sy = y - top, sx = x - left;
+    uint8_t* o = dst + i * 3;
+    if ((unsigned)sy < (unsigned)hh && (unsigned)sx < (unsigned)wh) {
+      const uint8_t* p0 = src + (((long long)b * h0 + 2 * sy) * w0 + 2 * sx) * 3;
+      const uint8_t* p1 = p0 + (long long)w0 * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[c] = (uint8_t)(((int)p0[c] + (int)p0[3 + c] + (int)p1[c] + (int)p1[3 + c] + 2) >> 2);
+    } else {
+      o[0] = o[1] = o[2] = (uint8_t)pad;
+    }
+  }
+}
+
+int letterbox_half(const uint8_t* src, int n, int h0, int w0, uint8_t* dst, int h1, int w1, int top, int left, int pad, cudaStream_t st) {
+  if (!src || !dst || n <= 0 || h0 <= 0 || w0 <= 0 || (h0 & 1) || (w0 & 1) || h1 <= 0 || w1 <= 0 || top < 0 || left < 0 ||
+      top + h0 / 2 > h1 || left + w0 / 2 > w1 || pad < 0 || pad > 255)
+    return set_error(VCB_ERR_INVALID, "letterbox_half: bad argument (even source size; the halved image must fit at (top, left))");
+  const long long total = (long long)n * h1 * w1;
+  letterbox_half_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, n, h0, w0, dst, h1, w1, top, left, pad);
+  return check_cuda(cudaGetLastError(), "letterbox_half launch");
+}
+
 // ---------------------------------------------------------------- nearest x2 upsample into a channel slice
 __global__ void upsample2x_kernel(const uint4* __restrict__ src, int src_pitch8, uint4* __restrict__ dst, int dst_pitch8, int n,
                                   int h, int w, int c8) {

@@ -69,34 +69,41 @@ __global__ void __launch_bounds__(256) roi_stem_patches_kernel(const VcbRoiDesc 
     }
   }
   __syncthreads();
-  // im2col rows: 16-byte chunk q of row `row` of block (by, bx) holds K elements [8q, 8q+8), k = (r*3+s)*3 + c.
-  // i = tid + 256*n keeps q = tid & 3 fixed per thread, so the eight (dy, dx, channel) triples are loop invariants.
-  const __half zero = __float2half_rn(0.0f);
-  const int q = threadIdx.x & 3;
-  int dy[8], dx[8], off[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int k = q * 8 + e;
-    const int tap = k / 3, c = k - tap * 3;
-    const int rr = tap / 3, ss = tap - rr * 3;
-    dy[e] = k < 27 ? rr - 1 : -1000;          // k >= 27: always out of range -> zero
-    dx[e] = ss - 1;
-    off[e] = ((rr - 1) * S + (ss - 1)) * 3 + c;
-  }
-  for (int i = threadIdx.x; i < kStemBlocks * kStemRows * 4; i += blockDim.x) {
-    const int row = (i >> 2) & (kStemRows - 1), blk = i >> 9;
+  // im2col rows: one thread per (block, row): the 27 taps are three runs of nine consecutive halves of the staged crop
+  // (k = (r*3+s)*3 + c), written as four 16-byte stores (64 contiguous bytes per thread, consecutive rows across the warp)
+  const unsigned short* cs = reinterpret_cast<const unsigned short*>(crop);
+  for (int i = threadIdx.x; i < kStemBlocks * kStemRows; i += blockDim.x) {
+    const int row = i & (kStemRows - 1), blk = i >> 7;
     const int by = blk / 5, bx = blk - by * 5;
     const int ti = row / 11, tj = row - ti * 11;
     const int cy = 10 * by - 1 + ti, cx = 10 * bx - 1 + tj;          // conv output position of this row
     const bool row_ok = row < 121 && cy >= 0 && cx >= 0;
-    const int base = (cy * S + cx) * 3;
-    __align__(16) __half v[8];
+    unsigned short v[32];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const bool ok = row_ok && (unsigned)(cy + dy[e]) < (unsigned)S && (unsigned)(cx + dx[e]) < (unsigned)S;
-      v[e] = ok ? crop[base + off[e]] : zero;
+    for (int e = 27; e < 32; ++e) v[e] = 0;
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) {
+      const int yy = cy + rr - 1;
+      const bool y_ok = row_ok && (unsigned)yy < (unsigned)S;
+#pragma unroll
+      for (int ss = 0; ss < 3; ++ss) {
+        const int xx = cx + ss - 1;
+        const bool ok = y_ok && (unsigned)xx < (unsigned)S;
+        const int base = ok ? (yy * S + xx) * 3 : 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[(rr * 3 + ss) * 3 + c] = ok ? cs[base + c] : (unsigned short)0;
+      }
     }
-    o[i] = *reinterpret_cast<const uint4*>(v);
+    uint4 w4[4];
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+      w4[qd].x = (uint32_t)v[8 * qd + 0] | ((uint32_t)v[8 * qd + 1] << 16);
+      w4[qd].y = (uint32_t)v[8 * qd + 2] | ((uint32_t)v[8 * qd + 3] << 16);
+      w4[qd].z = (uint32_t)v[8 * qd + 4] | ((uint32_t)v[8 * qd + 5] << 16);
+      w4[qd].w = (uint32_t)v[8 * qd + 6] | ((uint32_t)v[8 * qd + 7] << 16);
+    }
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) o[(long long)i * 4 + qd] = w4[qd];
   }
 }
 

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 from torch import nn
 
+from .. import ops
 from ..engine import YoloEngine
 from ..weights import load_yolov5_state_dict, synth_yolov5_state_dict
 
@@ -98,7 +99,8 @@ class YoloBackbone(BaseBackbone):
         self.class_names = list(class_names)
         self._device = device
         self._engines: Dict[Tuple[int, int, int], YoloEngine] = {}
-        self._pinned: Dict[Tuple[int, int, int], torch.Tensor] = {}
+        self._pinned: Dict[tuple, torch.Tensor] = {}
+        self._raw_dev: Dict[tuple, torch.Tensor] = {}
         # a parameter so that `.parameters()` / `.to()` behave like the reference module (detect.py:27-28)
         self._anchor = nn.Parameter(torch.zeros(1), requires_grad=False)
 
@@ -120,12 +122,31 @@ class YoloBackbone(BaseBackbone):
             shape1 = [max(shape1[0], h * g), max(shape1[1], w * g)]
         h1, w1 = (_make_divisible(v, 32) for v in shape1)
         eng = self._engine(len(imgs), h1, w1)
-        host = self._pinned[(len(imgs), h1, w1)]
-        hv = host.numpy()
-        for i, im in enumerate(imgs):
-            hv[i] = im if im.shape[:2] == (h1, w1) else _letterbox(im, (h1, w1))
         eng.set_scale(shape0)
-        eng.upload(host)
+        h0, w0 = shape0[0]
+        r = min(h1 / h0, w1 / w0)
+        if all(s == shape0[0] for s in shape0) and r == 0.5 and h0 % 2 == 0 and w0 % 2 == 0:
+            # exact 2x reduction (e.g. 1280x720 -> 640x360 inside 384x640): raw frames go up, the letterbox runs on the device
+            # (vcb_letterbox_half_u8: bit-identical to the cv2 path below for this ratio)
+            key = ("raw", len(imgs), h0, w0)
+            if key not in self._pinned:
+                self._pinned[key] = torch.empty(len(imgs), h0, w0, 3, dtype=torch.uint8).pin_memory()
+                self._raw_dev[key] = torch.empty(len(imgs), h0, w0, 3, dtype=torch.uint8, device=eng.frames.device)
+            host, raw = self._pinned[key], self._raw_dev[key]
+            hv = host.numpy()
+            for i, im in enumerate(imgs):
+                hv[i] = im
+            dh, dw = (h1 - h0 // 2) / 2, (w1 - w0 // 2) / 2
+            top, left = int(round(dh - 0.1)), int(round(dw - 0.1))
+            with torch.cuda.stream(eng.plan.stream):
+                raw.copy_(host, non_blocking=True)
+            ops.letterbox_half(raw, len(imgs), h0, w0, eng.frames, h1, w1, top, left, 114, stream=eng.plan.stream)
+        else:
+            host = self._pinned[(len(imgs), h1, w1)]
+            hv = host.numpy()
+            for i, im in enumerate(imgs):
+                hv[i] = im if im.shape[:2] == (h1, w1) else _letterbox(im, (h1, w1))
+            eng.upload(host)
         eng.forward()
         det, cnt = eng.download()
         if self.classes is not None:                            # optional class filter (yolo.py:64)
