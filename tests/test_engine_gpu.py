@@ -203,3 +203,40 @@ def test_reid_engine_matches_reference_golden(lib):
     eng_t.run(fr, np.array(rois, np.int32), seg_sizes=[8])
     got = eng_t.download(8)
     assert np.abs(got - z["feat_train"]).max() < 4e-3
+
+
+@pytest.mark.parametrize("bn_mode", ["train", "eval"])
+def test_video_tracker_batched_reid_equals_per_class_calls(lib, bn_mode):
+    """modules/track.py:30-70 mirror: ONE ReID pass per frame with one BatchNorm-statistics segment per class gives the rows of
+    the reference's per-class DeepSort.update calls (same embeddings, hence same track ids and integer boxes)."""
+    from vehicle_counting_b200.modules import VideoTracker
+    from vehicle_counting_b200.networks import DeepSort
+    cam = {"tracking_config": {"MAX_DIST": 0.3, "MIN_CONFIDENCE": 0.3, "NMS_MAX_OVERLAP": 0.5, "MAX_IOU_DISTANCE": 0.7, "MAX_AGE": 30,
+                               "N_INIT": 3, "NN_BUDGET": 50}}
+    nc = 3
+    vt = VideoTracker(nc, cam, {"num_frames": 8}, "synthetic", bn_mode=bn_mode)
+    ref = [DeepSort("synthetic", max_dist=0.3, min_confidence=0.3, nms_max_overlap=0.5, max_iou_distance=0.7, max_age=30, n_init=3,
+                    nn_budget=50, use_cuda=1, bn_mode=bn_mode) for _ in range(nc)]
+    rng = np.random.default_rng(17)
+    fh, fw = 360, 640
+    base = rng.uniform(20, 250, (9, 2)); size = rng.uniform(30, 90, (9, 2))
+    labels = np.array([0, 0, 0, 0, 2, 2, 2, 1, 0])
+    rows_seen = 0
+    for t in range(8):
+        frame, _ = _frame_and_boxes(100 + t, 1, fh, fw)
+        tl = base + 4.0 * t
+        boxes = np.concatenate([tl, size], 1)                                  # xywh (top-left), as ImageDetect returns them
+        scores = np.linspace(0.9, 0.4, 9)
+        got = vt.run(frame, boxes, labels, scores)
+        want = {"tracks": [], "boxes": [], "labels": []}
+        xyxy = boxes.copy(); xyxy[:, 2] += xyxy[:, 0]; xyxy[:, 3] += xyxy[:, 1]
+        for i in range(nc):
+            m = labels == i
+            if m.any():
+                for obj in ref[i].update(xyxy[m], scores[m], frame):
+                    want["tracks"].append(obj[4]); want["boxes"].append(obj[:4]); want["labels"].append(i)
+        assert [int(x) for x in got["tracks"]] == [int(x) for x in want["tracks"]], t
+        assert got["labels"] == want["labels"]
+        np.testing.assert_array_equal(np.array(got["boxes"]).reshape(-1, 4), np.array(want["boxes"]).reshape(-1, 4))
+        rows_seen += len(want["tracks"])
+    assert rows_seen > 0
