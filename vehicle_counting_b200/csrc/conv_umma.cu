@@ -634,7 +634,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       long long t_w = 0;
       const long long t_b = prof_clock(p.prof);
-      uint32_t it = 0;
+      uint32_t it = 0, ring_st = 0, ring_ph = 0;
       if (A_MODE == A_TMA && p.b_resident && (int)blockIdx.x < p.num_tiles) {
         // small layers: every packed weight chunk is loaded once per CTA and stays put
         const uint32_t bc = (uint32_t)(p.block_n * BK * 2);
@@ -657,8 +657,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t b_chunk = (uint32_t)(p.block_n * BK * 2);
         constexpr int G = kBlockK / BK;
         for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
-          const int st = it % p.num_stages;
-          const uint32_t ph = (it / p.num_stages) & 1u;
+          const int st = (int)ring_st;
+          const uint32_t ph = ring_ph;
+          if (++ring_st == (uint32_t)p.num_stages) { ring_st = 0; ring_ph ^= 1u; }      // no integer division in the issue loops
           const long long tw = prof_clock(p.prof);
           mbar_wait(empty_bar(st), ph ^ 1u, p.fault, FAULT_EMPTY_WAIT, st);
           t_w += prof_clock(p.prof) - tw;
@@ -695,7 +696,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr int G = kBlockK / BK;                                                // chunks per stage
       // descriptor high words are loop invariants; only the 14-bit start-address field changes
       const uint64_t desc_hi = umma_desc_kmajor(0, sbo, layout_type);
-      uint32_t it = 0, tile_iter = 0;
+      uint32_t it = 0, tile_iter = 0, ring_st = 0, ring_ph = 0;
       long long t_wf = 0, t_wt = 0;
       const long long t_b = prof_clock(p.prof);
       if (p.b_resident && (int)blockIdx.x < p.num_tiles) mbar_wait(bres_bar, 0u, p.fault, FAULT_FULL_WAIT, 300);
@@ -710,8 +711,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t ks = 0;                                  // K=16 steps issued for this tile
         const uint32_t chain_mask = (uint32_t)p.kchains - 1u;
         for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
-          const int st = it % p.num_stages;
-          const uint32_t ph = (it / p.num_stages) & 1u;
+          const int st = (int)ring_st;
+          const uint32_t ph = ring_ph;
+          if (++ring_st == (uint32_t)p.num_stages) { ring_st = 0; ring_ph ^= 1u; }      // no integer division in the issue loops
           const long long tw2 = prof_clock(p.prof);
           mbar_wait(full_bar(st), ph, p.fault, FAULT_FULL_WAIT, st);
           t_wf += prof_clock(p.prof) - tw2;
@@ -768,13 +770,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (!M256 && p.split_b && warp == kGatherWarp0 && lane == 0) {
       const uint32_t b_chunk = (uint32_t)(p.block_n * BK * 2);
       constexpr int G = kBlockK / BK;
-      uint32_t it = 0;
+      uint32_t ring_st = 0, ring_ph = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         int kidx = 0;
         for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
-          const int st = it % p.num_stages;
-          const uint32_t ph = (it / p.num_stages) & 1u;
+          const int st = (int)ring_st;
+          const uint32_t ph = ring_ph;
+          if (++ring_st == (uint32_t)p.num_stages) { ring_st = 0; ring_ph ^= 1u; }      // no integer division in the issue loops
           mbar_wait(empty_bar(st), ph ^ 1u, p.fault, FAULT_EMPTY_WAIT, 200 + st);
           const uint32_t b_dst = smem_base + (uint32_t)st * stage_bytes + kATileBytes;
           const int nch = (G == 1) ? 1 : min(G, p.total_chunks - kit * G);
@@ -787,7 +790,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ======================= gather producers (warps 10-13) =======================
     const int gtid = threadIdx.x - kGatherWarp0 * 32;
-    uint32_t it = 0;          // K-steps issued by this thread (same sequence in every gather thread)
+    uint32_t ring_st = 0, ring_ph = 0, it = 0;          // K-steps issued by this thread (same sequence in every gather thread)
     uint32_t arrived = 0;     // K-steps already signalled on their full barrier
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
@@ -812,8 +815,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       asm volatile("bar.sync 1, 128;" ::: "memory");
       int r = 0, s = 0, c = 0;
       for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
-        const int st = it % p.num_stages;
-        const uint32_t ph = (it / p.num_stages) & 1u;
+        const int st = (int)ring_st;
+        const uint32_t ph = ring_ph;
+        if (++ring_st == (uint32_t)p.num_stages) { ring_st = 0; ring_ph ^= 1u; }
         mbar_wait(empty_bar(st), ph ^ 1u, p.fault, FAULT_EMPTY_WAIT, 100 + st);
         const uint32_t a_dst = smem_base + (uint32_t)st * stage_bytes;
         if (A_MODE == A_GATHER) {
@@ -954,7 +958,7 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       constexpr uint32_t a_chunk = (uint32_t)(kBlockM * BK * 2);
       const uint32_t b_chunk = (uint32_t)((p.block_n >> 1) * BK * 2);
       constexpr int G = kBlockK / BK;
-      uint32_t it = 0;
+      uint32_t ring_st = 0, ring_ph = 0, it = 0;
       for (int tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters) {
         const int pm = tile / p.n_tiles, n_tile = tile - pm * p.n_tiles;
         const int m0 = (2 * pm + rank) * kBlockM;      // may lie past M for the last pair: the TMA zero-fills
@@ -964,8 +968,9 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int cw = q0 * p.stride - p.pad, ch = p0 * p.stride - p.pad;
         int r = 0, s = 0, c = 0, kidx = 0;
         for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
-          const int st = it % p.num_stages;
-          const uint32_t ph = (it / p.num_stages) & 1u;
+          const int st = (int)ring_st;
+          const uint32_t ph = ring_ph;
+          if (++ring_st == (uint32_t)p.num_stages) { ring_st = 0; ring_ph ^= 1u; }      // no integer division in the issue loops
           mbar_wait(empty_bar(st), ph ^ 1u, p.fault, FAULT_EMPTY_WAIT, st);
           const uint32_t a_dst = smem_base + (uint32_t)st * stage_bytes;
           const uint32_t b_dst = a_dst + kATileBytes;
@@ -993,7 +998,7 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       constexpr int ksteps = BK / 16;
       constexpr int G = kBlockK / BK;
       const uint64_t desc_hi = umma_desc_kmajor(0, sbo, layout_type);
-      uint32_t it = 0, tile_iter = 0;
+      uint32_t ring_st = 0, ring_ph = 0, it = 0, tile_iter = 0;
       for (int tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
         const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
         const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
@@ -1001,8 +1006,9 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.block_n;
         for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
-          const int st = it % p.num_stages;
-          const uint32_t ph = (it / p.num_stages) & 1u;
+          const int st = (int)ring_st;
+          const uint32_t ph = ring_ph;
+          if (++ring_st == (uint32_t)p.num_stages) { ring_st = 0; ring_ph ^= 1u; }      // no integer division in the issue loops
           mbar_wait(full_bar(st), ph, p.fault, FAULT_FULL_WAIT, st);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_base + (uint32_t)st * stage_bytes;
@@ -1061,7 +1067,7 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 // tcgen05.mma on one accumulator issue ~190 clk apart) that share every weight tile.
 // Warps: 0-7 epilogue (0-3 chain 0, 4-7 chain 1), 8 patch producer, 9 MMA issuer (+ TMEM), 10 weight producer.  One CTA per SM.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kThreadsPatch = 352;
+constexpr int kThreadsPatch = 448;      // warps 0-7 epilogue, 8 patch producer, 10 weight producer, 9/11/12/13 MMA issuers
 constexpr int kPatchMaxA = 4, kPatchMaxB = 8;
 
 __global__ void __launch_bounds__(kThreadsPatch, 1)
@@ -1093,10 +1099,16 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < p.cout_pad; i += blockDim.x) bias_gen[i] = __ldg(p.bias + i);
   griddep_launch_dependents();
+  const long long t_cta0 = prof_clock(p.prof);
+  // One thread issues tcgen05.mma at most every ~107 clk whatever N is; the limit is per issuing thread, not per CTA or per
+  // accumulator (tools/umma_rate_probe.cu, profiles/r01_umma_rate_probe.txt: 2 issuers 53 clk, 3-4 issuers ~40-48 clk per MMA per
+  // SM).  So each (row chain, K chain) accumulator gets its OWN issuing warp: 2 issuers, 4 for N <= 64.  Every issuer waits on the
+  // same full barriers and signals the same empty barriers (arrival count = number of issuers).
+  const uint32_t num_issuers = 2u * (uint32_t)p.kchains;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kPatchMaxA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
-    for (int s = 0; s < kPatchMaxB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8u * a, 1); mbar_init(tempty0 + 8u * a, kNumEpilogueThreads); }
+    for (int s = 0; s < kPatchMaxA; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), num_issuers); }
+    for (int s = 0; s < kPatchMaxB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), num_issuers); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8u * a, num_issuers); mbar_init(tempty0 + 8u * a, kNumEpilogueThreads); }
     mbar_init(bres_bar, 1);
     mbar_init(res_bar0, 1);
     mbar_init(res_bar0 + 8u, 1);
@@ -1124,17 +1136,19 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   if (warp == kProducerWarp) {
     if (lane == 0) {         // ---- patch producer: one 4-D box per (tile, channel chunk)
-      uint32_t ita = 0;
+      uint32_t sa = 0, pha = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles;
         const int ni = mt / per_img, rem = mt - ni * per_img;
         const int yt = rem / p.patch_xsegs, xs = rem - yt * p.patch_xsegs;
-        for (int c = 0; c < chunks; ++c, ++ita) {
-          const int sa = ita % p.a_stages;
-          mbar_wait(aempty(sa), ((ita / p.a_stages) & 1u) ^ 1u, p.fault, FAULT_EMPTY_WAIT, 600 + sa);
+        for (int c = 0; c < chunks; ++c) {
+          const long long tw = prof_clock(p.prof);
+          mbar_wait(aempty(sa), pha ^ 1u, p.fault, FAULT_EMPTY_WAIT, 600 + (int)sa);
+          prof_add(p.prof, PROF_PROD_WAIT_EMPTY, prof_clock(p.prof) - tw);
           mbar_arrive_expect_tx(afull(sa), (uint32_t)p.patch_box_bytes);
-          tma_load_4d(&tmap_a, afull(sa), a_region + (uint32_t)(sa * p.patch_stage_bytes), c * kBlockK, xs * p.patch_Xs - 1,
+          tma_load_4d(&tmap_a, afull(sa), a_region + sa * (uint32_t)p.patch_stage_bytes, c * kBlockK, xs * p.patch_Xs - 1,
                       yt * p.patch_R - 1, ni);
+          if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; }
         }
       }
     }
@@ -1146,65 +1160,78 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int kc = 0; kc < p.total_chunks; ++kc) tma_load_2d(&tmap_b, bres_bar, b_region + (uint32_t)kc * bc, kc * kBlockK, 0);
         }
       } else {
-        uint32_t itb = 0;
+        uint32_t sb = 0, phb = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
           const int nt = tile % p.n_tiles;
           for (int c = 0; c < chunks; ++c)
-            for (int t = 0; t < 9; ++t, ++itb) {
-              const int sb = itb % p.b_stages;
-              mbar_wait(bempty(sb), ((itb / p.b_stages) & 1u) ^ 1u, p.fault, FAULT_EMPTY_WAIT, 620 + sb);
+            for (int t = 0; t < 9; ++t) {
+              mbar_wait(bempty(sb), phb ^ 1u, p.fault, FAULT_EMPTY_WAIT, 620 + (int)sb);
               mbar_arrive_expect_tx(bfull(sb), b_tile_bytes);
-              tma_load_2d(&tmap_b, bfull(sb), b_region + (uint32_t)sb * b_tile_bytes, (t * chunks + c) * kBlockK, nt * p.block_n);
+              tma_load_2d(&tmap_b, bfull(sb), b_region + sb * b_tile_bytes, (t * chunks + c) * kBlockK, nt * p.block_n);
+              if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= 1u; }
             }
         }
       }
     }
-  } else if (warp == kMmaWarp) {
-    if (lane == 0) {         // ---- MMA issuer
+  } else if (warp == kMmaWarp || warp >= 11) {
+    const uint32_t issuer = warp == kMmaWarp ? 0u : (uint32_t)(warp - 10);       // warps 9, 11, 12, 13 -> issuers 0..3
+    if (lane == 0 && issuer < num_issuers) {         // ---- MMA issuer of accumulator (K chain kq, row chain h)
+      const uint32_t h = issuer & 1u, kq = issuer >> 1;
       const uint32_t idesc = umma_idesc_f16((uint32_t)p.block_n);
       const uint64_t desc_hi = umma_desc_kmajor(0, 1024u, 2u);      // SWIZZLE_128B, 8-row groups 1024 B apart, base_offset 0
-      uint32_t ita = 0, itb = 0, tile_iter = 0;
+      // The issue loop is ONE thread: every integer instruction in it delays the next tcgen05.mma (the first version spent ~8k
+      // cycles per tile on ring-index divisions and per-tap address arithmetic).  Everything loop-invariant is hoisted: the nine
+      // tap offsets in descriptor units, ring positions as counters, descriptors advanced by additions.
+      uint32_t tap_off[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_off[t] = ((uint32_t)((t / 3) * p.patch_Lp + (t % 3)) * 128u) >> 4;
+      const uint32_t bc16 = bc >> 4;
+      const uint32_t kstep0 = 2u * kq, kstep_inc = 2u * (uint32_t)p.kchains;      // descriptor offset of this issuer's first K step / stride
+      const uint32_t ksteps_mine = 4u / (uint32_t)p.kchains;
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tile_iter = 0;
       if (p.b_resident && (int)blockIdx.x < p.num_tiles) mbar_wait(bres_bar, 0u, p.fault, FAULT_FULL_WAIT, 640);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
         const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
         const uint32_t acc_ph = (p.acc_stages == 2) ? ((tile_iter >> 1) & 1u) : (tile_iter & 1u);
+        const long long tw1 = prof_clock(issuer == 0 ? p.prof : nullptr);
         mbar_wait(tempty0 + 8u * acc, acc_ph ^ 1u, p.fault, FAULT_TMEM_EMPTY_WAIT, (int)acc);
+        if (issuer == 0) prof_add(p.prof, PROF_MMA_WAIT_TMEM, prof_clock(p.prof) - tw1);
         tcgen05_fence_after();
-        // accumulators of a stage: [K chain kc][row chain: lattice rows 0-127 | 128-255][block_n]
-        const uint32_t d_tmem = tmem_base + acc * 2u * (uint32_t)(p.block_n * p.kchains);
-        uint32_t ks = 0;
-        const uint32_t kmask = (uint32_t)p.kchains - 1u;
-        for (int c = 0; c < chunks; ++c, ++ita) {
-          const int sa = ita % p.a_stages;
-          mbar_wait(afull(sa), (ita / p.a_stages) & 1u, p.fault, FAULT_FULL_WAIT, 650 + sa);
+        // accumulators of a stage: [K chain][row chain: lattice rows 0-127 | 128-255][block_n]
+        const uint32_t d_tmem = tmem_base + acc * 2u * (uint32_t)(p.block_n * p.kchains) + (kq * 2u + h) * (uint32_t)p.block_n;
+        uint32_t accumulate = 0u;
+        uint64_t bres_desc = desc_hi | (uint64_t)((b_region & 0x3FFFF) >> 4);      // resident weights: (tap, chunk) tiles, chunk c at +c*bc16
+        for (int c = 0; c < chunks; ++c) {
+          const long long tw2 = prof_clock(issuer == 0 ? p.prof : nullptr);
+          mbar_wait(afull(sa), pha, p.fault, FAULT_FULL_WAIT, 650 + (int)sa);
+          if (issuer == 0) prof_add(p.prof, PROF_MMA_WAIT_FULL, prof_clock(p.prof) - tw2);
           tcgen05_fence_after();
-          const uint32_t a_base = a_region + (uint32_t)(sa * p.patch_stage_bytes);
-#pragma unroll 1
-          for (int t = 0; t < 9; ++t) {
-            const int r = t / 3, sx = t - r * 3;
-            const uint32_t a_addr = a_base + (uint32_t)(r * p.patch_Lp + sx) * 128u;
-            uint32_t b_addr;
-            int sb = 0;
-            if (p.b_resident) {
-              b_addr = b_region + (uint32_t)(t * chunks + c) * bc;
-            } else {
-              sb = itb % p.b_stages;
-              mbar_wait(bfull(sb), (itb / p.b_stages) & 1u, p.fault, FAULT_FULL_WAIT, 660 + sb);
-              tcgen05_fence_after();
-              b_addr = b_region + (uint32_t)sb * b_tile_bytes;
-            }
-            const uint64_t a_desc = desc_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
-            const uint64_t b_desc = desc_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
+          // row chain 1 = lattice rows 128..255 of the patch
+          const uint64_t a_desc0 = (desc_hi | (uint64_t)(((a_region + sa * (uint32_t)p.patch_stage_bytes + h * 16384u) & 0x3FFFF) >> 4)) + kstep0;
+          uint64_t b_desc_res = bres_desc + (uint64_t)((uint32_t)c * bc16) + kstep0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k, ++ks) {      // 2 row chains x kchains K chains: independent accumulators sharing every weight tile
-              const uint32_t d = d_tmem + (ks & kmask) * 2u * (uint32_t)p.block_n;
-              const uint32_t accumulate = ks > kmask ? 1u : 0u;
-              umma_f16(d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
-              umma_f16(d + (uint32_t)p.block_n, a_desc + (uint64_t)(1024 + 2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
+          for (int t = 0; t < 9; ++t) {
+            uint64_t b_desc;
+            if (p.b_resident) {
+              b_desc = b_desc_res;
+              b_desc_res += (uint64_t)((uint32_t)chunks * bc16);
+            } else {
+              mbar_wait(bfull(sb), phb, p.fault, FAULT_FULL_WAIT, 660 + (int)sb);
+              tcgen05_fence_after();
+              b_desc = (desc_hi | (uint64_t)(((b_region + sb * b_tile_bytes) & 0x3FFFF) >> 4)) + kstep0;
             }
-            if (!p.b_resident) { umma_commit(bempty(sb)); ++itb; }
+            const uint64_t a_desc = a_desc0 + tap_off[t];
+            for (uint32_t k = 0; k < ksteps_mine; ++k) {      // this issuer's K steps of the 64-wide chunk
+              umma_f16(d_tmem, a_desc + (uint64_t)(k * kstep_inc), b_desc + (uint64_t)(k * kstep_inc), idesc, accumulate);
+              accumulate = 1u;
+            }
+            if (!p.b_resident) {
+              umma_commit(bempty(sb));
+              if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= 1u; }
+            }
           }
           umma_commit(aempty(sa));
+          if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; }
         }
         umma_commit(tfull0 + 8u * acc);
       }
@@ -1228,6 +1255,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tcgen05_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (threadIdx.x == 0 && p.prof) { prof_add(p.prof, PROF_CTA_TOTAL, clock64() - t_cta0); prof_add(p.prof, PROF_CTAS, 1); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1354,7 +1382,24 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
   // ---- patch mode: 3x3/s1/p1 with 64-channel chunks; reserved[3] == 5 forces it, == 1 (or any other forced mode) forbids it
   {
     const bool can = g.a_mode == A_TMA && !g.two_cta && g.epi_kind != 0 && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.pad == 1 && g.bk == 64;
-    const bool want = can && (d.reserved[3] == 5);
+    // automatic for narrow layers (N <= 64) with at least two waves of tiles: measured 4-14 % faster than the 128-row im2col mode
+    // (ReID layer 1, YOLOv5m 48->48, YOLOv5s 64->64; profiles/r01_layer_modes.md); wider layers lose (single CTA per SM)
+    bool want = can && (d.reserved[3] == 5);
+    if (can && d.reserved[3] == 0 && g.block_n <= 64 && g.n_tiles == 1) {
+      int best_tiles = 0;
+      double best_u = 0.0;
+      for (int nseg = 1; nseg <= 16; ++nseg) {
+        const int xs = (d.w + nseg - 1) / nseg;
+        if (xs + 2 > 128) continue;
+        int r = 256 / (xs + 2);
+        if (r > d.h) r = d.h;
+        if (r < 1) continue;
+        const int yt = (d.h + r - 1) / r;
+        const double util = (double)d.h * d.w / ((double)yt * nseg * 256.0);
+        if (util > best_u + 1e-9) { best_u = util; best_tiles = yt * nseg; }
+      }
+      if (best_u >= 0.75 && (long long)best_tiles * d.n >= 2 * 148) want = true;
+    }
     if (d.reserved[3] == 5 && !can) return set_error(VCB_ERR_INVALID, "conv: patch mode needs a 3x3/s1/p1 layer on the TMA path with 64-channel chunks");
     if (want) {
       // tile shape: R rows x Xs columns with R * (Xs + 2) <= 128, maximising useful rows per 128-row tile over the image
@@ -1376,8 +1421,8 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
       for (int res = 1; res >= 0 && !chosen; --res) {
         if (res && !(g.n_tiles == 1 && b_total <= 112 * 1024)) continue;
         const size_t b_res = res ? (b_total + 1023) / 1024 * 1024 : 0;
-        for (int bufs = 2; bufs >= 1 && !chosen; --bufs)
-          for (int as = 3; as >= 2 && !chosen; --as) {
+        for (int as = 3; as >= 2 && !chosen; --as)          // a third patch stage before a second staging buffer
+          for (int bufs = 2; bufs >= 1 && !chosen; --bufs) {
             const size_t fixed = tailp + b_res + (size_t)bufs * 2 * kStageOutBytes + (size_t)as * g.patch_stage_bytes;
             if (fixed > budget) continue;
             int bs = res ? 0 : (int)((budget - fixed) / ((size_t)g.block_n * 128));
