@@ -708,43 +708,50 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         t_wt += prof_clock(p.prof) - tw1;
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.block_n * (M256 ? 2u : (uint32_t)p.kchains);
-        uint32_t ks = 0;                                  // K=16 steps issued for this tile
+        uint32_t ks = 0;                                  // K=16 steps issued for this tile (K chains, opt-in)
         const uint32_t chain_mask = (uint32_t)p.kchains - 1u;
+        uint32_t accumulate = 0u;
+        uint64_t bres_desc = desc_hi | (uint64_t)((b_res & 0x3FFFF) >> 4);      // resident weights: chunk kc at + kc * b_chunk
         for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
+          // this loop is ONE thread: every integer instruction here delays the next tcgen05.mma (tools/umma_rate_probe.cu), so the
+          // ring position is a counter and the descriptors advance by additions
           const int st = (int)ring_st;
-          const uint32_t ph = ring_ph;
-          if (++ring_st == (uint32_t)p.num_stages) { ring_st = 0; ring_ph ^= 1u; }      // no integer division in the issue loops
           const long long tw2 = prof_clock(p.prof);
-          mbar_wait(full_bar(st), ph, p.fault, FAULT_FULL_WAIT, st);
+          mbar_wait(full_bar(st), ring_ph, p.fault, FAULT_FULL_WAIT, st);
           t_wf += prof_clock(p.prof) - tw2;
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_base + (uint32_t)st * stage_bytes;
+          const uint32_t a_addr = smem_base + ring_st * stage_bytes;
+          const uint64_t a_desc0 = desc_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+          const uint64_t b_desc0 = p.b_resident ? bres_desc : (a_desc0 + (uint64_t)(kATile >> 4));
           const int nch = (G == 1) ? 1 : min(G, p.total_chunks - kit * G);
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             if (g < nch) {
-              const uint64_t a_desc = desc_hi | (uint64_t)(((a_addr + (uint32_t)g * a_chunk) & 0x3FFFF) >> 4);
-              const uint32_t b_addr = p.b_resident ? b_res + (uint32_t)(kit * G + g) * b_chunk : a_addr + kATile + (uint32_t)g * b_chunk;
-              const uint64_t b_desc = desc_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
+              const uint64_t a_desc = a_desc0 + (uint64_t)(((uint32_t)g * a_chunk) >> 4);
+              const uint64_t b_desc = b_desc0 + (uint64_t)(((uint32_t)g * b_chunk) >> 4);
 #pragma unroll
               for (int k = 0; k < ksteps; ++k) {
                 // +32 bytes per UMMA_K step inside the swizzle row: +2 in the (addr >> 4) field
                 if (M256 && p.dbg_swap) {   // experiment: D^T[128 x 256 pixels] = W[128 x 16] * X[256 x 16]^T, one instruction per K step
-                  umma_f16(tmem_base + acc * 256u, b_desc + (uint64_t)(2 * k), a_desc + (uint64_t)(2 * k), umma_idesc_f16(256u), (kit | g | k) != 0 ? 1u : 0u);
+                  umma_f16(tmem_base + acc * 256u, b_desc + (uint64_t)(2 * k), a_desc + (uint64_t)(2 * k), umma_idesc_f16(256u), accumulate);
                 } else if (M256) {    // two row chains: rows 0..127 and 128..255 of the same chunk against the same weight tile
-                  umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kit | g | k) != 0 ? 1u : 0u);
-                  umma_f16(d_tmem + (uint32_t)p.block_n, a_desc + (uint64_t)((a_chain >> 4) + 2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                           (kit | g | k) != 0 ? 1u : 0u);
-                } else {       // K chains: step ks accumulates into accumulator ks % kchains
+                  umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
+                  umma_f16(d_tmem + (uint32_t)p.block_n, a_desc + (uint64_t)((a_chain >> 4) + 2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
+                } else if (chain_mask != 0u) {       // K chains (opt-in): step ks accumulates into accumulator ks % kchains
                   umma_f16(d_tmem + (ks & chain_mask) * (uint32_t)p.block_n, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                            ks > chain_mask ? 1u : 0u);
                   ++ks;
+                } else {
+                  umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accumulate);
                 }
+                accumulate = 1u;
               }
             }
           }
+          if (p.b_resident) bres_desc += (uint64_t)(((uint32_t)nch * b_chunk) >> 4);
           umma_commit(empty_bar(st));
           if (kit == p.num_k_iters - 1) umma_commit(tmem_full_bar(acc));
+          if (++ring_st == (uint32_t)p.num_stages) { ring_st = 0; ring_ph ^= 1u; }
         }
       }
       if (p.prof) { prof_add(p.prof, PROF_MMA_WAIT_FULL, t_wf); prof_add(p.prof, PROF_MMA_WAIT_TMEM, t_wt); prof_add(p.prof, PROF_MMA_TOTAL, clock64() - t_b); }
