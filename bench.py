@@ -162,9 +162,6 @@ def run_ours(a) -> dict:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        # rank 0's stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -343,7 +340,17 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: the hot path has no CPU fallback")
-    out = run_ours(a)
+    # stdout carries exactly ONE JSON line: anything libraries print while the run is in flight (e.g. NCCL's version banner,
+    # which goes to fd 1) is diverted to stderr, and the real stdout is restored for the result line
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        out = run_ours(a)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
     if rank == 0 and out is not None:
         if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not a.no_cpu_baseline:
             frames = 2
