@@ -78,3 +78,27 @@ def test_no_product_module_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_stage_wrapper_mirrors_keep_the_reference_signatures():
+    """modules/detect.py:8-60 and modules/track.py:8-70: same constructor / run parameters as the reference classes (compared with the
+    reference sources when they are mounted, with the recorded parameter lists otherwise)."""
+    import inspect
+    from vehicle_counting_b200.modules import ImageDetect, VideoTracker
+    want = {"ImageDetect.__init__": ["self", "args", "config"], "ImageDetect.run": ["self", "batch"],
+            "VideoTracker.__init__": ["self", "num_classes", "cam_config", "video_info", "deepsort_chepoint"],
+            "VideoTracker.build_tracker": ["self", "checkpoint", "cam_cfg"],
+            "VideoTracker.run": ["self", "image", "boxes", "labels", "scores"]}
+    ref_root = "/root/reference/modules"
+    if os.path.isdir(ref_root):           # build container: read the parameter lists from the reference sources themselves
+        import ast
+        for fn, cls in (("detect.py", "ImageDetect"), ("track.py", "VideoTracker")):
+            tree = ast.parse(open(os.path.join(ref_root, fn)).read())
+            node = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls)
+            for f in node.body:
+                if isinstance(f, ast.FunctionDef) and f"{cls}.{f.name}" in want:
+                    assert [a.arg for a in f.args.args] == want[f"{cls}.{f.name}"], (cls, f.name)
+    for key, params in want.items():
+        cls, name = key.split(".")
+        got = list(inspect.signature(getattr({"ImageDetect": ImageDetect, "VideoTracker": VideoTracker}[cls], name)).parameters)
+        assert got[:len(params)] == params, (key, got)          # extra keyword-only knobs (bn_mode) may follow

@@ -20,9 +20,19 @@
 // CTA = warps 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2), warp 8 TMA producer,
 // warp 9 MMA issuer (+ TMEM allocator), warps 10-13 gather producers (A_GATHER / A_C4 only).
 // Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...; the fp32 accumulator is double-buffered
-// in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.  The epilogue converts 128 x 64
+// in TMEM when it fits so the epilogue of tile i overlaps the main loop of tile i+1.  The epilogue converts 128 x 64
 // (fp16) / 128 x 32 (fp32) sub-tiles into a 128-byte-swizzled staging buffer and hands them to the TMA
-// store unit (coalesced, asynchronous, clipped to the tensor bounds), two buffers in flight.
+// store unit (coalesced, asynchronous, clipped to the tensor bounds); residual tiles arrive the same way.
+//
+// Kernels in this file (host side: conv_geometry picks one per layer; VcbConvDesc.reserved[3] forces one):
+//   conv_umma_kernel<A_MODE, BK, false>  128-pixel tiles, two persistent CTAs per SM (default)
+//   conv_umma_2cta_kernel<BK>            cta_group::2 CTA pairs (M = 256 over two SMs, each CTA loads half of every weight tile),
+//                                        two co-resident clusters per SM pair: 3x3 layers with N >= 128
+//   conv_patch_kernel                    3x3/s1/p1, N <= 64: one input patch per 64-channel chunk in shared memory, the nine taps
+//                                        through shifted UMMA descriptors, one MMA-issuing warp per accumulator
+//   conv_umma_kernel<A_TMA, BK, true>    256-pixel tiles in two accumulators (opt-in experiment)
+// Epilogues: conv_epilogue_fast<ACT, RES, F32OUT, M256, TWO_CTA, PATCH> (specialised, all TMA modes) and conv_epilogue
+// (generic, runtime flags: gather / debug modes).  Measured facts that shaped the design are in DESIGN.md section 3.
 #include "vcb_internal.h"
 #include "vcb_ptx.cuh"
 
