@@ -122,6 +122,37 @@ def kf_update(mean: np.ndarray, cov: np.ndarray, z: np.ndarray) -> Tuple[np.ndar
     return new_mean, new_cov
 
 
+def kf_update_batch(means: np.ndarray, covs: np.ndarray, zs: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """kalman_filter.py:154-186 for M matched tracks at once: means [M,8], covs [M,8,8], measurements zs [M,4].  The 4x4
+    innovation covariance is factored by batched LAPACK potrf (as cho_factor does per track) and the two triangular solves of
+    cho_solve are written out over the four rows; the matrix products keep the reference's association."""
+    h = means[:, 3]
+    pm = means[:, :4]
+    pc = covs[:, :4, :4].copy()
+    r = np.square(STD_POS * h)
+    pc[:, 0, 0] += r
+    pc[:, 1, 1] += r
+    pc[:, 2, 2] += np.square(1e-1)
+    pc[:, 3, 3] += r
+    L = np.linalg.cholesky(pc)                                   # [M,4,4] lower
+    B = covs[:, :, :4].transpose(0, 2, 1)                        # (P H^T)^T  [M,4,8]
+    # forward: L Y = B
+    y0 = B[:, 0] / L[:, 0, 0, None]
+    y1 = (B[:, 1] - L[:, 1, 0, None] * y0) / L[:, 1, 1, None]
+    y2 = (B[:, 2] - L[:, 2, 0, None] * y0 - L[:, 2, 1, None] * y1) / L[:, 2, 2, None]
+    y3 = (B[:, 3] - L[:, 3, 0, None] * y0 - L[:, 3, 1, None] * y1 - L[:, 3, 2, None] * y2) / L[:, 3, 3, None]
+    # backward: L^T X = Y
+    x3 = y3 / L[:, 3, 3, None]
+    x2 = (y2 - L[:, 3, 2, None] * x3) / L[:, 2, 2, None]
+    x1 = (y1 - L[:, 2, 1, None] * x2 - L[:, 3, 1, None] * x3) / L[:, 1, 1, None]
+    x0 = (y0 - L[:, 1, 0, None] * x1 - L[:, 2, 0, None] * x2 - L[:, 3, 0, None] * x3) / L[:, 0, 0, None]
+    gain = np.stack([x0, x1, x2, x3], axis=2)                    # [M,8,4] = P H^T S^-1
+    gt = gain.transpose(0, 2, 1)                                 # [M,4,8]
+    new_means = means + np.matmul((zs - pm)[:, None, :], gt)[:, 0, :]
+    new_covs = covs - np.matmul(gain, np.matmul(pc, gt))
+    return new_means, new_covs
+
+
 def kf_gating_distance(mean: np.ndarray, cov: np.ndarray, measurements: np.ndarray) -> np.ndarray:
     pm, pc = kf_project(mean, cov)
     L = np.linalg.cholesky(pc)
@@ -129,14 +160,65 @@ def kf_gating_distance(mean: np.ndarray, cov: np.ndarray, measurements: np.ndarr
     return np.sum(z * z, axis=0)
 
 
+def kf_gating_distance_batch(means: np.ndarray, covs: np.ndarray, measurements: np.ndarray) -> np.ndarray:
+    """Squared Mahalanobis distance of every measurement [D,4] to every track's projected state (kalman_filter.py:188-229) in
+    one pass: means [T,8], covs [T,8,8] -> [T,D].  H = [I4 | 0], so H P H^T is the top-left 4x4 block exactly; Cholesky per
+    track (batched LAPACK potrf, as the reference's np.linalg.cholesky) and the triangular solve written out as forward
+    substitution over the four rows (the reference calls scipy.linalg.solve_triangular once per track: 0.6 ms each here)."""
+    h = means[:, 3]
+    pc = covs[:, :4, :4].copy()
+    r = np.square(STD_POS * h)
+    pc[:, 0, 0] += r
+    pc[:, 1, 1] += r
+    pc[:, 2, 2] += np.square(1e-1)
+    pc[:, 3, 3] += r
+    L = np.linalg.cholesky(pc)                                   # [T,4,4] lower
+    d = measurements[None, :, :] - means[:, None, :4]            # [T,D,4]
+    z0 = d[:, :, 0] / L[:, 0, 0, None]
+    z1 = (d[:, :, 1] - L[:, 1, 0, None] * z0) / L[:, 1, 1, None]
+    z2 = (d[:, :, 2] - L[:, 2, 0, None] * z0 - L[:, 2, 1, None] * z1) / L[:, 2, 2, None]
+    z3 = (d[:, :, 3] - L[:, 3, 0, None] * z0 - L[:, 3, 1, None] * z1 - L[:, 3, 2, None] * z2) / L[:, 3, 3, None]
+    return ((z0 * z0 + z1 * z1) + z2 * z2) + z3 * z3
+
+
 # ---------------------------------------------------------------------------------------------
 # appearance gallery: per identity, the last `budget` embeddings
 # ---------------------------------------------------------------------------------------------
 class Gallery:
+    """nn_matching.py:99-177.  `samples` keeps the raw embeddings as the reference does; next to them every identity has its
+    L2-normalised rows in ONE contiguous array in chronological order (a 2x budget buffer, compacted once per `budget` inserts),
+    so that `distance` neither re-normalises nor re-stacks up to budget x 512 floats per identity and call."""
+
     def __init__(self, matching_threshold: float, budget: Optional[int]):
         self.matching_threshold = matching_threshold
         self.budget = budget
         self.samples = {}                       # track_id -> list of float32[512]
+        self._norm = {}                         # track_id -> [buffer [cap, dim], begin, end]
+
+    @staticmethod
+    def _normalise_rows(a: np.ndarray) -> np.ndarray:
+        return a / np.linalg.norm(a, axis=1, keepdims=True)       # the reference's expression (row-wise, independent of the other rows)
+
+    def _push(self, t, f: np.ndarray) -> None:
+        ent = self._norm.get(t)
+        row = self._normalise_rows(np.asarray(f)[None, :])[0]
+        if ent is None:
+            cap = 2 * self.budget if self.budget is not None else 64
+            ent = self._norm[t] = [np.empty((cap, row.shape[0]), row.dtype), 0, 0]
+        buf, b, e = ent
+        if e == buf.shape[0]:
+            if self.budget is not None:                             # compact: the live rows move to the front
+                n = e - b
+                buf[:n] = buf[b:e].copy()
+                b, e = 0, n
+            else:                                                   # unbounded gallery: grow
+                buf = np.concatenate([buf, np.empty_like(buf)], 0)
+                ent[0] = buf
+        buf[e] = row
+        e += 1
+        if self.budget is not None and e - b > self.budget:
+            b = e - self.budget
+        ent[1], ent[2] = b, e
 
     def partial_fit(self, features, targets, active_targets) -> None:
         for f, t in zip(features, targets):
@@ -144,19 +226,19 @@ class Gallery:
             lst.append(f)
             if self.budget is not None and len(lst) > self.budget:
                 del lst[:len(lst) - self.budget]
+            self._push(t, f)
         self.samples = {k: self.samples[k] for k in active_targets}
+        self._norm = {k: self._norm[k] for k in active_targets}
 
     def distance(self, features: np.ndarray, targets: Sequence[int]) -> np.ndarray:
         """min over the gallery of (1 - cosine similarity); both sides re-normalised (nn_matching.py:33-52)."""
         cost = np.zeros((len(targets), len(features)))
         if len(features) == 0:
             return cost
-        b = np.asarray(features)
-        b = b / np.linalg.norm(b, axis=1, keepdims=True)
+        bt = self._normalise_rows(np.asarray(features)).T
         for i, t in enumerate(targets):
-            a = np.asarray(self.samples[t])
-            a = a / np.linalg.norm(a, axis=1, keepdims=True)
-            cost[i] = (1.0 - a @ b.T).min(axis=0)
+            buf, b, e = self._norm[t]
+            cost[i] = (1.0 - buf[b:e] @ bt).min(axis=0)
         return cost
 
 
@@ -217,9 +299,9 @@ class Tracker:
         feats = np.array([dets[i].feature for i in det_idx])
         cost = self.metric.distance(feats, [self.tracks[i].track_id for i in track_idx])
         meas = np.asarray([dets[i].to_xyah() for i in det_idx])
-        for r, ti in enumerate(track_idx):
-            tr = self.tracks[ti]
-            cost[r, kf_gating_distance(tr.mean, tr.covariance, meas) > CHI2INV95_4DOF] = INFTY_COST
+        means = np.stack([self.tracks[ti].mean for ti in track_idx])
+        covs = np.stack([self.tracks[ti].covariance for ti in track_idx])
+        cost[kf_gating_distance_batch(means, covs, meas) > CHI2INV95_4DOF] = INFTY_COST
         return cost
 
     def _iou_cost(self, dets: List[Detection], track_idx: List[int], det_idx: List[int]) -> np.ndarray:
@@ -259,9 +341,14 @@ class Tracker:
 
     def update(self, dets: List[Detection]) -> None:
         matches, unmatched_t, unmatched_d = self._match(dets)
-        for ti, di in matches:
+        if matches:
+            m_means = np.stack([self.tracks[ti].mean for ti, _ in matches])
+            m_covs = np.stack([self.tracks[ti].covariance for ti, _ in matches])
+            m_z = np.stack([dets[di].to_xyah() for _, di in matches])
+            m_means, m_covs = kf_update_batch(m_means, m_covs, m_z)
+        for k, (ti, di) in enumerate(matches):
             tr, d = self.tracks[ti], dets[di]
-            tr.mean, tr.covariance = kf_update(tr.mean, tr.covariance, d.to_xyah())
+            tr.mean, tr.covariance = m_means[k], m_covs[k]
             tr.features.append(d.feature)
             tr.confidence_scores.append(d.confidence)
             tr.hits += 1
