@@ -126,3 +126,50 @@ def test_host_nms_matches_reference():
         boxes = np.concatenate([tl, wh], 1); scores = rng.uniform(0, 1, n)
         for thr in (0.3, 0.5, 1.0):
             assert host_nms(boxes, thr, scores) == [int(i) for i in ref_nms(boxes, thr, scores)]
+
+
+def test_batched_kalman_and_gating_equal_the_per_track_formulas():
+    """kf_update_batch / kf_gating_distance_batch against the per-track restatements of kalman_filter.py:154-229 (scipy cho_solve /
+    solve_triangular): same numbers to the last few bits on random positive-definite states."""
+    from vehicle_counting_b200.networks.deepsort import sort as S
+    rng = np.random.default_rng(5)
+    T, D = 23, 17
+    means = np.concatenate([rng.uniform(50, 600, (T, 2)), rng.uniform(0.3, 2.0, (T, 1)), rng.uniform(40, 300, (T, 1)), rng.normal(0, 2, (T, 4))], 1)
+    A = rng.normal(size=(T, 8, 8))
+    covs = A @ A.transpose(0, 2, 1) + 5.0 * np.eye(8)
+    meas = np.concatenate([rng.uniform(50, 600, (D, 2)), rng.uniform(0.3, 2.0, (D, 1)), rng.uniform(40, 300, (D, 1))], 1)
+    g = S.kf_gating_distance_batch(means, covs, meas)
+    for t in range(T):
+        np.testing.assert_allclose(g[t], S.kf_gating_distance(means[t], covs[t], meas), rtol=1e-12, atol=0)
+    zs = meas[rng.integers(0, D, T)]
+    nm, nc = S.kf_update_batch(means, covs, zs)
+    for t in range(T):
+        m1, c1 = S.kf_update(means[t], covs[t], zs[t])
+        np.testing.assert_allclose(nm[t], m1, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(nc[t], c1, rtol=1e-11, atol=1e-11)
+
+
+def test_gallery_cache_equals_the_reference_expression():
+    """Gallery.distance with cached normalised rows in a compacting buffer == min over (1 - a_n @ b_n^T) on the raw sample lists
+    (nn_matching.py:33-52, :137-177), bit for bit, across budget overflow, identities leaving and an unbounded gallery."""
+    from vehicle_counting_b200.networks.deepsort.sort import Gallery
+    rng = np.random.default_rng(6)
+    for budget in (3, 7, None):
+        gal = Gallery(0.2, budget)
+        ids = [1, 2, 5, 9]
+        for step in range(40):
+            feats = [rng.normal(size=64).astype(np.float32) for _ in range(6)]
+            targets = [ids[i] for i in rng.integers(0, len(ids), 6)]
+            active = ids if step < 25 else ids[:3]
+            gal.partial_fit(feats, targets, [t for t in active if t in gal.samples or t in targets])
+            q = rng.normal(size=(5, 64)).astype(np.float32)
+            have = [t for t in active if t in gal.samples]
+            if not have:
+                continue
+            got = gal.distance(q, have)
+            bn = q / np.linalg.norm(q, axis=1, keepdims=True)
+            for i, t in enumerate(have):
+                a = np.asarray(gal.samples[t])
+                a = a / np.linalg.norm(a, axis=1, keepdims=True)
+                want = (1.0 - a @ bn.T).min(axis=0)
+                np.testing.assert_array_equal(got[i], want.astype(np.float64))
