@@ -73,9 +73,16 @@ typedef struct VcbConvDesc {
   int32_t a_mode;             /* VCB_A_*: how the im2col operand reaches shared memory */
   int32_t block_n;            /* 0 = auto; N tile (multiple of 16, <= 256) */
   int32_t stages;             /* 0 = auto; smem pipeline depth */
-  int32_t reserved[4];        /* [0]=1: debug epilogue with direct global stores; [1]=1: debug 8-byte C4 gather, 2: im2col-mode TMA even for 1x1 convs;
-                               * [2]=16/32/64: force the K chunk (swizzle) width of the TMA path;
-                               * [3]=1: single-CTA kernel only, 2: require the CTA-pair (cta_group::2) kernel */
+  int32_t reserved[4];        /* all zero = automatic.  Tuning / debug switches (every non-zero [0] selects the generic epilogue):
+                               * [0] 1: direct global stores; 3: skip the epilogue (timing only, output undefined); 4: one accumulator
+                               *     stage; 5: no resident weights; 7: one CTA per SM
+                               * [1] 1: 8-byte C4 gather; 2: im2col-mode TMA even for 1x1; 3: one accumulation chain (patch mode);
+                               *     4: K steps dealt to several accumulators (128-row kernel); 6/7: main-loop timing experiments
+                               * [2] 16/32/64: force the K chunk (swizzle) width of the TMA path
+                               * [3] kernel: 1 = 128-row tiles, two CTAs per SM; 2 / 4 = CTA pairs (cta_group::2) with one / two clusters
+                               *     per SM pair; 3 = 256-row tiles, two accumulators; 5 = patch mode (3x3/s1/p1, 64-channel chunks).
+                               *     Automatic: CTA pairs x2 for 3x3 layers with N >= 128, patch mode for 3x3/s1 layers with N <= 64,
+                               *     128-row tiles otherwise. */
 } VcbConvDesc;
 
 /* element counts of the packed fp16 weight blob and the padded fp32 bias for this descriptor */
