@@ -1,5 +1,5 @@
-"""Drop-in for the hot-path stage wrappers of the reference's `modules` package."""
+"""Drop-in for the stage wrappers of the reference's `modules` package (detect.py, track.py)."""
 from .detect import ImageDetect
-from .track import VideoTracker
+from .track import VideoCounting, VideoTracker
 
-__all__ = ["ImageDetect", "VideoTracker"]
+__all__ = ["ImageDetect", "VideoTracker", "VideoCounting"]

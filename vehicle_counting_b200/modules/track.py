@@ -5,16 +5,19 @@ The reference calls each class tracker's Extractor separately (one H2D, one tiny
 detections, track.py:50-59).  Here the crops of ALL classes of the frame go through the ReID engine in ONE pass: the frame
 is uploaded once, the crop rectangles follow the reference rule (deep_sort.py:78-95, :119-125), and with train-mode
 BatchNorm each class is one statistics segment, which is exactly the reference's per-call batch, so the
-embeddings -- and therefore track ids and boxes -- are those of the per-class calls.  `VideoCounting` (zone filter, CSV) is
-host post-processing outside the hot path and is not mirrored."""
+embeddings -- and therefore track ids and boxes -- are those of the per-class calls.  `VideoCounting` (zone filter, movement
+direction, CSV; track.py:72-137) is once-per-video host post-processing, restated in ../counting.py."""
 from __future__ import annotations
+
+import random
 
 import numpy as np
 
+from ..counting import PALETTE, check_bbox_intersect_polygon, find_best_match_direction, load_zone_anno, save_tracking_to_csv
 from ..networks import DeepSort
 from ..networks.deepsort.deep_sort import _FRAMES
 
-__all__ = ["VideoTracker"]
+__all__ = ["VideoTracker", "VideoCounting"]
 
 
 class VideoTracker:
@@ -84,3 +87,34 @@ class VideoTracker:
                 result_dict["labels"].append(i)
         result_dict["boxes"] = np.array(result_dict["boxes"])
         return result_dict
+
+
+class VideoCounting:
+    """track.py:72-137: keeps, per label and track, the boxes (xyxy) whose corners touch the zone polygon, assigns each track the
+    annotated direction closest (cosine) to its first-centre -> last-centre vector and writes the tracking CSV."""
+
+    def __init__(self, class_names, zone_path, minimum_length=4) -> None:
+        self.class_names = class_names
+        self.num_classes = len(class_names)
+        self.track_dict = [{} for _ in range(self.num_classes)]
+        self.minimum_length = minimum_length
+        self.zone_path = zone_path
+        self.polygons, self.directions = load_zone_anno(zone_path)
+
+    def run(self, frames, tracks, labels, boxes, output_path=None):
+        for frame_id, track_id, label_id, box in zip(frames, tracks, labels, boxes):
+            if not check_bbox_intersect_polygon(self.polygons, box):
+                continue
+            per_label = self.track_dict[label_id]
+            if track_id not in per_label:
+                per_label[track_id] = {"boxes": [], "frames": [], "color": random.sample(PALETTE, 1)[0]}
+            per_label[track_id]["boxes"].append(box)
+            per_label[track_id]["frames"].append(frame_id)
+        for per_label in self.track_dict:
+            for rec in per_label.values():
+                b0, b1 = rec["boxes"][0], rec["boxes"][-1]
+                first = ((b0[2] + b0[0]) / 2, (b0[3] + b0[1]) / 2)
+                last = ((b1[2] + b1[0]) / 2, (b1[3] + b1[1]) / 2)
+                rec["direction"] = find_best_match_direction(obj_vector=(first, last), paths=self.directions)
+        if output_path is not None:
+            save_tracking_to_csv(self.track_dict, output_path)
