@@ -42,7 +42,11 @@ enum {
 enum { VCB_ACT_NONE = 0, VCB_ACT_SILU = 1, VCB_ACT_RELU = 2, VCB_ACT_SILU_TANH = 3 };
 enum { VCB_RES_NONE = 0, VCB_RES_AFTER_ACT = 1, VCB_RES_BEFORE_ACT = 2 };
 enum { VCB_F16 = 0, VCB_F32 = 1 };
-enum { VCB_A_AUTO = 0, VCB_A_IM2COL_TMA = 1, VCB_A_GATHER = 2, VCB_A_C4 = 3 };
+/* VCB_A_ROWWIN (stems: 3x3 / stride 1 / pad 1 over cin = cin_pitch = 16): x is W-PADDED, fp16 [n][h][w + 2][16] with pixel
+ * (y, x) at column x + 1, zero pad columns and 16 zero elements after the last row.  One K chunk = one filter row = the 64
+ * contiguous elements of 4 neighbouring pixels (the 4th has zero weights), fetched by ONE tiled TMA box per filter row through
+ * a tensor map whose pixel stride (32 B) is smaller than its 128-byte inner extent: 3 loads per tile instead of 9. */
+enum { VCB_A_AUTO = 0, VCB_A_IM2COL_TMA = 1, VCB_A_GATHER = 2, VCB_A_C4 = 3, VCB_A_ROWWIN = 4 };
 
 /* ---- library state ------------------------------------------------------------------------ */
 int vcb_init(int device);                 /* selects device, checks sm_100, resolves driver entry points */
@@ -51,7 +55,8 @@ int vcb_last_fault(int32_t out4[4]);      /* host: {code, block, info0, info1} o
 int vcb_version(void);
 /* library options (process-wide).  "pdl" = 1: convolution launches carry the programmatic-dependent-launch attribute, so the
  * set-up of one conv kernel overlaps the tail of the previous kernel on the stream (the kernels order their global-memory
- * accesses with griddepcontrol.wait); default from $VCB_PDL at vcb_init(), else 0.  Unknown names: VCB_ERR_INVALID / -1. */
+ * accesses with griddepcontrol.wait); default from $VCB_PDL at vcb_init(), else 0.  "l2_hint" = 1: activation TMA loads carry the
+ * evict-first L2 policy and weight loads evict-last ($VCB_L2_HINT).  Unknown names: VCB_ERR_INVALID / -1. */
 int vcb_set_option(const char* name, int32_t value);
 int vcb_get_option(const char* name);
 /* development aid: "prof" = 1 zeroes and enables per-role cycle counters inside the conv kernel (summed over CTAs: CTA
@@ -78,6 +83,8 @@ typedef struct VcbConvDesc {
                                *     stage; 5: no resident weights; 7: one CTA per SM
                                * [1] 1: 8-byte C4 gather; 2: im2col-mode TMA even for 1x1; 3: one accumulation chain (patch mode);
                                *     4: K steps dealt to several accumulators (128-row kernel); 6/7: main-loop timing experiments
+                               *     bit 8 (| 0x100), any kernel: walk the tiles from the last to the first, so that a layer starts on the
+                               *     part of its input that the previous layer wrote last (still in L2); results are identical
                                * [2] 16/32/64: force the K chunk (swizzle) width of the TMA path
                                * [3] kernel: 1 = 128-row tiles, two CTAs per SM; 2 / 4 = CTA pairs (cta_group::2) with one / two clusters
                                *     per SM pair; 3 = 256-row tiles, two accumulators; 5 = patch mode (3x3/s1/p1, 64-channel chunks).
@@ -101,6 +108,9 @@ int vcb_frames_to_f16c4(const uint8_t* frames, void* out, int32_t n, int32_t h, 
 /* uint8 HWC3 frames -> fp16 space-to-depth NHWC16: out[n][y/2][x/2][(dy*2+dx)*3+c] = in/255, channels 12..15 zero
  * (h, w even).  Turns the 6x6/s2/p2 YOLOv5 stem into a 3x3/s1/p1 convolution that the im2col TMA can feed. */
 int vcb_frames_to_f16_s2d(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t stream);
+/* the same pixels in the W-padded layout VCB_A_ROWWIN reads: out fp16 [n][h/2][w/2 + 2][16], pixel (y, x) at column x + 1.
+ * Columns 0 and w/2 + 1 and the 16 elements after the last row are never written: the caller zeroes the buffer once. */
+int vcb_frames_to_f16_s2d_wpad(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t stream);
 /* letterbox with an exact 2x reduction ([upstream] AutoShape: cv2.resize(INTER_LINEAR) + copyMakeBorder(114), reached from
  * networks/yolo.py:70): dst uint8 [n][h1][w1][3] = 2x2 box mean with round-half-up of src uint8 [n][h0][w0][3] (h0, w0 even)
  * placed at (top, left), pad_value elsewhere; bit-identical to cv2 for this ratio (1280x720 -> 640x360 inside 384x640) */

@@ -122,6 +122,13 @@ case("fast-big-3x3-192-res", mode="tma", n=64, h=40, w=40, k=3, p=1, cin=192, co
 case("fast-big-stem", mode="tma", n=32, h=320, w=320, k=3, p=1, cin=16, cout=48, act="silu")
 case("fast-big-stem-tanh", mode="tma", n=32, h=320, w=320, k=3, p=1, cin=16, cout=48, act="silu_tanh")
 
+# row-window stem mode (VCB_A_ROWWIN): W-padded 16-channel input, one tiled TMA box per filter row
+case("rowwin-stem-64", mode="rowwin", n=2, h=64, w=64, k=3, p=1, cin=16, cout=48, act="silu")
+case("rowwin-odd-23x37-relu", mode="rowwin", n=3, h=23, w=37, k=3, p=1, cin=16, cout=40, act="relu")
+case("rowwin-w160-cout64", mode="rowwin", n=2, h=24, w=160, k=3, p=1, cin=16, cout=64, act="silu")
+case("rowwin-cin12-w320", mode="rowwin", n=1, h=10, w=320, k=3, p=1, cin=12, cin_pitch=16, cout=48, act="silu")
+case("rowwin-big-stem", mode="rowwin", n=32, h=320, w=320, k=3, p=1, cin=16, cout=48, act="silu")
+
 # 256-row CTA tiles with two accumulator chains (cta_pair=3 forces them on small shapes; big layers pick them automatically)
 case("m256-3x3-s1", mode="tma", n=2, h=20, w=20, k=3, p=1, cta_pair=3)
 case("m256-3x3-s2-odd", mode="tma", n=3, h=25, w=25, k=3, s=2, p=1, cin=64, cout=128, act="relu", cta_pair=3)
@@ -234,7 +241,7 @@ def run_case(idx: int) -> dict:
     g = torch.Generator().manual_seed(1234 + idx)
     n, h, w, cin, cout, k, s, p = (c[x] for x in ("n", "h", "w", "cin", "cout", "k", "s", "p"))
     cin_pitch = c["cin_pitch"] or cin
-    mode = {"tma": L.A_IM2COL_TMA, "gather": L.A_GATHER, "c4": L.A_C4}[c["mode"]]
+    mode = {"tma": L.A_IM2COL_TMA, "gather": L.A_GATHER, "c4": L.A_C4, "rowwin": L.A_ROWWIN}[c["mode"]]
     act = {"none": L.ACT_NONE, "silu": L.ACT_SILU, "relu": L.ACT_RELU, "silu_tanh": L.ACT_SILU_TANH}[c["act"]]
     if c.get("pdl"):
         L.check(L.load().vcb_set_option(b"pdl", 1), "set_option")
@@ -267,7 +274,12 @@ def run_case(idx: int) -> dict:
         ref = ref + res_full[..., :cout].float().permute(0, 3, 1, 2)
     ref = ref.permute(0, 2, 3, 1).contiguous()                    # NHWC
 
-    xd = x_full.to(dev)
+    if c["mode"] == "rowwin":      # W-padded layout: pixel (y, x) at column x + 1, zero pad columns, 16 zero elements after the end
+        xpad = torch.zeros(n * h * (w + 2) * 16 + 16, dtype=torch.float16)
+        xpad[:n * h * (w + 2) * 16].view(n, h, w + 2, 16)[:, :, 1:w + 1, :] = x_full
+        xd = xpad.to(dev)
+    else:
+        xd = x_full.to(dev)
     wp, bp = ops.pack_conv_weights(d, wt.to(dev), bias.to(dev))
     out_dtype = torch.float32 if c["out"] == "f32" else torch.float16
     y = torch.full((n, ho, wo, cout_pitch), 777.0, dtype=out_dtype, device=dev)

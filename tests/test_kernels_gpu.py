@@ -37,6 +37,25 @@ def test_frames_to_f16_s2d(lib):
         assert (got[..., 12:] == 0).all()
 
 
+def test_frames_to_f16_s2d_wpad(lib):
+    """the W-padded ingest of the row-window stem: same pixels at column x + 1, pad columns and the tail untouched"""
+    from vehicle_counting_b200 import ops
+    rng = np.random.default_rng(2)
+    for shape in [(2, 64, 48), (1, 2, 2), (2, 6, 10), (2, 384, 640)]:       # widths with and without the 8-pixel fast path
+        fr = torch.from_numpy(rng.integers(0, 256, shape + (3,), dtype=np.uint8))
+        n, h, w = shape
+        h2, w2 = h // 2, w // 2
+        flat = torch.full((n * h2 * (w2 + 2) * 16 + 16,), 5.0, dtype=torch.float16, device=DEV)
+        ops.frames_to_f16_s2d_wpad(fr.to(DEV), flat)
+        x = (fr.float() / 255.0).half()
+        ref = x.view(n, h2, 2, w2, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(n, h2, w2, 12)
+        got = flat.cpu()
+        body = got[:n * h2 * (w2 + 2) * 16].view(n, h2, w2 + 2, 16)
+        assert torch.equal(body[:, :, 1:w2 + 1, :12], ref)
+        assert (body[:, :, 1:w2 + 1, 12:] == 0).all()
+        assert (body[:, :, 0] == 5.0).all() and (body[:, :, w2 + 1] == 5.0).all() and (got[-16:] == 5.0).all()
+
+
 def test_upsample2x_into_slice(lib):
     from vehicle_counting_b200 import ops
     g = torch.Generator().manual_seed(0)

@@ -91,7 +91,8 @@ def main():
         for i in np.argsort(-per_r)[:14]:
             fl = rp.step_flops[i]
             print(f"  step {i:3d}: {per_r[i] * 1e3:8.1f} us  {fl / per_r[i] / 1e9 if fl else 0:7.1f} TF/s  {rp.labels[i]}")
-        res["reid"] = {"n": a.reid, "ms_graph": ms_r, "eager_ms": per_r.tolist(), "conv_flops": rp.conv_flops}
+        res["reid"] = {"n": a.reid, "ms_graph": ms_r, "eager_ms": per_r.tolist(), "conv_flops": rp.conv_flops,
+                       "labels": rp.labels, "step_flops": rp.step_flops}
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(res, open(a.out, "w"))
 

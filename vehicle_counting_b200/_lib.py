@@ -11,13 +11,14 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvcb200.so")
+# $VCB_LIB_PATH: an alternative build of the same library (A/B builds made by tools/ab_build.sh)
+LIB_PATH = os.environ.get("VCB_LIB_PATH") or os.path.join(_HERE, "libvcb200.so")
 
 VCB_OK = 0
 ACT_NONE, ACT_SILU, ACT_RELU, ACT_SILU_TANH = 0, 1, 2, 3
 RES_NONE, RES_AFTER_ACT, RES_BEFORE_ACT = 0, 1, 2
 F16, F32 = 0, 1
-A_AUTO, A_IM2COL_TMA, A_GATHER, A_C4 = 0, 1, 2, 3
+A_AUTO, A_IM2COL_TMA, A_GATHER, A_C4, A_ROWWIN = 0, 1, 2, 3, 4
 
 
 class VcbError(RuntimeError):
@@ -87,6 +88,7 @@ _SIGNATURES = {
     "vcb_conv_out_hw": ([C.POINTER(ConvDesc), C.POINTER(_I32), C.POINTER(_I32)], _I32),
     "vcb_frames_to_f16c4": ([_VP, _VP, _I32, _I32, _I32, _VP], _I32),
     "vcb_frames_to_f16_s2d": ([_VP, _VP, _I32, _I32, _I32, _VP], _I32),
+    "vcb_frames_to_f16_s2d_wpad": ([_VP, _VP, _I32, _I32, _I32, _VP], _I32),
     "vcb_letterbox_half_u8": ([_VP, _I32, _I32, _I32, _VP, _I32, _I32, _I32, _I32, _I32, _VP], _I32),
     "vcb_upsample2x": ([_VP, _I32, _VP, _I32, _I32, _I32, _I32, _I32, _VP], _I32),
     "vcb_sppf_pool": ([_VP, _I32, _I32, _I32, _I32, _I32, _VP], _I32),

@@ -12,6 +12,7 @@ namespace vcb {
 // other translation units
 int frames_to_f16c4(const uint8_t*, void*, int, int, int, cudaStream_t);
 int frames_to_f16_s2d(const uint8_t*, void*, int, int, int, cudaStream_t);
+int frames_to_f16_s2d_wpad(const uint8_t*, void*, int, int, int, cudaStream_t);
 int letterbox_half(const uint8_t*, int, int, int, uint8_t*, int, int, int, int, int, cudaStream_t);
 int upsample2x(const void*, int, void*, int, int, int, int, int, cudaStream_t);
 int sppf_pool(void*, int, int, int, int, int, cudaStream_t);
@@ -99,12 +100,14 @@ int vcb_init(int device) {
   s.device = device;
   s.initialised = true;
   if (const char* e_pdl = getenv("VCB_PDL")) s.pdl = atoi(e_pdl) != 0 ? 1 : 0;
+  if (const char* e_l2 = getenv("VCB_L2_HINT")) s.l2_hint = atoi(e_l2) != 0 ? 1 : 0;
   return VCB_OK;
 }
 
 int vcb_set_option(const char* name, int32_t value) {
   if (!name) return set_error(VCB_ERR_INVALID, "null option name");
   if (strcmp(name, "pdl") == 0) { state().pdl = value != 0 ? 1 : 0; return VCB_OK; }
+  if (strcmp(name, "l2_hint") == 0) { state().l2_hint = value != 0 ? 1 : 0; return VCB_OK; }
   if (strcmp(name, "prof") == 0) {
     State& s = state();
     if (value && s.prof_dev == nullptr) {
@@ -125,6 +128,7 @@ int vcb_read_prof(uint64_t out16[16]) {
 }
 int vcb_get_option(const char* name) {
   if (name && strcmp(name, "pdl") == 0) return state().pdl;
+  if (name && strcmp(name, "l2_hint") == 0) return state().l2_hint;
   return -1;
 }
 
@@ -162,6 +166,10 @@ int vcb_frames_to_f16c4(const uint8_t* frames, void* out, int32_t n, int32_t h, 
 int vcb_frames_to_f16_s2d(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t st) {
   const int rc = require_init(); if (rc) return rc;
   return frames_to_f16_s2d(frames, out, n, h, w, (cudaStream_t)st);
+}
+int vcb_frames_to_f16_s2d_wpad(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return frames_to_f16_s2d_wpad(frames, out, n, h, w, (cudaStream_t)st);
 }
 int vcb_letterbox_half_u8(const uint8_t* src, int32_t n, int32_t h0, int32_t w0, uint8_t* dst, int32_t h1, int32_t w1, int32_t top,
                           int32_t left, int32_t pad_value, vcb_stream_t st) {

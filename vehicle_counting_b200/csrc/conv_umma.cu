@@ -93,6 +93,11 @@ struct ConvParams {
   int kchains;         // 1, 2 or 4 accumulators per tile: K steps are dealt round-robin to independent accumulation chains
                        // (dependent tcgen05.mma on ONE accumulator issue ~200 clk apart), the epilogue sums them
   int cout_pad;        // n_tiles * block_n = length of the packed bias
+  int a_rowwin;        // VCB_A_ROWWIN: one tiled 4-D TMA box per filter ROW over the W-padded input (patch_R x patch_Xs = 128 pixels)
+  int ksteps_lim;      // K = 16 steps issued per 64-element chunk (3 in row-window mode: the 4th pixel has zero weights)
+  int tile_rev;        // walk the tiles from the last to the first: a layer that starts where its producer stopped finds the
+                       // most recently written part of its input still in L2 (the engine alternates the direction per layer)
+  unsigned long long a_policy, b_policy;   // L2 cache policies of the activation / weight TMA loads (kL2Evict*)
   const __half* x;
   const float* bias;
   const __half* residual;
@@ -152,7 +157,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtenso
     const int num_sub = (p.block_n + sub_cols - 1) / sub_cols;
     const bool issuer = threadIdx.x == 0;
     uint32_t tile_iter = 0, sub_count = 0;
-    for (int tile = first_tile; tile < (kTwoCta ? p.num_pair_tiles : p.num_tiles); tile += tile_step, ++tile_iter) {
+    for (int tile_seq = first_tile; tile_seq < (kTwoCta ? p.num_pair_tiles : p.num_tiles); tile_seq += tile_step, ++tile_iter) {
+      const int tile = p.tile_rev ? (kTwoCta ? p.num_pair_tiles : p.num_tiles) - 1 - tile_seq : tile_seq;
       const int m_tile = kTwoCta ? 2 * (tile / p.n_tiles) + cta_rank : tile / p.n_tiles;
       const int n_tile = tile % p.n_tiles;
       const uint32_t acc = (p.acc_stages == 2) ? (tile_iter & 1u) : 0u;
@@ -318,6 +324,33 @@ __device__ __forceinline__ float act_fast(float v) {
   return v;
 }
 
+// Four activations at once.  SiLU = v / (1 + 2^(-v*log2e)) needs one reciprocal per element; the special-function unit (16 lanes
+// per clock per SM against 128 for the FMA pipe) is the busiest pipe of the 1x1 / stem epilogues (ncu: XU 50 % on 1x1 96->96,
+// profiles/r01_ncu_conv_kernels.md).  One rcp.approx serves four elements: r = 1/(d0*d1*d2*d3), 1/d0 = r*d1*(d2*d3), ... -- 1.25
+// MUFU operations per element instead of 2, at 3.25 extra FMULs.  The exponent is clamped at 31 so that the product of four
+// denominators stays below 2^124 (no overflow, no denormal reciprocal); below v = -21.5 the exact result is under half an fp16
+// subnormal (|v * sigmoid(v)| < 1.1e-8), and so is the clamped one.
+template <int ACT>
+__device__ __forceinline__ void act_fast4(float& v0, float& v1, float& v2, float& v3) {
+#ifndef VCB_SILU_PLAIN      // -DVCB_SILU_PLAIN: one ex2 + one rcp per element (A/B builds, tools/ab_build.sh)
+  if (ACT == VCB_ACT_SILU) {
+    float e0, e1, e2, e3, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(v0 * -1.4426950408889634f, 31.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(v1 * -1.4426950408889634f, 31.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fminf(v2 * -1.4426950408889634f, 31.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fminf(v3 * -1.4426950408889634f, 31.0f)));
+    const float d0 = 1.0f + e0, d1 = 1.0f + e1, d2 = 1.0f + e2, d3 = 1.0f + e3;
+    const float p01 = d0 * d1, p23 = d2 * d3;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
+    const float r01 = r * p23, r23 = r * p01;        // 1/(d0*d1), 1/(d2*d3)
+    v0 *= r01 * d1; v1 *= r01 * d0; v2 *= r23 * d3; v3 *= r23 * d2;
+  } else
+#endif
+  {
+    v0 = act_fast<ACT>(v0); v1 = act_fast<ACT>(v1); v2 = act_fast<ACT>(v2); v3 = act_fast<ACT>(v3);
+  }
+}
+
 template <int ACT, int RES, bool F32OUT, bool M256, bool TWO_CTA = false, bool PATCH = false>
 __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CUtensorMap* tmap_out_ptr, const CUtensorMap* tmap_res_ptr,
                                                    uint32_t tmem_base, uint32_t out_stage, uint32_t bias_smem, uint32_t res_bar0,
@@ -385,12 +418,15 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
   uint32_t tile_iter = 0, sub_count = 0;
   long long t_wait = 0, t_sync = 0;
   const long long t_begin = prof_clock(issuer ? p.prof : nullptr);
+  auto map_tile = [&](int seq) { return p.tile_rev ? total_tiles - 1 - seq : seq; };
   if (RES != VCB_RES_NONE && issuer && first_tile < total_tiles) {      // residual of the first sub-tile
-    const int pm0 = first_tile / p.n_tiles, nt0 = first_tile - pm0 * p.n_tiles;
+    const int ft = map_tile(first_tile);
+    const int pm0 = ft / p.n_tiles, nt0 = ft - pm0 * p.n_tiles;
     const int mt0 = TWO_CTA ? 2 * pm0 + cta_rank : pm0;
     issue_res_load(res_bar0, out_stage, nt0 * p.block_n, mt0);
   }
-  for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++tile_iter) {
+  for (int tile_seq = first_tile; tile_seq < total_tiles; tile_seq += tile_step, ++tile_iter) {
+    const int tile = map_tile(tile_seq);
     const int pm_tile = tile / p.n_tiles;
     const int n_tile = tile - pm_tile * p.n_tiles;
     const int m_tile = TWO_CTA ? 2 * pm_tile + cta_rank : pm_tile;
@@ -480,20 +516,18 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
             for (int hh = 0; hh < 2; ++hh) {
               const __half2* rh = reinterpret_cast<const __half2*>(&rv[g][hh]);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 t = __half22float2(rh[i]);
-                if (RES == VCB_RES_BEFORE_ACT) {
-                  f[hh * 8 + 2 * i] = act_fast<ACT>(f[hh * 8 + 2 * i] + t.x);
-                  f[hh * 8 + 2 * i + 1] = act_fast<ACT>(f[hh * 8 + 2 * i + 1] + t.y);
-                } else {
-                  f[hh * 8 + 2 * i] = act_fast<ACT>(f[hh * 8 + 2 * i]) + t.x;
-                  f[hh * 8 + 2 * i + 1] = act_fast<ACT>(f[hh * 8 + 2 * i + 1]) + t.y;
-                }
+              for (int i = 0; i < 4; i += 2) {                    // four elements = two half2 of the staged residual
+                const float2 ta = __half22float2(rh[i]), tb = __half22float2(rh[i + 1]);
+                float& f0 = f[hh * 8 + 2 * i]; float& f1 = f[hh * 8 + 2 * i + 1];
+                float& f2 = f[hh * 8 + 2 * i + 2]; float& f3 = f[hh * 8 + 2 * i + 3];
+                if (RES == VCB_RES_BEFORE_ACT) { f0 += ta.x; f1 += ta.y; f2 += tb.x; f3 += tb.y; }
+                act_fast4<ACT>(f0, f1, f2, f3);
+                if (RES == VCB_RES_AFTER_ACT) { f0 += ta.x; f1 += ta.y; f2 += tb.x; f3 += tb.y; }
               }
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = act_fast<ACT>(f[i]);
+            for (int i = 0; i < 16; i += 4) act_fast4<ACT>(f[i], f[i + 1], f[i + 2], f[i + 3]);
           }
           // staged row = 128 bytes; this pass owns 16-byte chunks [colhalf*4, colhalf*4+4); 128-byte swizzle
           const uint32_t row_addr = stage_buf + row_off;
@@ -530,10 +564,11 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
         issue_store(stage_buf, n_base + sub * SUB_COLS, m_tile);
         tma_store_commit();
         if (RES != VCB_RES_NONE) {                        // request the residual of the next sub-tile (maybe of the next tile)
-          int nt = tile, nsub = sub + 1;
-          if (nsub == num_sub) { nsub = 0; nt = tile + tile_step; }
-          if (nt < total_tiles) {
+          int nseq = tile_seq, nsub = sub + 1;
+          if (nsub == num_sub) { nsub = 0; nseq = tile_seq + tile_step; }
+          if (nseq < total_tiles) {
             if (!two_bufs) tma_store_wait_read<0>();        // same buffer: the store just issued must have read it
+            const int nt = map_tile(nseq);
             const int npm = nt / p.n_tiles, nn = nt - npm * p.n_tiles;
             const int nm = TWO_CTA ? 2 * npm + cta_rank : npm;
             const uint32_t nb = two_bufs ? ((sub_count + 1u) & 1u) : 0u;
@@ -649,12 +684,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // small layers: every packed weight chunk is loaded once per CTA and stays put
         const uint32_t bc = (uint32_t)(p.block_n * BK * 2);
         mbar_arrive_expect_tx(bres_bar, (uint32_t)p.total_chunks * bc);
-        for (int kc = 0; kc < p.total_chunks; ++kc) tma_load_2d(&tmap_b, bres_bar, b_res + (uint32_t)kc * bc, kc * BK, 0);
+        for (int kc = 0; kc < p.total_chunks; ++kc) tma_load_2d(&tmap_b, bres_bar, b_res + (uint32_t)kc * bc, kc * BK, 0, p.b_policy);
       }
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile_seq = blockIdx.x; tile_seq < p.num_tiles; tile_seq += gridDim.x) {
+        const int tile = p.tile_rev ? p.num_tiles - 1 - tile_seq : tile_seq;
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         int cw = 0, ch = 0, cn = 0;
-        if (A_MODE == A_TMA) {
+        if (A_MODE == A_TMA && p.a_rowwin) {        // tile = patch_R rows x patch_Xs columns of image cn, top-left (ch, cw)
+          const int per_img = p.patch_ytiles * p.patch_xsegs;
+          cn = m_tile / per_img;
+          const int rem = m_tile - cn * per_img;
+          const int yt = rem / p.patch_xsegs;
+          ch = yt * p.patch_R;
+          cw = (rem - yt * p.patch_xsegs) * p.patch_Xs;
+        } else if (A_MODE == A_TMA) {
           const int m0 = m_tile * kTileM;
           cn = m0 / p.PQ;
           const int rem = m0 - cn * p.PQ;
@@ -679,15 +722,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (A_MODE == A_TMA) {
             mbar_arrive_expect_tx(full_bar(st), (uint32_t)nch * ((p.split_b || p.b_resident) ? a_chunk : a_chunk + b_chunk));
             for (int g = 0; g < nch; ++g, ++kidx) {
-              if (p.a_tiled) tma_load_2d(&tmap_a, full_bar(st), a_dst + (uint32_t)g * a_chunk, c * BK, m_tile * kTileM);
-              else tma_load_im2col_4d(&tmap_a, full_bar(st), a_dst + (uint32_t)g * a_chunk, c * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+              if (p.a_rowwin) tma_load_4d(&tmap_a, full_bar(st), a_dst, 0, cw, ch - 1 + kit, cn, p.a_policy);
+              else if (p.a_tiled) tma_load_2d(&tmap_a, full_bar(st), a_dst + (uint32_t)g * a_chunk, c * BK, m_tile * kTileM, p.a_policy);
+              else tma_load_im2col_4d(&tmap_a, full_bar(st), a_dst + (uint32_t)g * a_chunk, c * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r, p.a_policy);
               if (!p.split_b && !p.b_resident)
-                tma_load_2d(&tmap_b, full_bar(st), b_dst + (uint32_t)g * b_chunk, kidx * BK, n_tile * p.block_n);
+                tma_load_2d(&tmap_b, full_bar(st), b_dst + (uint32_t)g * b_chunk, kidx * BK, n_tile * p.block_n, p.b_policy);
               if (++c == p.chunks_per_tap) { c = 0; if (++s == p.kw) { s = 0; ++r; } }
             }
           } else {
             mbar_arrive_expect_tx(full_bar(st), b_tile_bytes);
-            tma_load_2d(&tmap_b, full_bar(st), b_dst, kit * kBlockK, n_tile * p.block_n);
+            tma_load_2d(&tmap_b, full_bar(st), b_dst, kit * kBlockK, n_tile * p.block_n, p.b_policy);
           }
         }
       }
@@ -707,6 +751,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // descriptor high words are loop invariants; only the 14-bit start-address field changes
       const uint64_t desc_hi = umma_desc_kmajor(0, sbo, layout_type);
       uint32_t it = 0, tile_iter = 0, ring_st = 0, ring_ph = 0;
+      const int klim = p.ksteps_lim;
       long long t_wf = 0, t_wt = 0;
       const long long t_b = prof_clock(p.prof);
       if (p.b_resident && (int)blockIdx.x < p.num_tiles) mbar_wait(bres_bar, 0u, p.fault, FAULT_FULL_WAIT, 300);
@@ -741,6 +786,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               const uint64_t b_desc = b_desc0 + (uint64_t)(((uint32_t)g * b_chunk) >> 4);
 #pragma unroll
               for (int k = 0; k < ksteps; ++k) {
+                if (k >= klim) continue;
                 // +32 bytes per UMMA_K step inside the swizzle row: +2 in the (addr >> 4) field
                 if (M256 && p.dbg_swap) {   // experiment: D^T[128 x 256 pixels] = W[128 x 16] * X[256 x 16]^T, one instruction per K step
                   umma_f16(tmem_base + acc * 256u, b_desc + (uint64_t)(2 * k), a_desc + (uint64_t)(2 * k), umma_idesc_f16(256u), accumulate);
@@ -769,6 +815,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp < kEpilogueWarps) {
 #define VCB_EPI_CASE(K, ACT, RES, F32) \
     case K: conv_epilogue_fast<ACT, RES, F32, M256>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), tmem_empty_bar(0)); break;
+    if (A_MODE == A_TMA && !M256 && p.a_rowwin) {   // 2-D pixel blocks: the patch-mode staging / 4-D store with a dense lattice (Lp = Xs)
+      if (p.epi_kind == 1)
+        conv_epilogue_fast<VCB_ACT_SILU, VCB_RES_NONE, false, false, false, true>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), tmem_empty_bar(0));
+      else
+        conv_epilogue_fast<VCB_ACT_RELU, VCB_RES_NONE, false, false, false, true>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), tmem_empty_bar(0));
+    } else
     switch (A_MODE == A_TMA ? p.epi_kind : 0) {
       VCB_EPI_CASE(1, VCB_ACT_SILU, VCB_RES_NONE, false)
       VCB_EPI_CASE(2, VCB_ACT_SILU, VCB_RES_AFTER_ACT, false)
@@ -788,8 +840,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t b_chunk = (uint32_t)(p.block_n * BK * 2);
       constexpr int G = kBlockK / BK;
       uint32_t ring_st = 0, ring_ph = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
+      for (int tile_seq = blockIdx.x; tile_seq < p.num_tiles; tile_seq += gridDim.x) {
+        const int n_tile = (p.tile_rev ? p.num_tiles - 1 - tile_seq : tile_seq) % p.n_tiles;
         int kidx = 0;
         for (int kit = 0; kit < p.num_k_iters; ++kit, ++it) {
           const int st = (int)ring_st;
@@ -809,8 +861,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int gtid = threadIdx.x - kGatherWarp0 * 32;
     uint32_t ring_st = 0, ring_ph = 0, it = 0;          // K-steps issued by this thread (same sequence in every gather thread)
     uint32_t arrived = 0;     // K-steps already signalled on their full barrier
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles;
+    for (int tile_seq = blockIdx.x; tile_seq < p.num_tiles; tile_seq += gridDim.x) {
+      const int m_tile = (p.tile_rev ? p.num_tiles - 1 - tile_seq : tile_seq) / p.n_tiles;
       asm volatile("bar.sync 1, 128;" ::: "memory");     // everyone is done reading the previous table
       {
         const int m = m_tile * kBlockM + gtid;
@@ -976,7 +1028,8 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const uint32_t b_chunk = (uint32_t)((p.block_n >> 1) * BK * 2);
       constexpr int G = kBlockK / BK;
       uint32_t ring_st = 0, ring_ph = 0, it = 0;
-      for (int tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters) {
+      for (int tile_seq = cluster_id; tile_seq < p.num_pair_tiles; tile_seq += num_clusters) {
+        const int tile = p.tile_rev ? p.num_pair_tiles - 1 - tile_seq : tile_seq;
         const int pm = tile / p.n_tiles, n_tile = tile - pm * p.n_tiles;
         const int m0 = (2 * pm + rank) * kBlockM;      // may lie past M for the last pair: the TMA zero-fills
         const int cn = m0 / p.PQ;
@@ -996,10 +1049,10 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           if (leader) mbar_arrive_expect_tx(full_bar(st), 2u * (uint32_t)nch * (a_chunk + b_chunk));
           else mbar_arrive_remote(full_bar(st), 0);
           for (int g = 0; g < nch; ++g, ++kidx) {
-            if (p.a_tiled) tma_load_2d_2cta(&tmap_a, lead_full, a_dst + (uint32_t)g * a_chunk, c * BK, m0);
-            else tma_load_im2col_4d_2cta(&tmap_a, lead_full, a_dst + (uint32_t)g * a_chunk, c * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+            if (p.a_tiled) tma_load_2d_2cta(&tmap_a, lead_full, a_dst + (uint32_t)g * a_chunk, c * BK, m0, p.a_policy);
+            else tma_load_im2col_4d_2cta(&tmap_a, lead_full, a_dst + (uint32_t)g * a_chunk, c * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r, p.a_policy);
             tma_load_2d_2cta(&tmap_b, lead_full, b_dst + (uint32_t)g * b_chunk, kidx * BK,
-                             n_tile * p.block_n + rank * (p.block_n >> 1));
+                             n_tile * p.block_n + rank * (p.block_n >> 1), p.b_policy);
             if (++c == p.chunks_per_tap) { c = 0; if (++s == p.kw) { s = 0; ++r; } }
           }
         }
@@ -1154,8 +1207,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == kProducerWarp) {
     if (lane == 0) {         // ---- patch producer: one 4-D box per (tile, channel chunk)
       uint32_t sa = 0, pha = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles;
+      for (int tile_seq = blockIdx.x; tile_seq < p.num_tiles; tile_seq += gridDim.x) {
+        const int mt = (p.tile_rev ? p.num_tiles - 1 - tile_seq : tile_seq) / p.n_tiles;
         const int ni = mt / per_img, rem = mt - ni * per_img;
         const int yt = rem / p.patch_xsegs, xs = rem - yt * p.patch_xsegs;
         for (int c = 0; c < chunks; ++c) {
@@ -1164,7 +1217,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           prof_add(p.prof, PROF_PROD_WAIT_EMPTY, prof_clock(p.prof) - tw);
           mbar_arrive_expect_tx(afull(sa), (uint32_t)p.patch_box_bytes);
           tma_load_4d(&tmap_a, afull(sa), a_region + sa * (uint32_t)p.patch_stage_bytes, c * kBlockK, xs * p.patch_Xs - 1,
-                      yt * p.patch_R - 1, ni);
+                      yt * p.patch_R - 1, ni, p.a_policy);
           if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; }
         }
       }
@@ -1174,17 +1227,17 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (p.b_resident) {
         if ((int)blockIdx.x < p.num_tiles) {
           mbar_arrive_expect_tx(bres_bar, (uint32_t)p.total_chunks * bc);
-          for (int kc = 0; kc < p.total_chunks; ++kc) tma_load_2d(&tmap_b, bres_bar, b_region + (uint32_t)kc * bc, kc * kBlockK, 0);
+          for (int kc = 0; kc < p.total_chunks; ++kc) tma_load_2d(&tmap_b, bres_bar, b_region + (uint32_t)kc * bc, kc * kBlockK, 0, p.b_policy);
         }
       } else {
         uint32_t sb = 0, phb = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-          const int nt = tile % p.n_tiles;
+        for (int tile_seq = blockIdx.x; tile_seq < p.num_tiles; tile_seq += gridDim.x) {
+          const int nt = (p.tile_rev ? p.num_tiles - 1 - tile_seq : tile_seq) % p.n_tiles;
           for (int c = 0; c < chunks; ++c)
             for (int t = 0; t < 9; ++t) {
               mbar_wait(bempty(sb), phb ^ 1u, p.fault, FAULT_EMPTY_WAIT, 620 + (int)sb);
               mbar_arrive_expect_tx(bfull(sb), b_tile_bytes);
-              tma_load_2d(&tmap_b, bfull(sb), b_region + sb * b_tile_bytes, (t * chunks + c) * kBlockK, nt * p.block_n);
+              tma_load_2d(&tmap_b, bfull(sb), b_region + sb * b_tile_bytes, (t * chunks + c) * kBlockK, nt * p.block_n, p.b_policy);
               if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= 1u; }
             }
         }
@@ -1281,12 +1334,17 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias, __half* __restrict__ wp,
                                     float* __restrict__ bp, int cout, int cin, int kh, int kw, int cout_pad, int k_pad,
-                                    int cin_pad, int c4) {
+                                    int cin_pad, int c4, int rowwin) {
   const long long total = (long long)cout_pad * k_pad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int o = (int)(i / k_pad), k = (int)(i - (long long)o * k_pad);
     int tap, c;
-    if (c4) { tap = k >> 2; c = k & 3; } else { tap = k / cin_pad; c = k - tap * cin_pad; }
+    if (c4) { tap = k >> 2; c = k & 3; }
+    else if (rowwin) {        // k = r * 64 + s * 16 + c, s = 3 is the zero pixel that completes the 128-byte row
+      const int r = k >> 6, sx = (k >> 4) & 3;
+      c = k & 15;
+      tap = sx < 3 ? r * 3 + sx : kh * kw;
+    } else { tap = k / cin_pad; c = k - tap * cin_pad; }
     float v = 0.0f;
     if (o < cout && c < cin && tap < kh * kw) {
       const int r = tap / kw, s = tap - r * kw;
@@ -1318,10 +1376,13 @@ struct ConvGeom {
   int patch;            // patch mode (conv_patch_kernel)
   int patch_R, patch_Xs, patch_Lp, patch_xsegs, patch_ytiles, patch_stage_bytes, a_stages, b_stages;
   int b_resident, b_res_bytes;
+  int rowwin;           // VCB_A_ROWWIN (patch_R x patch_Xs pixel blocks, dense lattice)
   size_t smem_bytes;
 };
 
-static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
+static int conv_geometry(const VcbConvDesc& d_in, ConvGeom& g) {
+  VcbConvDesc d = d_in;
+  d.reserved[1] &= 0xff;      // bits 8.. are per-launch flags that do not change the geometry (conv2d_fwd)
   if (d.n <= 0 || d.h <= 0 || d.w <= 0 || d.cin <= 0 || d.cout <= 0 || d.kh <= 0 || d.kw <= 0 || d.stride <= 0 ||
       d.pad < 0)
     return set_error(VCB_ERR_INVALID, "conv: non-positive dimension");
@@ -1333,7 +1394,28 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
   g.M = (int)M;
   int mode = d.a_mode;
   if (mode == VCB_A_AUTO) mode = (d.cin_pitch == 4 && d.cin <= 4) ? VCB_A_C4 : VCB_A_IM2COL_TMA;
-  if (mode == VCB_A_C4) {
+  g.rowwin = 0;
+  if (mode == VCB_A_ROWWIN) {
+    if (d.cin > 16 || d.cin_pitch != 16 || d.kh != 3 || d.kw != 3 || d.stride != 1 || d.pad != 1 || d.cout > 256 ||
+        d.res_mode != VCB_RES_NONE || d.out_dtype != VCB_F16 || (d.act != VCB_ACT_SILU && d.act != VCB_ACT_RELU) || d.reserved[0] != 0 ||
+        (d.reserved[3] != 0 && d.reserved[3] != 1) || d.reserved[2] != 0)
+      return set_error(VCB_ERR_INVALID, "conv: VCB_A_ROWWIN needs a 3x3/s1/p1 layer over cin_pitch = 16 (W-padded input), SiLU or ReLU, fp16 out, no residual");
+    g.a_mode = A_TMA;
+    g.rowwin = 1;
+    g.bk = kBlockK;
+    g.chunks_per_tap = 1;
+    g.cin_pad = 16;
+    g.total_chunks = 3;                                  // filter rows
+    // pixel block R x Xs = 128 with the fewest junk pixels
+    double best = -1.0;
+    for (int xs = 128; xs >= 8; xs >>= 1) {
+      const int r = 128 / xs;
+      const int nseg = (d.w + xs - 1) / xs, yt = (d.h + r - 1) / r;
+      const double util = (double)d.h * d.w / ((double)nseg * yt * 128.0);
+      if (util > best + 1e-9) { best = util; g.patch_R = r; g.patch_Xs = xs; g.patch_xsegs = nseg; g.patch_ytiles = yt; }
+    }
+    g.patch_Lp = g.patch_Xs;
+  } else if (mode == VCB_A_C4) {
     if (d.cin_pitch != 4 || d.cin > 4) return set_error(VCB_ERR_INVALID, "conv: A_C4 needs cin<=4 and cin_pitch==4");
     g.a_mode = A_C4;
     g.bk = kBlockK;
@@ -1373,7 +1455,7 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
   }
   if (g.n_tiles > 1 && g.block_n % 64 != 0) return set_error(VCB_ERR_INVALID, "conv: block_n must be a multiple of 64 when cout spans several N tiles");
   g.cout_pad = g.n_tiles * g.block_n;
-  g.m_tiles = (g.M + kBlockM - 1) / kBlockM;
+  g.m_tiles = g.rowwin ? d.n * g.patch_ytiles * g.patch_xsegs : (g.M + kBlockM - 1) / kBlockM;
   const int cout_store = (d.cout + 7) / 8 * 8;
   if (d.cout_pitch < cout_store || d.cout_pitch % 8 != 0)
     return set_error(VCB_ERR_INVALID, "conv: cout_pitch must be a multiple of 8 and >= round_up(cout, 8)");
@@ -1386,7 +1468,7 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
   // parity elsewhere (profiles/r01_layer_modes.md).  reserved[3]: 1 = never, 2 = pair kernel with one cluster per SM pair,
   // 4 = pair kernel with two.
   const int epi0 = (d.reserved[0] == 0) ? epi_kind_of(d.act, d.res_mode, d.out_dtype == VCB_F32 ? 1 : 0) : 0;
-  const bool auto_pair = d.reserved[3] == 0 && g.a_mode == A_TMA && epi0 != 0 && d.kh * d.kw > 1 && g.block_n >= 128 &&
+  const bool auto_pair = d.reserved[3] == 0 && g.a_mode == A_TMA && !g.rowwin && epi0 != 0 && d.kh * d.kw > 1 && g.block_n >= 128 &&
                          (long long)((g.m_tiles + 1) / 2) * g.n_tiles >= 2 * 148;
   g.two_cta = (g.a_mode == A_TMA && g.m_tiles >= 2 && (d.reserved[3] == 2 || d.reserved[3] == 4 || auto_pair)) ? 1 : 0;
   if ((d.reserved[3] == 2 || d.reserved[3] == 4) && !g.two_cta) return set_error(VCB_ERR_INVALID, "conv: the CTA-pair kernel needs the TMA path and >= 2 M tiles");
@@ -1398,7 +1480,7 @@ static int conv_geometry(const VcbConvDesc& d, ConvGeom& g) {
   int chosen = 0;
   // ---- patch mode: 3x3/s1/p1 with 64-channel chunks; reserved[3] == 5 forces it, == 1 (or any other forced mode) forbids it
   {
-    const bool can = g.a_mode == A_TMA && !g.two_cta && g.epi_kind != 0 && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.pad == 1 && g.bk == 64;
+    const bool can = g.a_mode == A_TMA && !g.rowwin && !g.two_cta && g.epi_kind != 0 && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.pad == 1 && g.bk == 64;
     // automatic for narrow layers (N <= 64) with at least two waves of tiles: measured 4-14 % faster than the 128-row im2col mode
     // (ReID layer 1, YOLOv5m 48->48, YOLOv5s 64->64; profiles/r01_layer_modes.md); wider layers lose (single CTA per SM)
     bool want = can && (d.reserved[3] == 5);
@@ -1572,7 +1654,7 @@ int conv_pack_weights(const VcbConvDesc& d, const float* w, const float* bias, v
   const long long total = (long long)g.cout_pad * g.k_pad;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   pack_weights_kernel<<<blocks, 256, 0, st>>>(w, bias, reinterpret_cast<__half*>(wp), bp, d.cout, d.cin, d.kh, d.kw,
-                                              g.cout_pad, g.k_pad, g.cin_pad, g.a_mode == A_C4 ? 1 : 0);
+                                              g.cout_pad, g.k_pad, g.cin_pad, g.a_mode == A_C4 ? 1 : 0, g.rowwin);
   return check_cuda(cudaGetLastError(), "pack_weights launch");
 }
 
@@ -1627,8 +1709,11 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return check_cuda(cudaLaunchKernelEx(&cfg, conv_umma_kernel<A_MODE, BK, M256>, ta, tb, to, tr, p), "conv launch");
 }
 
-int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const float* bias_packed, const void* residual,
+int conv2d_fwd(const VcbConvDesc& d_in, const void* x, const void* w_packed, const float* bias_packed, const void* residual,
                void* y, cudaStream_t st) {
+  VcbConvDesc d = d_in;
+  const int launch_flags = d.reserved[1] >> 8;      // bit 0: walk the tiles in reverse order
+  d.reserved[1] &= 0xff;
   int rc = require_init();
   if (rc != VCB_OK) return rc;
   ConvGeom g;
@@ -1667,6 +1752,10 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
   if (p.dbg_swap) { p.tmem_cols = 512; p.acc_stages = 2; }
   p.cout_pad = g.cout_pad;
   p.epi_kind = g.epi_kind;
+  p.tile_rev = (launch_flags & 1) ? 1 : 0;
+  p.ksteps_lim = 4;
+  p.a_policy = state().l2_hint ? kL2EvictFirst : kL2EvictNormal;
+  p.b_policy = state().l2_hint ? kL2EvictLast : kL2EvictNormal;
   p.kchains = g.kchains;
   if (g.patch) {
     p.patch_R = g.patch_R; p.patch_Xs = g.patch_Xs; p.patch_Lp = g.patch_Lp; p.patch_xsegs = g.patch_xsegs; p.patch_ytiles = g.patch_ytiles;
@@ -1740,6 +1829,48 @@ int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const 
     cudaLaunchAttribute attr[1];
     fill_launch_config(cfg, attr, grid, kThreadsPatch, g.smem_bytes, st);
     return check_cuda(cudaLaunchKernelEx(&cfg, conv_patch_kernel, ta, tb, to, tr, p), "conv (patch) launch");
+  }
+  if (g.rowwin) {
+    // Row-window mode.  Input: W-padded NHWC16, pixel (y, x) at column x + 1.  Tensor-map view (k, x, y, n): element k of window x
+    // of row y at byte 2k + 32x + 32(W+2)y -- the pixel stride (32 B) is SMALLER than the 128-byte inner extent, i.e. neighbouring
+    // windows overlap; the window of output column x holds input columns x-1 .. x+2 (the last one against zero weights).  Rows
+    // y = -1 and y = H are out of range and zero-filled by the TMA unit, the left / right borders are the buffer's zero pad columns.
+    p.a_rowwin = 1;
+    p.ksteps_lim = 3;
+    p.patch_R = g.patch_R; p.patch_Xs = g.patch_Xs; p.patch_Lp = g.patch_Lp; p.patch_xsegs = g.patch_xsegs; p.patch_ytiles = g.patch_ytiles;
+    p.patch_out_bytes = kStageOutBytes;
+    p.m_tiles = g.m_tiles;
+    p.num_tiles = p.m_tiles * g.n_tiles;
+    const cuuint32_t estr4[4] = {1, 1, 1, 1};
+    {
+      const cuuint64_t wp = (cuuint64_t)d.w + 2;
+      const cuuint64_t dims[4] = {64u, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
+      const cuuint64_t strides[3] = {32u, wp * 32u, (cuuint64_t)d.h * wp * 32u};
+      const cuuint32_t box[4] = {64u, (cuuint32_t)g.patch_Xs, (cuuint32_t)g.patch_R, 1u};
+      const CUresult r = state().encode_tiled(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr4,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(row windows) failed: %d", (int)r);
+    }
+    {
+      const cuuint64_t dims[4] = {(cuuint64_t)d.cout, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
+      const cuuint64_t strides[3] = {(cuuint64_t)d.cout_pitch * 2, (cuuint64_t)d.w * d.cout_pitch * 2, (cuuint64_t)d.h * d.w * d.cout_pitch * 2};
+      const cuuint32_t box[4] = {64u, (cuuint32_t)g.patch_Xs, (cuuint32_t)g.patch_R, 1u};
+      const CUresult r = state().encode_tiled(&to, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, y, dims, strides, box, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(row-window output) failed: %d", (int)r);
+    }
+    {
+      const cuuint64_t dims[2] = {(cuuint64_t)g.k_pad, (cuuint64_t)g.cout_pad};
+      const cuuint64_t strides[1] = {(cuuint64_t)g.k_pad * 2};
+      const cuuint32_t box[2] = {64u, (cuuint32_t)g.block_n};
+      const cuuint32_t estr[2] = {1, 1};
+      const CUresult r = state().encode_tiled(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    }
+    return launch_conv<A_TMA, 64>(ta, tb, to, tr, p, g, st);
   }
   if (p.epi_kind != 0 && d.res_mode != VCB_RES_NONE) {   // residual: [M][cout] fp16 view with row pitch res_pitch, same boxes as the output
     const cuuint64_t dims[2] = {(cuuint64_t)d.cout, (cuuint64_t)g.M};

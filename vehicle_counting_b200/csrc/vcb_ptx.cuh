@@ -181,6 +181,46 @@ __device__ __forceinline__ void tma_load_im2col_4d_2cta(const CUtensorMap* m, ui
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
+// ---- the same loads with an L2 cache-policy operand (createpolicy encodings, as CUTLASS's TMA::CacheHintSm90):
+// activations that are read once can be marked evict-first so that they do not push the layer's freshly written
+// output (the next layer's input) out of the 126 MB L2; weights, which every CTA re-reads, evict-last
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_2cta(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c, int w, int h,
+                                                        int n, uint16_t off_w, uint16_t off_h, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h), "l"(pol)
+      : "memory");
+}
 // 2-D tiled store smem -> global (bulk async group)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

@@ -127,6 +127,10 @@ class _Plan:
         self.keep: list = []          # tensors that must outlive the plan (weights, descriptors)
         self.graph: Optional[ops.Graph] = None
         self.stream = torch.cuda.Stream(device=device)
+        # $VCB_TILE_REV=1: consecutive convolutions walk their tiles in opposite directions, so a layer starts on the part of
+        # its input that its producer wrote last (still in the 126 MB L2) instead of the part written first (evicted)
+        self.alternate = os.environ.get("VCB_TILE_REV", "0") == "1"
+        self._rev = False
 
     def add(self, fn: Callable[[object], None], label: str = "op", flops: float = 0.0) -> None:
         self.steps.append(fn)
@@ -140,7 +144,9 @@ class _Plan:
         cout, cin = int(w.shape[0]), int(w.shape[1])
         d = ops.make_conv_desc(n, x.h, x.w, cin, cout, k, s, p, cin_pitch=x.pitch, cout_pitch=y.pitch, act=act,
                                res_mode=res_mode if residual is not None else L.RES_NONE,
-                               res_pitch=residual.pitch if residual is not None else 0, out_dtype=out_dtype, a_mode=a_mode)
+                               res_pitch=residual.pitch if residual is not None else 0, out_dtype=out_dtype, a_mode=a_mode,
+                               tile_rev=self.alternate and self._rev)
+        self._rev = not self._rev
         ho, wo = ops.conv_out_hw(d)
         assert (ho, wo) == (y.h, y.w), ((ho, wo), (y.h, y.w))
         assert x.c == cin or (cin <= 4 and x.pitch == 4), (x.c, cin)
@@ -178,6 +184,13 @@ class _Plan:
             self.run_eager(self.stream)
 
 
+_ROWWIN_OK: Optional[bool] = None
+
+
+def SILU_DEFAULT() -> bool:
+    return os.environ.get("VCB_SILU", "exp") != "tanh"
+
+
 class YoloEngine:
     """YOLOv5 v6.0 detector for a fixed batch of `batch` frames at inference size (h, w) (multiples of 32)."""
 
@@ -208,6 +221,23 @@ class YoloEngine:
     # -- buffer helpers ------------------------------------------------------------------------
     def _buf(self, h, w, c, dtype=torch.float16) -> torch.Tensor:
         return torch.zeros(self.batch, h, w, c, dtype=dtype, device=self.device)
+
+    def _probe_rowwin(self) -> bool:
+        """One tiny row-window convolution: does the driver encode a tensor map whose windows overlap?"""
+        global _ROWWIN_OK
+        if _ROWWIN_OK is None:
+            try:
+                dev = self.device
+                x = torch.zeros(1 * 8 * 10 * 16 + 16, dtype=torch.float16, device=dev)
+                y = torch.zeros(1, 8, 8, 16, dtype=torch.float16, device=dev)
+                d = ops.make_conv_desc(1, 8, 8, 16, 16, 3, 1, 1, cin_pitch=16, cout_pitch=16, act=L.ACT_SILU, a_mode=L.A_ROWWIN)
+                wp, bp = ops.pack_conv_weights(d, torch.zeros(16, 16, 3, 3, device=dev), None)
+                ops.conv2d(d, x, wp, bp, y)
+                torch.cuda.synchronize(dev)
+                _ROWWIN_OK = True
+            except L.VcbError:
+                _ROWWIN_OK = False
+        return _ROWWIN_OK
 
     def _build(self, sd, gd, gw) -> None:
         B, dev, plan = self.batch, self.device, self.plan
@@ -259,8 +289,18 @@ class YoloEngine:
         # uint8 frames -> fp16 space-to-depth NHWC16 (12 used): the 6x6/s2/p2 stem becomes a 3x3/s1/p1 conv over 16
         # channels that the im2col TMA feeds like any other layer (csrc/pointwise.cu frames_to_f16_s2d_kernel)
         self.frames = torch.zeros(B, self.h, self.w, 3, dtype=torch.uint8, device=dev)
-        self.x_s2d = torch.zeros(B, self.h // 2, self.w // 2, 16, dtype=torch.float16, device=dev)
-        plan.add(lambda st: ops.frames_to_f16_s2d(self.frames, self.x_s2d, stream=st), "ingest u8->f16 s2d")
+        h2, w2 = self.h // 2, self.w // 2
+        # Row-window stem ($VCB_STEM_ROWWIN=0 turns it off): the ingest writes a W-padded buffer and the stem fetches one TMA box per
+        # filter ROW (3 per tile instead of 9 im2col boxes); falls back to the im2col stem if the driver rejects the overlapping map
+        self.stem_rowwin = (os.environ.get("VCB_STEM_ROWWIN", "1") != "0" and self.a_mode == L.A_AUTO and SILU_DEFAULT()
+                            and self._probe_rowwin())
+        if self.stem_rowwin:
+            self._s2d_flat = torch.zeros(B * h2 * (w2 + 2) * 16 + 16, dtype=torch.float16, device=dev)
+            self.x_s2d = torch.as_strided(self._s2d_flat, (B, h2, w2, 16), (h2 * (w2 + 2) * 16, (w2 + 2) * 16, 16, 1))
+            plan.add(lambda st: ops.frames_to_f16_s2d_wpad(self.frames, self._s2d_flat, stream=st), "ingest u8->f16 s2d (W-padded)")
+        else:
+            self.x_s2d = torch.zeros(B, h2, w2, 16, dtype=torch.float16, device=dev)
+            plan.add(lambda st: ops.frames_to_f16_s2d(self.frames, self.x_s2d, stream=st), "ingest u8->f16 s2d")
 
         def src_of(i, f) -> TRef:
             return TRef(self.x_s2d, 0, 16) if (i == 0 and f == -1) else home[i - 1 if f == -1 else f]
@@ -276,7 +316,8 @@ class YoloEngine:
                     assert (k, s, p) == (6, 2, 2) and w_.shape[1] == 3
                     w_, k, s, p = stem_weights_to_s2d(w_), 3, 1, 1
                     stem_flops = 2.0 * B * hw[0][0] * hw[0][1] * w_.shape[0] * 3 * 36      # the 6x6 conv's own count
-                    plan.conv(src_of(i, f), B, w_, b_, home[i], k, s, p, SILU, a_mode=self.a_mode, flops=stem_flops)
+                    plan.conv(src_of(i, f), B, w_, b_, home[i], k, s, p, SILU, a_mode=L.A_ROWWIN if self.stem_rowwin else self.a_mode,
+                              flops=stem_flops)
                     continue
                 plan.conv(src_of(i, f), B, w_, b_, home[i], k, s, p, SILU, a_mode=self.a_mode)
             elif kind == "C3":

@@ -23,7 +23,8 @@ def _st(stream) -> int:
 # ------------------------------------------------------------------------------------------ conv
 def make_conv_desc(n, h, w, cin, cout, k, stride, pad, *, cin_pitch=None, cout_pitch=None, act=L.ACT_SILU,
                    res_mode=L.RES_NONE, res_pitch=0, out_dtype=L.F16, a_mode=L.A_AUTO, block_n=0, stages=0,
-                   kw=None, epi_direct=False, c4_narrow=False, bk=0, cta_pair=0, a_im2col=False, one_chain=False, dbg1=0) -> L.ConvDesc:
+                   kw=None, epi_direct=False, c4_narrow=False, bk=0, cta_pair=0, a_im2col=False, one_chain=False, dbg1=0,
+                   tile_rev=False) -> L.ConvDesc:
     d = L.ConvDesc()
     d.n, d.h, d.w = n, h, w
     d.cin, d.cin_pitch = cin, cin if cin_pitch is None else cin_pitch
@@ -35,6 +36,8 @@ def make_conv_desc(n, h, w, cin, cout, k, stride, pad, *, cin_pitch=None, cout_p
     d.out_dtype, d.a_mode, d.block_n, d.stages = out_dtype, a_mode, block_n, stages
     d.reserved[0] = int(epi_direct)   # debug: 1 = direct global stores; 2 = second TMA producer for B; 3 = skip epilogue; 4 = one accumulator
     d.reserved[1] = dbg1 if dbg1 else 3 if one_chain else (2 if a_im2col else (1 if c4_narrow else 0))   # debug: 1 = 8-byte C4 gather; 2 = im2col TMA even for 1x1; 3 = one accumulation chain
+    if tile_rev:
+        d.reserved[1] |= 0x100                  # per-launch flag: walk the tiles from the last to the first (L2 reuse between layers)
     d.reserved[2] = bk                          # 0 = auto; 16/32/64 forces the K chunk width of the TMA path
     d.reserved[3] = cta_pair                    # 0 = auto; 1 = single-CTA 128-row kernel; 2 = CTA-pair (cta_group::2) kernel; 3 = 256-row tiles
     return d
@@ -84,6 +87,14 @@ def frames_to_f16_s2d(frames_u8: torch.Tensor, out: torch.Tensor, stream=None) -
     n, h, w, c = frames_u8.shape
     assert c == 3 and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
     L.check(L.load().vcb_frames_to_f16_s2d(L.ptr(frames_u8), L.ptr(out), n, h, w, _st(stream)), "vcb_frames_to_f16_s2d")
+
+
+def frames_to_f16_s2d_wpad(frames_u8: torch.Tensor, out: torch.Tensor, stream=None) -> None:
+    """out: fp16 buffer of n*(h/2)*(w/2+2)*16 + 16 elements, zeroed once by the caller (pad columns stay zero)"""
+    n, h, w, c = frames_u8.shape
+    assert c == 3 and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+    assert out.numel() >= n * (h // 2) * (w // 2 + 2) * 16 + 16
+    L.check(L.load().vcb_frames_to_f16_s2d_wpad(L.ptr(frames_u8), L.ptr(out), n, h, w, _st(stream)), "vcb_frames_to_f16_s2d_wpad")
 
 
 def upsample2x(src, src_pitch, dst, dst_pitch, n, h, w, c, stream=None) -> None:
