@@ -49,7 +49,8 @@ enum { VCB_F16 = 0, VCB_F32 = 1 };
 enum { VCB_A_AUTO = 0, VCB_A_IM2COL_TMA = 1, VCB_A_GATHER = 2, VCB_A_C4 = 3, VCB_A_ROWWIN = 4 };
 
 /* ---- library state ------------------------------------------------------------------------ */
-int vcb_init(int device);                 /* selects device, checks sm_100, resolves driver entry points */
+int vcb_init(int device);                 /* selects device, checks sm_100, resolves driver entry points.  One process per GPU:
+                                            * a second, different device in the same process is VCB_ERR_INVALID */
 const char* vcb_last_error_string(void);  /* thread-local, never NULL */
 int vcb_last_fault(int32_t out4[4]);      /* host: {code, block, info0, info1} of the last kernel fault */
 int vcb_version(void);
@@ -144,6 +145,11 @@ typedef struct VcbDetectDesc {
   float conf_thres;
   int32_t max_candidates;  /* capacity per frame of the candidate arrays */
   VcbDetectLevel level[4];
+  /* optional class filter (upstream non_max_suppression `classes=`, set by networks/yolo.py:64): a prediction whose BEST class is
+   * not in the mask is dropped before the max_nms / max_det cuts, as upstream does.  Bit c of class_mask[c / 32]; classes >= 256
+   * are never filtered.  use_class_mask = 0: keep every class. */
+  int32_t use_class_mask;
+  uint32_t class_mask[8];
 } VcbDetectDesc;
 
 /* cand_box: float [n][max_candidates][4] xyxy (inference-image pixels); cand_score: float; cand_cls: int32;

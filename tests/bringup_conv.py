@@ -120,6 +120,9 @@ case("fast-big-1x1-96", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, ac
 case("fast-big-1x1-96-tanh", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, act="silu_tanh")
 case("fast-big-3x3-192-res", mode="tma", n=64, h=40, w=40, k=3, p=1, cin=192, cout=192, act="silu", res="after")
 case("fast-big-stem", mode="tma", n=32, h=320, w=320, k=3, p=1, cin=16, cout=48, act="silu")
+case("noepi-big-stem", mode="tma", n=32, h=320, w=320, k=3, p=1, cin=16, cout=48, act="silu", epi_direct=3)
+case("noepi-big-1x1-96", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, act="silu", epi_direct=3)
+case("noepi-big-1x1-192", mode="tma", n=64, h=40, w=40, k=1, cin=192, cout=192, act="silu", epi_direct=3)
 case("fast-big-stem-tanh", mode="tma", n=32, h=320, w=320, k=3, p=1, cin=16, cout=48, act="silu_tanh")
 
 # row-window stem mode (VCB_A_ROWWIN): W-padded 16-channel input, one tiled TMA box per filter row

@@ -50,6 +50,7 @@ class DetectDesc(C.Structure):
         ("n", C.c_int32), ("nc", C.c_int32), ("num_levels", C.c_int32), ("logits_dtype", C.c_int32),
         ("conf_thres", C.c_float), ("max_candidates", C.c_int32),
         ("level", DetectLevel * 4),
+        ("use_class_mask", C.c_int32), ("class_mask", C.c_uint32 * 8),
     ]
 
 

@@ -73,6 +73,9 @@ const char* vcb_last_error_string(void) { return g_err; }
 int vcb_init(int device) {
   State& s = state();
   if (s.initialised && s.device == device) return VCB_OK;
+  // one process per GPU: function attributes (opt-in shared memory), the SM count and the fault record are per device, and
+  // the library keeps one copy of each -- a second device in the same process is refused instead of half-working
+  if (s.initialised) return set_error(VCB_ERR_INVALID, "libvcb200 is bound to device %d in this process (one process per GPU); cannot switch to device %d", s.device, device);
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return check_cuda(e, "cudaSetDevice");
   cudaDeviceProp prop;
@@ -101,6 +104,7 @@ int vcb_init(int device) {
   s.initialised = true;
   if (const char* e_pdl = getenv("VCB_PDL")) s.pdl = atoi(e_pdl) != 0 ? 1 : 0;
   if (const char* e_l2 = getenv("VCB_L2_HINT")) s.l2_hint = atoi(e_l2) != 0 ? 1 : 0;
+  if (const char* e_sp = getenv("VCB_EPI_SPLIT")) s.epi_split = atoi(e_sp) != 0 ? 1 : 0;
   return VCB_OK;
 }
 
@@ -108,6 +112,7 @@ int vcb_set_option(const char* name, int32_t value) {
   if (!name) return set_error(VCB_ERR_INVALID, "null option name");
   if (strcmp(name, "pdl") == 0) { state().pdl = value != 0 ? 1 : 0; return VCB_OK; }
   if (strcmp(name, "l2_hint") == 0) { state().l2_hint = value != 0 ? 1 : 0; return VCB_OK; }
+  if (strcmp(name, "epi_split") == 0) { state().epi_split = value != 0 ? 1 : 0; return VCB_OK; }
   if (strcmp(name, "prof") == 0) {
     State& s = state();
     if (value && s.prof_dev == nullptr) {
@@ -129,6 +134,7 @@ int vcb_read_prof(uint64_t out16[16]) {
 int vcb_get_option(const char* name) {
   if (name && strcmp(name, "pdl") == 0) return state().pdl;
   if (name && strcmp(name, "l2_hint") == 0) return state().l2_hint;
+  if (name && strcmp(name, "epi_split") == 0) return state().epi_split;
   return -1;
 }
 

@@ -93,6 +93,8 @@ struct ConvParams {
   int kchains;         // 1, 2 or 4 accumulators per tile: K steps are dealt round-robin to independent accumulation chains
                        // (dependent tcgen05.mma on ONE accumulator issue ~200 clk apart), the epilogue sums them
   int cout_pad;        // n_tiles * block_n = length of the packed bias
+  int epi_split;       // split epilogue (two independent four-warp groups, conv_epilogue_split)
+  int epi_empty_count; // arrivals that free an accumulator stage: epilogue threads that read each tile (x2 for CTA pairs)
   int a_rowwin;        // VCB_A_ROWWIN: one tiled 4-D TMA box per filter ROW over the W-padded input (patch_R x patch_Xs = 128 pixels)
   int ksteps_lim;      // K = 16 steps issued per 64-element chunk (3 in row-window mode: the 4th pixel has zero weights)
   int tile_rev;        // walk the tiles from the last to the first: a layer that starts where its producer stopped finds the
@@ -332,7 +334,9 @@ __device__ __forceinline__ float act_fast(float v) {
 // subnormal (|v * sigmoid(v)| < 1.1e-8), and so is the clamped one.
 template <int ACT>
 __device__ __forceinline__ void act_fast4(float& v0, float& v1, float& v2, float& v3) {
-#ifndef VCB_SILU_PLAIN      // -DVCB_SILU_PLAIN: one ex2 + one rcp per element (A/B builds, tools/ab_build.sh)
+#ifdef VCB_SILU_BATCH4     // A/B build only (tools/ab_build.sh batch4 -DVCB_SILU_BATCH4).  Measured on B200 (round 2, call 1): every 1x1 SiLU layer
+                           // got 8-12 % SLOWER (192->192 at M=102400: 28.7 -> 32.8 us) -- the epilogue is bound by its dependent-latency chain, not by
+                           // MUFU throughput, and the shared reciprocal lengthens that chain.  Default: one ex2 + one rcp per element.
   if (ACT == VCB_ACT_SILU) {
     float e0, e1, e2, e3, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(v0 * -1.4426950408889634f, 31.0f)));
@@ -588,6 +592,192 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Split epilogue (round 2).  ncu + role timers on the 1x1 / stem layers (profiles/r02_epilogue_analysis.md): these layers are
+// bound by the LATENCY of the epilogue's dependent chain per sub-tile (accumulator wait -> tcgen05.ld -> bias -> ex2 -> rcp ->
+// cvt -> st.shared -> fence -> CTA-wide barrier -> TMA store), not by MUFU or issue throughput: eight warps in lockstep leave
+// the SM with two such chains (two CTAs).  Here the eight warps are TWO independent groups of four (one TMEM lane quarter per
+// warp, 128 rows per group); a group takes every other work item -- whole tiles when the layer has one 64-column sub-tile
+// (each group then owns one accumulator stage), else every other (tile, sub-tile) -- and handles all 64 columns of it in two
+// halves.  Each group has its own staging buffer, 128-thread named barrier, store-issuing thread and residual barrier, so the
+// SM runs four epilogue chains out of phase and the per-item fixed costs are paid once per 64 columns instead of once per 32.
+// The buffer-free handshake (previous store has read the staging buffer) sits after the first half's arithmetic, where it is
+// normally already satisfied.  Requires two staging buffers, one K chain and, in whole-tile mode, two accumulator stages.
+// ---------------------------------------------------------------------------------------------------------------
+template <int ACT, int RES, bool F32OUT, bool TWO_CTA>
+__device__ __forceinline__ void conv_epilogue_split(const ConvParams& p, const CUtensorMap* tmap_out_ptr, const CUtensorMap* tmap_res_ptr,
+                                                    uint32_t tmem_base, uint32_t out_stage, uint32_t bias_smem, uint32_t res_bar0,
+                                                    uint32_t tmem_full0, uint32_t tmem_empty0, int first_tile, int tile_step, int cta_rank) {
+  const int total_tiles = TWO_CTA ? p.num_pair_tiles : p.num_tiles;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q = warp & 3;                      // TMEM lane quarter
+  const int grp = warp >> 2;                   // epilogue group 0 / 1
+  const int row_in_tile = q * 32 + lane;
+  constexpr int SUB_COLS = F32OUT ? 32 : 64;   // columns per staged sub-tile (128 bytes per row)
+  constexpr int HALF = SUB_COLS / 2;           // columns per half: 32 (fp16) or 16 (fp32)
+  constexpr int NG = HALF / 16;                // 16-column TMEM loads per half
+  const int num_sub = (p.block_n + SUB_COLS - 1) / SUB_COLS;
+  const bool issuer = (threadIdx.x & 127) == 0;
+  const uint32_t stage_buf = out_stage + (uint32_t)grp * kStageOutBytes;
+  const uint32_t res_bar = res_bar0 + 8u * (uint32_t)grp;
+  const uint32_t row_addr = stage_buf + (uint32_t)row_in_tile * 128u;
+  const int sw = row_in_tile & 7;
+  const uint32_t bar_id = 2u + (uint32_t)grp;
+  const bool two_acc = p.acc_stages == 2;
+  const int n_tiles = p.n_tiles;
+  const int per_img = p.patch_ytiles * p.patch_xsegs;      // row-window mode only
+
+  // (tile ordinal, sub-tile) of this group's current item; items alternate between the groups
+  int t_idx = (num_sub == 1) ? grp : 0;
+  int sub = (num_sub == 1) ? 0 : grp;
+  int waited = -1;                                          // tile ordinal whose accumulator this thread has waited for
+  uint32_t my_items = 0;
+
+  auto decode = [&](int tidx, int& m_tile, int& n_base) {
+    const int seq = first_tile + tidx * tile_step;
+    const int tile = p.tile_rev ? total_tiles - 1 - seq : seq;
+    const int pm = (n_tiles == 1) ? tile : tile / n_tiles;
+    n_base = (n_tiles == 1) ? 0 : (tile - pm * n_tiles) * p.block_n;
+    m_tile = TWO_CTA ? 2 * pm + cta_rank : pm;
+  };
+  auto issue_res_load = [&](int tidx, int sb) {
+    int mt, nb;
+    decode(tidx, mt, nb);
+    mbar_arrive_expect_tx(res_bar, (uint32_t)kStageOutBytes);
+    tma_load_2d(tmap_res_ptr, res_bar, stage_buf, nb + sb * SUB_COLS, mt * kBlockM);
+  };
+  if (RES != VCB_RES_NONE && issuer && first_tile + t_idx * tile_step < total_tiles) issue_res_load(t_idx, sub);
+
+  while (first_tile + t_idx * tile_step < total_tiles) {
+    int m_tile, n_base;
+    decode(t_idx, m_tile, n_base);
+    const uint32_t acc = two_acc ? ((uint32_t)t_idx & 1u) : 0u;
+    if (t_idx != waited) {
+      const uint32_t acc_ph = two_acc ? (((uint32_t)t_idx >> 1) & 1u) : ((uint32_t)t_idx & 1u);
+      mbar_wait(tmem_full0 + 8u * acc, acc_ph, p.fault, FAULT_TMEM_FULL_WAIT, (int)acc);
+      tcgen05_fence_after();
+      waited = t_idx;
+    }
+    const bool last_in_tile = sub + 2 >= num_sub;           // this group's last item of the tile
+    const uint32_t t_row = tmem_base + acc * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
+    const int col0 = sub * SUB_COLS;
+    const int ncols = min(SUB_COLS, p.block_n - col0);     // multiple of 16
+    if (RES != VCB_RES_NONE) mbar_wait(res_bar, my_items & 1u, p.fault, FAULT_FULL_WAIT, 400 + grp);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cb = col0 + h * HALF;                        // first column (within the N tile) of this half
+      int ng = (ncols - h * HALF) >> 4;                      // warp-uniform
+      ng = ng < 0 ? 0 : (ng > NG ? NG : ng);
+      uint32_t v[NG][16];
+      if (ng > 0) tmem_ld_x16(t_row + (uint32_t)cb, v[0]);
+      if (NG == 2 && ng > 1) tmem_ld_x16(t_row + (uint32_t)(cb + 16), v[NG - 1]);
+      uint4 rv[NG][2];
+      if (RES != VCB_RES_NONE) {                             // this thread's own chunks of the staged residual sub-tile
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t src = row_addr + (uint32_t)(((h * 4 + g * 2 + hh) ^ sw) << 4);
+            if (g < ng)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv[g][hh].x), "=r"(rv[g][hh].y), "=r"(rv[g][hh].z), "=r"(rv[g][hh].w) : "r"(src));
+            else
+              rv[g][hh] = make_uint4(0u, 0u, 0u, 0u);
+          }
+      }
+      if (ng > 0) tmem_ld_wait();
+      if (h == 1 && last_in_tile) {                          // this thread is done with the accumulator
+        tcgen05_fence_before();
+        if (TWO_CTA && cta_rank != 0) mbar_arrive_remote(tmem_empty0 + 8u * acc, 0);
+        else mbar_arrive(tmem_empty0 + 8u * acc);
+      }
+      uint32_t packed[NG][F32OUT ? 16 : 8];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        if (g >= ng) continue;
+        const uint32_t b_addr = bias_smem + (uint32_t)(n_base + cb + g * 16) * 4u;
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float b0, b1, b2, b3;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(b_addr + 16u * i));
+          f[4 * i + 0] = __uint_as_float(v[g][4 * i + 0]) + b0;
+          f[4 * i + 1] = __uint_as_float(v[g][4 * i + 1]) + b1;
+          f[4 * i + 2] = __uint_as_float(v[g][4 * i + 2]) + b2;
+          f[4 * i + 3] = __uint_as_float(v[g][4 * i + 3]) + b3;
+        }
+        if (RES != VCB_RES_NONE) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv[g][hh]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 t = __half22float2(rh[i]);
+              if (RES == VCB_RES_BEFORE_ACT) {
+                f[hh * 8 + 2 * i] = act_fast<ACT>(f[hh * 8 + 2 * i] + t.x);
+                f[hh * 8 + 2 * i + 1] = act_fast<ACT>(f[hh * 8 + 2 * i + 1] + t.y);
+              } else {
+                f[hh * 8 + 2 * i] = act_fast<ACT>(f[hh * 8 + 2 * i]) + t.x;
+                f[hh * 8 + 2 * i + 1] = act_fast<ACT>(f[hh * 8 + 2 * i + 1]) + t.y;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = act_fast<ACT>(f[i]);
+        }
+        if (F32OUT) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) packed[g][i] = __float_as_uint(f[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+            packed[g][i] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+        }
+      }
+      if (RES == VCB_RES_NONE && h == 0) {                   // the group's previous store must have read the staging buffer
+        if (issuer) tma_store_wait_read<0>();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      }
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        if (g >= ng) continue;
+        constexpr int CH = F32OUT ? 4 : 2;                   // 16-byte chunks per 16-column group
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const uint32_t dst = row_addr + (uint32_t)(((h * 4 + g * CH + i) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[g][4 * i]), "r"(packed[g][4 * i + 1]),
+                       "r"(packed[g][4 * i + 2]), "r"(packed[g][4 * i + 3]) : "memory");
+        }
+      }
+    }
+    fence_proxy_async_smem();                                // staged writes -> visible to the TMA (async proxy)
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    // next item of this group (two items ahead in the CTA's sequence)
+    int nt = t_idx, ns = sub + 2;
+    if (ns >= num_sub) { ns -= num_sub; ++nt; if (ns >= num_sub) { ns -= num_sub; ++nt; } }
+    if (issuer) {
+      if (p.a_rowwin) {
+        const int ni = m_tile / per_img, rem = m_tile - ni * per_img;
+        const int yt = rem / p.patch_xsegs, xs = rem - yt * p.patch_xsegs;
+        tma_store_4d(tmap_out_ptr, stage_buf, n_base + col0, xs * p.patch_Xs, yt * p.patch_R, ni);
+      } else {
+        tma_store_2d(tmap_out_ptr, stage_buf, n_base + col0, m_tile * kBlockM);
+      }
+      tma_store_commit();
+      if (RES != VCB_RES_NONE && first_tile + nt * tile_step < total_tiles) {
+        tma_store_wait_read<0>();                            // same buffer: the store just issued must have read it
+        issue_res_load(nt, ns);
+      }
+    }
+    t_idx = nt; sub = ns;
+    ++my_items;
+  }
+  if (issuer) tma_store_wait_all<0>();
+}
+
 // epilogue variants with a specialised instance; anything else runs the generic conv_epilogue
 __host__ __device__ constexpr int epi_kind_of(int act, int res, int f32) {
   return f32 ? ((act == VCB_ACT_NONE && res == VCB_RES_NONE) ? 7 : 0)
@@ -651,7 +841,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), kNumEpilogueThreads);
+      mbar_init(tmem_empty_bar(a), (uint32_t)p.epi_empty_count);
     }
     mbar_init(bres_bar, 1);
     if (A_MODE == A_TMA) { mbar_init(res_bar0, 1); mbar_init(res_bar0 + 8u, 1); }
@@ -814,8 +1004,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp < kEpilogueWarps) {
 #define VCB_EPI_CASE(K, ACT, RES, F32) \
-    case K: conv_epilogue_fast<ACT, RES, F32, M256>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), tmem_empty_bar(0)); break;
-    if (A_MODE == A_TMA && !M256 && p.a_rowwin) {   // 2-D pixel blocks: the patch-mode staging / 4-D store with a dense lattice (Lp = Xs)
+    case K: \
+      if (!M256 && p.epi_split) conv_epilogue_split<ACT, RES, F32, false>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), tmem_empty_bar(0), blockIdx.x, gridDim.x, 0); \
+      else conv_epilogue_fast<ACT, RES, F32, M256>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), tmem_empty_bar(0)); \
+      break;
+    if (A_MODE == A_TMA && !M256 && p.a_rowwin && !p.epi_split) {   // 2-D pixel blocks: the patch-mode staging / 4-D store with a dense lattice (Lp = Xs)
       if (p.epi_kind == 1)
         conv_epilogue_fast<VCB_ACT_SILU, VCB_RES_NONE, false, false, false, true>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), tmem_empty_bar(0));
       else
@@ -1000,7 +1193,7 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 2 * kNumEpilogueThreads);   // both CTAs' epilogues (leader's copy is the live one)
+      mbar_init(tmem_empty_bar(a), (uint32_t)p.epi_empty_count);   // both CTAs' epilogues (leader's copy is the live one)
     }
     mbar_init(res_bar0, 1);
     mbar_init(res_bar0 + 8u, 1);
@@ -1100,8 +1293,12 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
   } else if (warp < kEpilogueWarps) {
 #define VCB_EPI_CASE(K, ACT, RES, F32) \
-    case K: conv_epilogue_fast<ACT, RES, F32, false, true>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), \
-                                                           tmem_empty_bar(0), cluster_id, num_clusters, rank); break;
+    case K: \
+      if (p.epi_split) conv_epilogue_split<ACT, RES, F32, true>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), \
+                                                                tmem_empty_bar(0), cluster_id, num_clusters, rank); \
+      else conv_epilogue_fast<ACT, RES, F32, false, true>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), \
+                                                          tmem_empty_bar(0), cluster_id, num_clusters, rank); \
+      break;
     switch (p.epi_kind) {
       VCB_EPI_CASE(1, VCB_ACT_SILU, VCB_RES_NONE, false)
       VCB_EPI_CASE(2, VCB_ACT_SILU, VCB_RES_AFTER_ACT, false)
@@ -1754,6 +1951,13 @@ int conv2d_fwd(const VcbConvDesc& d_in, const void* x, const void* w_packed, con
   p.epi_kind = g.epi_kind;
   p.tile_rev = (launch_flags & 1) ? 1 : 0;
   p.ksteps_lim = 4;
+  {
+    const int sub_cols = d.out_dtype == VCB_F32 ? 32 : 64;
+    const int num_sub = (g.block_n + sub_cols - 1) / sub_cols;
+    p.epi_split = (state().epi_split && g.epi_kind != 0 && !g.patch && !g.m256 && g.out_bufs == 2 && g.kchains == 1 &&
+                   (num_sub >= 2 || g.acc_stages == 2)) ? 1 : 0;
+    p.epi_empty_count = (p.epi_split && num_sub == 1 ? kNumEpilogueThreads / 2 : kNumEpilogueThreads) * (g.two_cta ? 2 : 1);
+  }
   p.a_policy = state().l2_hint ? kL2EvictFirst : kL2EvictNormal;
   p.b_policy = state().l2_hint ? kL2EvictLast : kL2EvictNormal;
   p.kchains = g.kchains;

@@ -83,7 +83,8 @@ __global__ void detect_decode_kernel(const DecodeParams prm, float* __restrict__
         const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
         if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
       }
-      if (lane == 0 && best > d.conf_thres) {
+      const bool cls_ok = !d.use_class_mask || best_j >= 256 || ((d.class_mask[best_j >> 5] >> (best_j & 31)) & 1u);
+      if (lane == 0 && best > d.conf_thres && cls_ok) {
         const int gy = cl / L.nx, gx = cl - gy * L.nx;
         const float cx = (head[0] * 2.0f - 0.5f + (float)gx) * L.stride;
         const float cy = (head[1] * 2.0f - 0.5f + (float)gy) * L.stride;

@@ -28,6 +28,7 @@ struct State {
   KernelFault* fault_host = nullptr;   // pinned + mapped: still readable after a trapped kernel
   KernelFault* fault_dev = nullptr;
   int l2_hint = 0;                     // activation TMA loads evict-first, weight loads evict-last ($VCB_L2_HINT / vcb_set_option)
+  int epi_split = 1;                   // conv epilogue as two independent four-warp groups ($VCB_EPI_SPLIT / vcb_set_option)
   int prof_on = 0;                     // conv role timers (development aid)
   unsigned long long* prof_dev = nullptr;   // 16 counters in device memory
 };

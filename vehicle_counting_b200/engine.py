@@ -139,8 +139,9 @@ class _Plan:
 
     def conv(self, x: TRef, n: int, w: torch.Tensor, b: Optional[torch.Tensor], y: TRef, k: int, s: int, p: int, act: int,
              residual: Optional[TRef] = None, res_mode: int = L.RES_NONE, out_dtype: int = L.F16, a_mode: int = L.A_AUTO,
-             flops: Optional[float] = None):
-        """`flops`: algorithmic FLOPs of the layer when the launched geometry is a re-expression of it (stems)."""
+             flops: Optional[float] = None, wcache: Optional[dict] = None, wkey=None):
+        """`flops`: algorithmic FLOPs of the layer when the launched geometry is a re-expression of it (stems).
+        `wcache` / `wkey`: packed weights are a function of the layer, not of the batch: plans of different batch sizes share them."""
         cout, cin = int(w.shape[0]), int(w.shape[1])
         d = ops.make_conv_desc(n, x.h, x.w, cin, cout, k, s, p, cin_pitch=x.pitch, cout_pitch=y.pitch, act=act,
                                res_mode=res_mode if residual is not None else L.RES_NONE,
@@ -151,7 +152,12 @@ class _Plan:
         assert (ho, wo) == (y.h, y.w), ((ho, wo), (y.h, y.w))
         assert x.c == cin or (cin <= 4 and x.pitch == 4), (x.c, cin)
 
-        wp, bp = ops.pack_conv_weights(d, w, b)
+        if wcache is not None and wkey in wcache:
+            wp, bp = wcache[wkey]
+        else:
+            wp, bp = ops.pack_conv_weights(d, w, b)
+            if wcache is not None:
+                wcache[wkey] = (wp, bp)
         xp, yp, rp = x.ptr, y.ptr, (residual.ptr if residual is not None else 0)
         self.keep += [d, wp, bp, x.buf, y.buf] + ([residual.buf] if residual is not None else [])
         fl = 2.0 * n * ho * wo * cout * cin * k * k if flops is None else flops
@@ -165,7 +171,7 @@ class _Plan:
         for fn in self.steps:
             fn(st)
 
-    def capture(self) -> None:
+    def capture(self) -> "ops.Graph":
         torch.cuda.synchronize(self.device)
         ops.graph_begin(self.stream)
         try:
@@ -173,6 +179,7 @@ class _Plan:
                 fn(self.stream)
         finally:
             self.graph = ops.graph_end(self.stream)
+        return self.graph
 
     def run(self, use_graph: bool = True) -> None:
         """Enqueue one pass on the plan's stream."""
@@ -196,7 +203,7 @@ class YoloEngine:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, h: int, w: int, *, device="cuda:0", conf=0.25, iou=0.45,
                  max_det=300, max_wh=4096.0, max_nms=30000, model_name: Optional[str] = None, fp32_logits: bool = True,
-                 a_mode: int = L.A_AUTO):
+                 a_mode: int = L.A_AUTO, classes: Optional[Sequence[int]] = None):
         assert h % 32 == 0 and w % 32 == 0, "inference shape must be a multiple of the max stride (32)"
         self.device = torch.device(device)
         L.init(self.device.index or 0)
@@ -204,6 +211,7 @@ class YoloEngine:
         self.conf, self.iou, self.max_det, self.max_wh, self.max_nms = conf, iou, max_det, max_wh, max_nms
         self.name = model_name or infer_model_name(state_dict)
         self.fp32_logits = fp32_logits
+        self.classes = None if classes is None else sorted(int(c) for c in classes)     # upstream non_max_suppression(classes=...)
         self.a_mode = a_mode
         self.fuse_c3 = os.environ.get("VCB_C3_FUSE", "1") != "0"      # C3: cv1|cv2 as one GEMM, bottlenecks in place
         gd, gw = MODEL_SCALES[self.name]
@@ -391,6 +399,11 @@ class YoloEngine:
         dd.n, dd.nc, dd.num_levels = B, self.nc, len(feats)
         dd.logits_dtype = L.F32 if self.fp32_logits else L.F16
         dd.conf_thres = float(self.conf)
+        if self.classes is not None:        # dropped in the decode kernel, i.e. before the max_nms / max_det cuts (as upstream)
+            dd.use_class_mask = 1
+            for c in self.classes:
+                if 0 <= c < 256:
+                    dd.class_mask[c >> 5] |= (1 << (c & 31))
         P = 0
         for li, ft in enumerate(feats):
             lg = torch.zeros(B, ft.h, ft.w, pitch, dtype=ldt, device=dev)
@@ -517,7 +530,11 @@ class ReidEngine:
         self.capacity = capacity
         self.bn_mode = bn_mode
         self.a_mode = a_mode
-        self._plans: Dict[int, dict] = {}
+        self._plans: Dict[int, dict] = {}          # crop-count bucket -> {"plan", "graphs"}: nothing here depends on the caller's frames
+        self._wcache: dict = {}                    # packed (BN-folded) weights per layer, shared by every bucket
+        self._cur = [0, 0, 0]                      # frames pointer, height, width of the call in flight (read by the ROI launch)
+        self._frame_bufs: Dict[tuple, Tuple[torch.Tensor, torch.Tensor]] = {}     # (F, H, W) -> (pinned, device) staging, engine-owned
+        self.max_graphs = 4                        # CUDA graphs kept per bucket (one per distinct frames pointer / shape), LRU
         self.stream = torch.cuda.Stream(device=self.device)
         self.rois = torch.zeros(capacity, 5, dtype=torch.int32, device=self.device)
         self.rois_host = torch.zeros(capacity, 5, dtype=torch.int32).pin_memory()
@@ -535,12 +552,40 @@ class ReidEngine:
         sd = self.sd
         return (sd[p + ".weight"], sd[p + ".bias"], sd[p + ".running_mean"], sd[p + ".running_var"])
 
-    # -- eval-mode plan (graph captured per crop-count bucket) -----------------------------------
-    def _build_eval(self, nb: int, frames: torch.Tensor) -> dict:
+    # -- engine-owned frame staging -------------------------------------------------------------
+    def stage_frames(self, frames_np: np.ndarray) -> torch.Tensor:
+        """Host uint8 [F, H, W, 3] (or [H, W, 3]) -> device tensor in an engine-owned buffer keyed by shape (stable pointer, so
+        the CUDA graph captured for it is reused); the copy is enqueued on the engine's stream, in order with run()."""
+        if frames_np.ndim == 3:
+            frames_np = frames_np[None]
+        key = tuple(frames_np.shape[:3])
+        if key not in self._frame_bufs:
+            if len(self._frame_bufs) >= 4:                      # bounded: drop the oldest shape
+                self._frame_bufs.pop(next(iter(self._frame_bufs)))
+            self._frame_bufs[key] = (torch.empty(key + (3,), dtype=torch.uint8).pin_memory(),
+                                     torch.empty(key + (3,), dtype=torch.uint8, device=self.device))
+        pinned, dev = self._frame_bufs[key]
+        self.stream.synchronize()                               # the previous upload from this pinned buffer has been consumed
+        np.copyto(pinned.numpy(), frames_np)
+        with torch.cuda.stream(self.stream):
+            dev.copy_(pinned, non_blocking=True)
+        return dev
+
+    def atlas(self, nbytes: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(pinned, device) byte buffers of at least `nbytes`, engine-owned, growing geometrically (Extractor.__call__'s crop atlas)"""
+        cur = getattr(self, "_atlas", None)
+        if cur is None or cur[0].numel() < nbytes:
+            cap = 1 << max(20, int(nbytes - 1).bit_length())
+            self.stream.synchronize()
+            self._atlas = cur = (torch.empty(cap, dtype=torch.uint8).pin_memory(), torch.empty(cap, dtype=torch.uint8, device=self.device))
+        return cur
+
+    # -- eval-mode plan: one per crop-count bucket; the frames pointer / size are launch-time values ------------------
+    def _build_eval(self, nb: int) -> dict:
         dev, sd = self.device, self.sd
         plan = _Plan(dev)
         plan.stream = self.stream
-        fh, fw = frames.shape[1], frames.shape[2]
+        wc = self._wcache
 
         def buf(h, c, dtype=torch.float16):
             return torch.zeros(nb, h, h, c, dtype=dtype, device=dev)
@@ -549,50 +594,64 @@ class ReidEngine:
         rd.num_rois, rd.out_size, rd.out_channels = nb, REID_SIZE, 16
         for c in range(3):
             rd.mean[c] = REID_MEAN[c]; rd.inv_std[c] = 1.0 / REID_STD[c]
-        plan.keep += [rd, frames]
+        plan.keep += [rd]
+        cur_ = self._cur
         RELU = L.ACT_RELU
-        w_, b_ = _fold_plain(sd["conv.0.weight"], sd["conv.0.bias"], self._bn("conv.1"), REID_BN_EPS, dev)
+        if "stem" not in wc:
+            wc["stem"] = _fold_plain(sd["conv.0.weight"], sd["conv.0.bias"], self._bn("conv.1"), REID_BN_EPS, dev)
+        w_, b_ = wc["stem"]
         cur = TRef(buf(25, 64), 0, 64)
         stem_flops = 2.0 * nb * 2500 * 64 * 27
         if self.fused_stem:
             # crop -> im2col patches of the stem (K = 27 -> 32), then ONE kernel: tcgen05 GEMM + bias + ReLU + 3x3/s2 max-pool
             # (csrc/reid_stem.cu): the 50x50x64 stem map never reaches HBM
             patches = torch.zeros(nb, 25, 128, 32, dtype=torch.float16, device=dev)
-            wp, bp = ops.pack_reid_stem_weights(w_, b_)
-            plan.keep += [patches, wp, bp]
-            plan.add(lambda st: ops.roi_stem_patches(rd, frames, fh, fw, self.rois, patches, stream=st), "roi crop+resize+norm -> stem patches")
+            if "stem_packed" not in wc:
+                wc["stem_packed"] = ops.pack_reid_stem_weights(w_, b_)
+            wp, bp = wc["stem_packed"]
+            plan.keep += [patches]
+            plan.add(lambda st: ops.roi_stem_patches(rd, cur_[0], cur_[1], cur_[2], self.rois, patches, stream=st),
+                     "roi crop+resize+norm -> stem patches")
             plan.conv_flops += stem_flops
             plan.num_convs += 1
             plan.add(lambda st, cur=cur: ops.reid_stem_pool(patches, wp, bp, cur.buf, nb, stream=st),
                      f"stem conv3x3 3->64 + maxpool3x3s2 (fused) M={nb * 2500}", stem_flops)
         else:
             x0 = buf(REID_SIZE, 16)          # 3 real + 13 zero channels: one 32-byte TMA box per tap (bk = 16)
-            plan.add(lambda st: ops.roi_resize_norm(rd, frames, fh, fw, self.rois, x0, stream=st), "roi crop+resize+norm")
+            plan.add(lambda st: ops.roi_resize_norm(rd, cur_[0], cur_[1], cur_[2], self.rois, x0, stream=st), "roi crop+resize+norm")
             s0 = buf(50, 64)
-            plan.conv(TRef(x0, 0, 16), nb, _pad_cin(w_, 16), b_, TRef(s0, 0, 64), 3, 1, 1, RELU, a_mode=self.a_mode, flops=stem_flops)
+            plan.conv(TRef(x0, 0, 16), nb, _pad_cin(w_, 16), b_, TRef(s0, 0, 64), 3, 1, 1, RELU, a_mode=self.a_mode, flops=stem_flops,
+                      wcache=wc, wkey="stem16")
             plan.add(lambda st, s0=s0, cur=cur: ops.maxpool(s0, 64, cur.buf, 64, nb, 50, 50, 64, 3, 2, 1, stream=st), "maxpool3x3s2")
         size = 25
+
+        def folded(name, wname, bnname):
+            if name not in wc:
+                wc[name] = _fold_plain(sd[wname], None, self._bn(bnname), REID_BN_EPS, dev)
+            return wc[name]
+
         for prefix, ci, co, down in REID_BLOCKS:
             s = 2 if down else 1
             osz = (size + 2 - 3) // s + 1
-            w1, b1 = _fold_plain(sd[prefix + ".conv1.weight"], None, self._bn(prefix + ".bn1"), REID_BN_EPS, dev)
+            w1, b1 = folded(prefix + ".f1", prefix + ".conv1.weight", prefix + ".bn1")
             t = TRef(buf(osz, co), 0, co)
-            plan.conv(cur, nb, w1, b1, t, 3, s, 1, RELU, a_mode=self.a_mode)
+            plan.conv(cur, nb, w1, b1, t, 3, s, 1, RELU, a_mode=self.a_mode, wcache=wc, wkey=prefix + ".p1")
             if down:
-                wd, bd = _fold_plain(sd[prefix + ".downsample.0.weight"], None, self._bn(prefix + ".downsample.1"), REID_BN_EPS, dev)
+                wd, bd = folded(prefix + ".fd", prefix + ".downsample.0.weight", prefix + ".downsample.1")
                 sc = TRef(buf(osz, co), 0, co)
-                plan.conv(cur, nb, wd, bd, sc, 1, 2, 0, L.ACT_NONE, a_mode=self.a_mode)
+                plan.conv(cur, nb, wd, bd, sc, 1, 2, 0, L.ACT_NONE, a_mode=self.a_mode, wcache=wc, wkey=prefix + ".pd")
             else:
                 sc = cur
-            w2, b2 = _fold_plain(sd[prefix + ".conv2.weight"], None, self._bn(prefix + ".bn2"), REID_BN_EPS, dev)
+            w2, b2 = folded(prefix + ".f2", prefix + ".conv2.weight", prefix + ".bn2")
             y = TRef(buf(osz, co), 0, co)
-            plan.conv(t, nb, w2, b2, y, 3, 1, 1, RELU, residual=sc, res_mode=L.RES_BEFORE_ACT, a_mode=self.a_mode)
+            plan.conv(t, nb, w2, b2, y, 3, 1, 1, RELU, residual=sc, res_mode=L.RES_BEFORE_ACT, a_mode=self.a_mode, wcache=wc, wkey=prefix + ".p2")
             cur, size = y, osz
         assert size == 4
         feats = self.features
         plan.add(lambda st, cur=cur: ops.avgpool_l2norm(cur.buf, 512, nb, 16, 512, feats, stream=st), "avgpool+l2norm")
         self.conv_flops_per_crop = plan.conv_flops / nb
-        return {"plan": plan, "frames_ptr": frames.data_ptr(), "shape": tuple(frames.shape)}
+        from collections import OrderedDict
+        return {"plan": plan, "graphs": OrderedDict()}
 
     # -- train-mode (reference-faithful) pass, launched eagerly ----------------------------------
     def _run_train(self, frames: torch.Tensor, n: int, seg_sizes: Sequence[int]) -> None:
@@ -685,12 +744,27 @@ class ReidEngine:
             self._run_train(frames, n, list(seg_sizes) if seg_sizes is not None else [n])
             return self.features[:n]
         nb = self._bucket(n)
-        key = (nb, frames.data_ptr(), tuple(frames.shape))
-        ent = self._plans.get(key)
+        ent = self._plans.get(nb)
         if ent is None:
-            ent = self._build_eval(nb, frames)
-            self._plans[key] = ent
-        ent["plan"].run(use_graph)
+            ent = self._plans[nb] = self._build_eval(nb)
+        plan = ent["plan"]
+        self._cur[0], self._cur[1], self._cur[2] = frames.data_ptr(), int(frames.shape[1]), int(frames.shape[2])
+        if not use_graph:
+            plan.run_eager(self.stream)
+            return self.features[:n]
+        # graphs bake the frames pointer and size: one per (pointer, shape), least recently used dropped beyond max_graphs.
+        # Callers whose frames live in a fresh tensor every call (Extractor.__call__) pass use_graph=False instead.
+        gkey = (self._cur[0], self._cur[1], self._cur[2])
+        g = ent["graphs"].get(gkey)
+        if g is None:
+            g = plan.capture()
+            ent["graphs"][gkey] = g
+            while len(ent["graphs"]) > self.max_graphs:
+                ent["graphs"].popitem(last=False)
+        else:
+            ent["graphs"].move_to_end(gkey)
+            plan.graph = g
+        g.launch(self.stream)
         return self.features[:n]
 
     def download(self, n: int) -> np.ndarray:

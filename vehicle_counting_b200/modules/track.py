@@ -15,7 +15,6 @@ import numpy as np
 
 from ..counting import PALETTE, check_bbox_intersect_polygon, find_best_match_direction, load_zone_anno, save_tracking_to_csv
 from ..networks import DeepSort
-from ..networks.deepsort.deep_sort import _FRAMES
 
 __all__ = ["VideoTracker", "VideoCounting"]
 
@@ -36,7 +35,7 @@ class VideoTracker:
                         max_age=cam_cfg["MAX_AGE"], n_init=cam_cfg["N_INIT"], nn_budget=cam_cfg["NN_BUDGET"], use_cuda=1,
                         bn_mode=self.bn_mode)
 
-    def _features_all_classes(self, image, per_class):
+    def _features_all_classes(self, frame_dev, image, per_class):
         """one ReID pass for the whole frame; per_class: list of (class id, xyxy float64 [n,4]) -> {class id: float32 [n,512]}"""
         ds0 = self.deepsort[per_class[0][0]]
         eng = ds0.extractor.engine
@@ -53,9 +52,8 @@ class VideoTracker:
         n = len(rects)
         if n > eng.capacity:        # more detections than the shared engine was sized for: fall back to per-class calls
             return None
-        dev = _FRAMES.get(image, eng.stream)
         rois = np.concatenate([np.zeros((n, 1), np.int32), rects], 1)
-        eng.run(dev, rois, seg_sizes=seg)
+        eng.run(frame_dev, rois, seg_sizes=seg)
         feats = eng.download(n)
         out, off = {}, 0
         for (i, _), k in zip(per_class, seg):
@@ -77,10 +75,14 @@ class VideoTracker:
             mask = labels == i
             if mask.any():
                 per_class.append((i, bbox_xyxy[mask], scores[mask]))
-        feats = self._features_all_classes(image, [(i, b) for i, b, _ in per_class]) if per_class else {}
+        feats, frame_dev = {}, None
+        if per_class:
+            # the frame goes up ONCE per run() into the shared engine's staging buffer; every class tracker gets the device copy
+            frame_dev = self.deepsort[per_class[0][0]].extractor.engine.stage_frames(image)
+            feats = self._features_all_classes(frame_dev, image, [(i, b) for i, b, _ in per_class])
         for i, b, s in per_class:
             # output rows: x1, y1, x2, y2, track_id, -1, int(score)
-            outputs = self.deepsort[i].update(b, s, image, features=None if feats is None else feats[i])
+            outputs = self.deepsort[i].update(b, s, image, features=None if feats is None else feats[i], frame_dev=frame_dev)
             for obj in outputs:
                 result_dict["tracks"].append(obj[4])
                 result_dict["boxes"].append(obj[:4])
@@ -118,3 +120,4 @@ class VideoCounting:
                 rec["direction"] = find_best_match_direction(obj_vector=(first, last), paths=self.directions)
         if output_path is not None:
             save_tracking_to_csv(self.track_dict, output_path)
+        return self.track_dict                                  # track.py:137; CountingPipeline keeps it as `result_dict`

@@ -33,31 +33,6 @@ def _shared_engine(model_path: str, bn_mode: str, capacity: int = 512) -> ReidEn
     return _ENGINES[key]
 
 
-class _FrameCache:
-    """Device copy of the most recent frame: DeepSort.update is called once per class with the same image."""
-
-    def __init__(self):
-        self.key = None
-        self.dev: Optional[torch.Tensor] = None
-        self.pinned: Optional[torch.Tensor] = None
-
-    def get(self, img: np.ndarray, stream) -> torch.Tensor:
-        flat = img.reshape(-1)
-        key = (img.__array_interface__["data"][0], img.shape, bytes(flat[:: max(flat.size // 257, 1)][:257]))
-        if key != self.key:
-            if self.pinned is None or tuple(self.pinned.shape[1:]) != img.shape:
-                self.pinned = torch.empty((1,) + img.shape, dtype=torch.uint8).pin_memory()
-                self.dev = torch.empty((1,) + img.shape, dtype=torch.uint8, device="cuda")
-            self.pinned.numpy()[0] = img
-            with torch.cuda.stream(stream):
-                self.dev.copy_(self.pinned, non_blocking=True)
-            self.key = key
-        return self.dev
-
-
-_FRAMES = _FrameCache()
-
-
 class Extractor:
     """feature_extractor.py:9-47: `Extractor(model_path, use_cuda)(im_crops) -> float32 [n, 512]`."""
 
@@ -72,25 +47,34 @@ class Extractor:
         n = len(im_crops)
         if n == 0:
             return np.zeros((0, 512), np.float32)
-        hm = max(c.shape[0] for c in im_crops)
+        # the crops are stacked into ONE atlas "frame" (rows of crop i at [y_i, y_i + h_i), columns [0, w_i)) inside an engine-owned
+        # staging buffer that only ever grows; its height / width change from call to call, so this path launches eagerly instead
+        # of replaying a graph (nothing is captured, packed or allocated per call)
         wm = max(c.shape[1] for c in im_crops)
-        atlas = torch.zeros(n, hm, wm, 3, dtype=torch.uint8).pin_memory()
-        av = atlas.numpy()
         rois = np.zeros((n, 5), np.int32)
+        y = 0
         for i, c in enumerate(im_crops):
             if c.shape[0] == 0 or c.shape[1] == 0:
                 raise ValueError("empty crop (the reference fails inside cv2.resize here)")
-            av[i, :c.shape[0], :c.shape[1]] = c
-            rois[i] = (i, 0, 0, c.shape[1], c.shape[0])
-        with torch.cuda.stream(self.engine.stream):
-            dev = atlas.to("cuda", non_blocking=True)
-        self.engine.run(dev, rois, seg_sizes=[n])
-        return self.engine.download(n)
+            rois[i] = (0, 0, y, c.shape[1], y + c.shape[0])
+            y += c.shape[0]
+        eng = self.engine
+        host, dev = eng.atlas(y * wm * 3)
+        eng.stream.synchronize()                        # the previous upload out of the pinned atlas has been consumed
+        av = host[:y * wm * 3].numpy().reshape(y, wm, 3)
+        for i, c in enumerate(im_crops):
+            av[rois[i, 2]:rois[i, 4], :c.shape[1]] = c
+        with torch.cuda.stream(eng.stream):
+            dev[:y * wm * 3].copy_(host[:y * wm * 3], non_blocking=True)
+        eng.run(dev[:y * wm * 3].view(1, y, wm, 3), rois, seg_sizes=[n], use_graph=False)
+        return eng.download(n)
 
-    def from_frame(self, frame: np.ndarray, rois_xyxy: np.ndarray) -> np.ndarray:
-        """Same result as __call__ on `frame[y1:y2, x1:x2]` crops, without materialising them on the host."""
+    def from_frame(self, frame: np.ndarray, rois_xyxy: np.ndarray, frame_dev: Optional[torch.Tensor] = None) -> np.ndarray:
+        """Same result as __call__ on `frame[y1:y2, x1:x2]` crops, without materialising them on the host.  `frame_dev`: the frame
+        already on the device (VideoTracker uploads it once per frame and hands it to every class tracker); otherwise it is
+        uploaded here, every call -- there is no content-based guess about whether this is "the same" frame as last time."""
         n = len(rois_xyxy)
-        dev = _FRAMES.get(frame, self.engine.stream)
+        dev = frame_dev if frame_dev is not None else self.engine.stage_frames(frame)
         rois = np.concatenate([np.zeros((n, 1), np.int32), np.asarray(rois_xyxy, np.int32)], 1)
         self.engine.run(dev, rois, seg_sizes=[n])
         return self.engine.download(n)
@@ -126,22 +110,23 @@ class DeepSort:
         x, y, w, h = tlwh
         return max(int(x), 0), max(int(y), 0), min(int(x + w), self.width - 1), min(int(y + h), self.height - 1)
 
-    def _get_features(self, bbox_xywh: np.ndarray, ori_img: np.ndarray) -> np.ndarray:
+    def _get_features(self, bbox_xywh: np.ndarray, ori_img: np.ndarray, frame_dev: Optional[torch.Tensor] = None) -> np.ndarray:
         """deep_sort.py:119-129: crops come from the BGR original-resolution frame."""
         rects = np.array([self._crop_rect(b) for b in bbox_xywh], np.int32).reshape(-1, 4)
         if len(rects) == 0:
             return np.array([])
         if ((rects[:, 2] <= rects[:, 0]) | (rects[:, 3] <= rects[:, 1])).any():
             raise ValueError("empty crop (the reference fails inside cv2.resize here)")
-        return self.extractor.from_frame(ori_img, rects)
+        return self.extractor.from_frame(ori_img, rects, frame_dev)
 
-    def update(self, bbox_xyxy, confidences, ori_img, features: Optional[np.ndarray] = None):
-        """deep_sort.py:25-59.  `features` (optional, not in the reference) injects precomputed embeddings."""
+    def update(self, bbox_xyxy, confidences, ori_img, features: Optional[np.ndarray] = None, frame_dev: Optional[torch.Tensor] = None):
+        """deep_sort.py:25-59.  `features` (optional, not in the reference) injects precomputed embeddings; `frame_dev` (optional)
+        is `ori_img` already uploaded by the caller."""
         self.height, self.width = ori_img.shape[:2]
         bbox_xyxy = np.asarray(bbox_xyxy, dtype=np.float64)
         bbox_xywh = self._xyxy_to_xywh(bbox_xyxy)
         if features is None:
-            features = self._get_features(bbox_xywh, ori_img)
+            features = self._get_features(bbox_xywh, ori_img, frame_dev)
         tlwh = bbox_xywh.copy()
         tlwh[:, 0] = bbox_xywh[:, 0] - bbox_xywh[:, 2] / 2.0
         tlwh[:, 1] = bbox_xywh[:, 1] - bbox_xywh[:, 3] / 2.0

@@ -20,7 +20,7 @@ from torch import nn
 
 from .. import ops
 from ..engine import YoloEngine
-from ..weights import load_yolov5_state_dict, synth_yolov5_state_dict
+from ..weights import load_yolov5_checkpoint, synth_yolov5_state_dict
 
 COCO_NAMES = ['person', 'bicycle', 'car', 'motorcycle', 'airplane', 'bus', 'train', 'truck', 'boat', 'traffic light',
               'fire hydrant', 'stop sign', 'parking meter', 'bench', 'bird', 'cat', 'dog', 'horse', 'sheep', 'cow', 'elephant',
@@ -87,7 +87,9 @@ class YoloBackbone(BaseBackbone):
             if isinstance(weight, str) and weight.startswith("synthetic:"):
                 state_dict = synth_yolov5_state_dict(weight.split(":", 1)[1], seed=0)
             else:
-                state_dict = load_yolov5_state_dict(weight)
+                state_dict, names = load_yolov5_checkpoint(weight)      # custom models carry their own class names
+                if class_names is None:
+                    class_names = names
         self._sd = state_dict
         self.size = size                       # AutoShape's `size=` (the reference always uses the default 640)
         self.conf, self.iou, self.max_det = min_conf, min_iou, max_det
@@ -108,7 +110,8 @@ class YoloBackbone(BaseBackbone):
         key = (b, h, w)
         if key not in self._engines:
             dev = self._device or (f"cuda:{torch.cuda.current_device()}")
-            self._engines[key] = YoloEngine(self._sd, b, h, w, device=dev, conf=self.conf, iou=self.iou, max_det=self.max_det)
+            self._engines[key] = YoloEngine(self._sd, b, h, w, device=dev, conf=self.conf, iou=self.iou, max_det=self.max_det,
+                                            classes=self.classes)
             self._pinned[key] = torch.empty(b, h, w, 3, dtype=torch.uint8).pin_memory()
         return self._engines[key]
 
@@ -148,16 +151,8 @@ class YoloBackbone(BaseBackbone):
                 hv[i] = im if im.shape[:2] == (h1, w1) else _letterbox(im, (h1, w1))
             eng.upload(host)
         eng.forward()
-        det, cnt = eng.download()
-        if self.classes is not None:                            # optional class filter (yolo.py:64)
-            det, cnt = det.copy(), cnt.copy()
-            for b in range(len(imgs)):
-                rows = det[b, :cnt[b]]
-                keep = np.isin(rows[:, 5].astype(np.int64), np.asarray(self.classes, dtype=np.int64))
-                k = int(keep.sum())
-                det[b, :k] = rows[keep]
-                cnt[b] = k
-        return det, cnt
+        # the optional class filter (yolo.py:64) runs inside the decode kernel, before the max_nms / max_det cuts
+        return eng.download()
 
     def detect(self, batch, device=None):
         """networks/yolo.py:68-99"""

@@ -120,17 +120,37 @@ def synth_reid_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
     return sd
 
 
-def load_yolov5_state_dict(path: str) -> Dict[str, torch.Tensor]:
-    """A v6.0 state_dict file: a plain dict of tensors, or {'model': state_dict} / {'state_dict': ...}.
-    (Upstream .pt files pickle the upstream Model class and need the ultralytics/yolov5 sources to
-    unpickle; export `ckpt['model'].float().state_dict()` once where those sources are available.)"""
-    obj = torch.load(path, map_location="cpu", weights_only=True)
-    for key in ("model", "state_dict"):
+def load_yolov5_checkpoint(path: str):
+    """-> (state_dict, class names or None).
+
+    Accepted: a plain v6.0 state_dict file, or {'state_dict' | 'model': state_dict, 'names': [...]} as written by
+    tools/export_yolov5_state_dict.py.  The reference itself loads upstream `yolov5*.pt` files through
+    torch.hub (networks/yolo.py:58): those pickle the upstream `Model` CLASS under ckpt['model'] (fp16 weights, `.names`),
+    which can only be unpickled with the ultralytics/yolov5 sources on the path -- they are not available offline, so such a
+    file is rejected here with the one-line export recipe instead of an opaque UnpicklingError."""
+    try:
+        obj = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as e:     # pickle.UnpicklingError (unsupported global models.yolo.Model), or a zip/EOF error
+        raise ValueError(
+            f"{path}: cannot be read as a tensor-only checkpoint ({type(e).__name__}). Upstream yolov5*.pt files pickle the "
+            "ultralytics Model class; convert once where the yolov5 sources are importable:\n"
+            "    python tools/export_yolov5_state_dict.py yolov5s.pt yolov5s_sd.pt\n"
+            "and pass the result as --weight.") from e
+    names = None
+    if isinstance(obj, dict) and "names" in obj:
+        nm = obj["names"]
+        names = [nm[i] for i in sorted(nm)] if isinstance(nm, dict) else list(nm)
+    for key in ("state_dict", "model"):
         if isinstance(obj, dict) and key in obj and isinstance(obj[key], dict):
             obj = obj[key]
     if not (isinstance(obj, dict) and "model.0.conv.weight" in obj):
         raise ValueError(f"{path}: not a YOLOv5 v6.0 state_dict (expected key 'model.0.conv.weight')")
-    return {k: v.float() if v.is_floating_point() else v for k, v in obj.items()}
+    sd = {k: v.float() if v.is_floating_point() else v for k, v in obj.items() if torch.is_tensor(v)}
+    return sd, names
+
+
+def load_yolov5_state_dict(path: str) -> Dict[str, torch.Tensor]:
+    return load_yolov5_checkpoint(path)[0]
 
 
 def load_reid_state_dict(path: str) -> Dict[str, torch.Tensor]:
