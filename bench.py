@@ -4,11 +4,21 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (one JSON line on rank 0)
     python bench.py --impl reference --gpus N ...             # the CPU reference path (oracle port) on host cores
     torchrun --nnodes=1 --nproc-per-node N bench.py --gpus N  # one rank per GPU, frames sharded, weak scaling
+    python bench.py --config {1,2,4}                          # the other BASELINE.json configurations (records under profiles/)
 
-Workload (BASELINE.json: "end-to-end FPS (detect+ReID+NMS) 640x640", config "YOLOv5m 640x640 ... frames sharded
-over ranks"): per step and per GPU a batch of B synthetic random-uint8 640x640 frames goes through YOLOv5m
-(seeded synthetic weights) + decode + NMS, and 64 synthetic ROIs per frame (w,h~U(32,256))
-go through crop/resize/normalise + the ReID CNN (folded BatchNorm).  A "step" = one such batch.
+Default workload (BASELINE.json: "end-to-end FPS (detect+ReID+NMS) 640x640", configs[3] per-GPU shard): per step and per GPU a
+batch of B synthetic random-uint8 640x640 frames goes through YOLOv5m (seeded synthetic weights) + decode + NMS, and 64 synthetic
+ROIs per frame (w,h~U(32,256)) go through crop/resize/normalise + the ReID CNN with the reference's own
+BatchNorm behaviour (batch statistics per call -- its Extractor never calls .eval(); one 64-crop segment per frame).  A "step" =
+one such batch.  The JSON line carries, next to the contract keys:
+  value          whole-job frames/s, inputs resident in HBM (CUDA events on the plan stream, graph replay)
+  e2e            frames/s through the reference-shaped Python surface: ImageDetect.run(batch of numpy frames) -> dict of lists,
+                 then Extractor.from_frames(BGR numpy frames, float64 boxes) -> numpy embeddings; every H2D / D2H copy, the
+                 host-side gathering of the frame lists and the result conversion are inside the timed region
+  e2e_pipelined  the same work through the double-buffered FramePipeline (pinned tensors in / out; uploads overlap compute)
+  dropin_b1      the reference's own granularity: one frame per call (ImageDetect.run on a 1-frame batch, then one ReID call
+                 for that frame's boxes), i.e. what modules/__init__.py:54-70 drives
+  folded_bn      the device-resident number with BatchNorm folded (eval statistics) instead of the reference's batch statistics
 """
 from __future__ import annotations
 
@@ -20,6 +30,7 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -55,7 +66,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -91,50 +102,62 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def synth_rois(rng, frames: int, per_frame: int, size: int) -> np.ndarray:
-    """w,h ~ U(32,256), box inside the frame; reference crop rule applied (int truncation)."""
-    wh = rng.uniform(32, 256, (frames, per_frame, 2))
-    tl = rng.uniform(0, 1, (frames, per_frame, 2)) * (size - wh)
-    x1y1 = np.maximum(tl.astype(np.int64), 0)
-    x2y2 = np.minimum((tl + wh).astype(np.int64), size - 1)
-    f = np.repeat(np.arange(frames)[:, None, None], per_frame, 1)
-    return np.concatenate([f, x1y1, x2y2], 2).reshape(-1, 5).astype(np.int32)
+def synth_boxes(rng, frames: int, per_frame: int, h: int, w: int) -> np.ndarray:
+    """w,h ~ U(32,256), box inside the frame; float64 xyxy [frames, per_frame, 4]."""
+    wh = rng.uniform(32, min(256, h - 2, w - 2), (frames, per_frame, 2))
+    tl = rng.uniform(0, 1, (frames, per_frame, 2)) * (np.array([w, h]) - wh)
+    return np.concatenate([tl, tl + wh], 2)
+
+
+def boxes_to_rois(boxes: np.ndarray, h: int, w: int) -> np.ndarray:
+    """reference crop rule (deep_sort.py:78-95): centre/size in float64, int() truncation, clip -> int32 [n, 5] (frame, x1, y1, x2, y2)"""
+    F, P = boxes.shape[:2]
+    b = boxes.reshape(-1, 4)
+    bw, bh = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+    cx, cy = b[:, 0] + bw / 2, b[:, 1] + bh / 2
+    x1 = np.maximum(np.trunc(cx - bw / 2), 0); x2 = np.minimum(np.trunc(cx + bw / 2), w - 1)
+    y1 = np.maximum(np.trunc(cy - bh / 2), 0); y2 = np.minimum(np.trunc(cy + bh / 2), h - 1)
+    f = np.repeat(np.arange(F), P)
+    return np.stack([f, x1, y1, x2, y2], 1).astype(np.int32)
 
 
 # ---------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline leg (the only place outside tests/ that executes oracle/)
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_step(model_name: str, size: int, frames: int, rois_per_frame: int, state=None):
-    """One bounded sample of the workload on the host cores: the reference path restated (oracle YOLOv5 v6.0 +
-    the ReID restatement with the same weights layout, eval-mode BN like the GPU arm)."""
+def cpu_reference_step(model_name: str, h: int, w: int, frames: int, rois_per_frame: int, state=None, bn="train"):
+    """One bounded sample of the workload on the host cores: the reference path restated (oracle YOLOv5 v6.0 + the ReID
+    restatement with the same weights, BatchNorm in the reference's mode: batch statistics per frame's call)."""
     from oracle import reid as R
     from oracle import yolov5 as Y
     if state is None:
         torch.set_num_threads(os.cpu_count() or 1)
         rng = np.random.default_rng(0)
         ckpt = os.path.join(ROOT, "oracle", "_ref", "reid_ckpt.npz")
+        boxes = synth_boxes(rng, frames, rois_per_frame, h, w)
         state = {"model": Y.build(model_name, seed=0), "rng": rng,
                  "reid_sd": R.load_state_dict(ckpt) if os.path.isfile(ckpt) else R.seeded_state_dict(0),
-                 "imgs": [rng.integers(0, 256, (size, size, 3), dtype=np.uint8) for _ in range(frames)],
-                 "rois": synth_rois(rng, frames, rois_per_frame, size)}
+                 "imgs": [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(frames)],
+                 "rois": boxes_to_rois(boxes, h, w)}
     t0 = time.perf_counter()
-    Y.yolo_backbone_detect(state["model"], {"imgs": state["imgs"]}, size=size)
-    for f in range(frames):
-        bgr = state["imgs"][f][:, :, ::-1]
-        crops = [bgr[y1:y2, x1:x2] for (_, x1, y1, x2, y2) in state["rois"][f * rois_per_frame:(f + 1) * rois_per_frame]]
-        R.extract(state["reid_sd"], crops, "eval")
+    Y.yolo_backbone_detect(state["model"], {"imgs": state["imgs"]}, size=max(h, w))
+    if rois_per_frame > 0:
+        for f in range(frames):
+            bgr = state["imgs"][f][:, :, ::-1]
+            crops = [bgr[y1:y2, x1:x2] for (_, x1, y1, x2, y2) in state["rois"][f * rois_per_frame:(f + 1) * rois_per_frame]]
+            R.extract(state["reid_sd"], crops, bn)
     return time.perf_counter() - t0, state
 
 
 def run_reference_arm(a) -> dict:
     frames = a.ref_frames
-    dt, st = cpu_reference_step(a.model, a.size, frames, a.rois, None)      # warm-up (thread pools, allocations)
+    dt, st = cpu_reference_step(a.model, a.h, a.w, frames, a.rois, None, a.reid_bn)      # warm-up (thread pools, allocations)
     for _ in range(max(a.warmup - 1, 0)):
-        cpu_reference_step(a.model, a.size, frames, a.rois, st)
-    times = [cpu_reference_step(a.model, a.size, frames, a.rois, st)[0] for _ in range(a.steps)]
+        cpu_reference_step(a.model, a.h, a.w, frames, a.rois, st, a.reid_bn)
+    times = [cpu_reference_step(a.model, a.h, a.w, frames, a.rois, st, a.reid_bn)[0] for _ in range(a.steps)]
     ms = 1e3 * sum(times) / len(times)
     fps = frames / (ms / 1e3)
-    sample = f"{frames} frames x (YOLOv5 {a.model} {a.size}x{a.size} fp32 oracle + {a.rois} ReID crops) per step, torch CPU"
+    sample = (f"{frames} frames x (YOLOv5 {a.model} {a.h}x{a.w} fp32 oracle + {a.rois} ReID crops, BatchNorm {a.reid_bn}) per step, "
+              f"torch CPU")
     return {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a, frames),
@@ -143,19 +166,54 @@ def run_reference_arm(a) -> dict:
 
 
 def workload_config(a, batch):
-    return {"workload": f"{a.model} {a.size}x{a.size} detect+decode+NMS, {a.rois} ROI/frame crop+resize+ReID CNN (BASELINE configs[3] per-GPU shard)",
-            "frames_per_step_per_gpu": batch, "rois_per_frame": a.rois, "reid_bn": "folded (eval)", "conf": 0.25, "iou": 0.45,
-            "max_det": 300, "sharding": "frames round-robin over ranks; one NCCL all-gather of int64[3] counters at the end",
+    return {"workload": f"{a.model} {a.h}x{a.w} detect+decode+NMS" + (f", {a.rois} ROI/frame crop+resize+ReID CNN" if a.rois else " (detect only)")
+            + f" ({a.config_name})",
+            "frames_per_step_per_gpu": batch, "rois_per_frame": a.rois,
+            "reid_bn": "batch statistics per frame's call (reference: Extractor never calls .eval())" if a.reid_bn == "train" else "folded (eval)",
+            "conf": 0.25, "iou": 0.45, "max_det": 300,
+            "sharding": "frames round-robin over ranks; one NCCL all-gather of int64[3] counters at the end",
             "l2": "inputs rotate through a pool of distinct batches larger than L2; per-step activations (GBs) exceed L2"}
 
 
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def _event_time(stream, fn, steps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        fn(i)
+    e1.record(stream)
+    return e0, e1
+
+
+def per_launch_times(plans, reps=3):
+    """CUDA events around every launch of the given plans (same streams): (conv ms, other ms, yolo conv ms) summed per step"""
+    out = []
+    for plan in plans:
+        n = len(plan.steps)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n + 1)] for _ in range(reps)]
+        for r in range(reps):
+            ev[r][0].record(plan.stream)
+            for j, fn in enumerate(plan.steps):
+                fn(plan.stream)
+                ev[r][j + 1].record(plan.stream)
+        torch.cuda.synchronize()
+        per = np.array([[ev[r][j].elapsed_time(ev[r][j + 1]) for j in range(n)] for r in range(1, reps)]).mean(0)
+        conv = sum(per[j] for j in range(n) if plan.step_flops[j] > 0)
+        out.append((conv, per.sum() - conv))
+    return out
+
+
 def run_ours(a) -> dict:
     import torch.distributed as dist
     from vehicle_counting_b200 import _lib as L
     from vehicle_counting_b200.engine import ReidEngine, YoloEngine
+    from vehicle_counting_b200.modules import ImageDetect
+    from vehicle_counting_b200.networks import yolo as NY
+    from vehicle_counting_b200.networks.deepsort.deep_sort import Extractor
+    from vehicle_counting_b200.pipeline import FramePipeline
+    from vehicle_counting_b200.sharding import gather_counters, max_over_ranks
     from vehicle_counting_b200.weights import load_reid_state_dict, synth_reid_state_dict, synth_yolov5_state_dict
 
     rank = int(os.environ.get("RANK", "0"))
@@ -166,52 +224,41 @@ def run_ours(a) -> dict:
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     L.init(local)                      # raises if libvcb200.so is missing or the device is not sm_100
-    B, S, R_ = a.batch, a.size, a.rois
+    B, H, W, R_ = a.batch, a.h, a.w, a.rois
     rng = np.random.default_rng(1000 + rank)
+    with_reid = R_ > 0
 
     ysd = synth_yolov5_state_dict(a.model, seed=0, obj_bias=a.obj_bias)
     ckpt = os.path.join(ROOT, "oracle", "_ref", "reid_ckpt.npz")
+    reid_path = ckpt if os.path.isfile(ckpt) else "synthetic"
     rsd = load_reid_state_dict(ckpt) if os.path.isfile(ckpt) else synth_reid_state_dict(0)
-    yolo = YoloEngine(ysd, B, S, S, device=str(dev), model_name=a.model)
-    reid = ReidEngine(rsd, capacity=B * R_, device=str(dev), bn_mode="eval")
+    yolo = YoloEngine(ysd, B, H, W, device=str(dev), model_name=a.model)
+    ncrops = B * R_
+    reid = ReidEngine(rsd, capacity=max(ncrops, 8), device=str(dev), bn_mode=a.reid_bn, max_segments=max(B, 8)) if with_reid else None
 
-    # synthetic stream shard: a pool of distinct batches (device copies for `value`, pinned host copies for `e2e`)
-    pool_n = max(2, min(8, int(np.ceil(140e6 / (B * S * S * 3)))))
-    host_pool = [torch.from_numpy(rng.integers(0, 256, (B, S, S, 3), dtype=np.uint8)).pin_memory() for _ in range(pool_n)]
+    # synthetic stream shard: a pool of distinct batches (device copies for `value`, pinned host copies for the pipelined arm)
+    pool_n = max(2, min(8, int(np.ceil(140e6 / (B * H * W * 3)))))
+    host_pool = [torch.from_numpy(rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)).pin_memory() for _ in range(pool_n)]
     dev_pool = [h.to(dev) for h in host_pool]
-    rois_np = synth_rois(rng, B, R_, S)
-    ncrops = rois_np.shape[0]
+    boxes = synth_boxes(rng, B, max(R_, 1), H, W)                  # float64 xyxy, what the tracker stage receives
+    rois_np = boxes_to_rois(boxes, H, W) if with_reid else None
+    seg = [R_] * B                                                  # one reference call (BatchNorm segment) per frame
 
-    ys, rs = yolo.plan.stream, reid.stream
+    ys = yolo.plan.stream
+    rs = reid.stream if with_reid else None
 
     def step_device(i):
         """inputs already in HBM: D2D from the pool into the plan's static input, detect, then ReID on the same frames"""
         with torch.cuda.stream(ys):
             yolo.frames.copy_(dev_pool[i % pool_n], non_blocking=True)
         yolo.forward()
-        rs.wait_stream(ys)
-        reid.run(yolo.frames, None, n=ncrops)
-        ys.wait_stream(rs)
+        if with_reid:
+            rs.wait_stream(ys)
+            reid.run(yolo.frames, None, n=ncrops, seg_sizes=seg)
+            ys.wait_stream(rs)
 
-    from vehicle_counting_b200.pipeline import FramePipeline
-    pipe = FramePipeline(yolo, reid)
-
-    def run_e2e(nsteps):
-        """host buffers in, host results out: every step's frames + ROIs are uploaded from pinned memory and its detections +
-        embeddings are read back; uploads of step i+1 overlap the compute of step i (double buffering)"""
-        n_det = n_feat = 0
-        for i in range(nsteps):
-            pipe.submit(host_pool[i % pool_n], rois_np)
-            if pipe.submitted - pipe.collected == 2:
-                det, cnt, feats = pipe.collect()
-                n_det += int(cnt.sum()); n_feat += feats.shape[0]
-        while pipe.collected < pipe.submitted:
-            det, cnt, feats = pipe.collect()
-            n_det += int(cnt.sum()); n_feat += feats.shape[0]
-        return n_det, n_feat
-
-    # ROIs resident on the device for the HBM-resident arm
-    reid.run(yolo.frames, rois_np)
+    if with_reid:                       # ROIs (and segment tables) resident on the device for the HBM-resident arm
+        reid.run(yolo.frames, rois_np, seg_sizes=seg)
     torch.cuda.synchronize()
 
     def barrier():
@@ -219,19 +266,16 @@ def run_ours(a) -> dict:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- value: device-resident ---------------------------------------------------------------------------------
     for i in range(a.warmup):
         step_device(i)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     profile_region = os.environ.get("VCB_BENCH_PROFILE", "0") == "1"      # ncu --profile-from-start off: capture only the timed steps
     if profile_region:
         torch.cuda.profiler.start()
-    e0.record(ys)
-    for i in range(a.steps):
-        step_device(i)
-    e1.record(ys)
+    e0, e1 = _event_time(ys, step_device, a.steps)
     barrier()
     if profile_region:
         torch.cuda.profiler.stop()
@@ -239,55 +283,126 @@ def run_ours(a) -> dict:
     clocks = sampler.stop()
     det_total = int(yolo.det_count.sum().item())
 
-    # end-to-end through host buffers
-    run_e2e(max(a.warmup, 2))
+    # ---- folded-BN device-resident number (the designed fast path; not the reference's numerics) ------------------
+    folded = None
+    if with_reid and a.reid_bn == "train" and not a.quick:
+        reid_f = ReidEngine(rsd, capacity=max(ncrops, 8), device=str(dev), bn_mode="eval")
+        reid_f.run(yolo.frames, rois_np)
+
+        def step_folded(i):
+            with torch.cuda.stream(ys):
+                yolo.frames.copy_(dev_pool[i % pool_n], non_blocking=True)
+            yolo.forward()
+            reid_f.stream.wait_stream(ys)
+            reid_f.run(yolo.frames, None, n=ncrops)
+            ys.wait_stream(reid_f.stream)
+        for i in range(3):
+            step_folded(i)
+        barrier()
+        f0, f1 = _event_time(ys, step_folded, a.steps)
+        barrier()
+        folded = f0.elapsed_time(f1) / a.steps
+        folded_plan = next(iter(reid_f._plans.values()))["plan"]
+        folded_times = per_launch_times([folded_plan])[0]
+        del reid_f
+
+    # ---- e2e through the reference-shaped surface ----------------------------------------------------------------
+    # ImageDetect(args, config).run(batch) exactly as modules/__init__.py:57 calls it (lists of numpy frames in, dict of lists
+    # out), then the tracker stage's feature call for the same frames (BGR numpy frames + float64 boxes in, numpy embeddings out)
+    os.environ["VCB_REID_CAPACITY"] = str(max(ncrops, 512))
+    monkey = NY.synth_yolov5_state_dict
+    NY.synth_yolov5_state_dict = lambda name, seed=0: ysd              # same weights as the engine above (obj_bias included)
+    os.environ["VCB_SYNTH_WEIGHTS"] = "1"
+    cfg = types.SimpleNamespace(model_name=a.model, min_iou=0.45, min_conf=0.25, max_det=300)
+    det_stage = ImageDetect(types.SimpleNamespace(weight=None, mapping=None, mapping_dict=None), cfg)
+    det_stage.model.model.size = max(H, W)
+    NY.synth_yolov5_state_dict = monkey
+    extractor = Extractor(reid_path, use_cuda=True, bn_mode=a.reid_bn) if with_reid else None
+    np_pool = [[hp.numpy()[k] for k in range(B)] for hp in host_pool]     # lists of HWC uint8 frames (RGB for the detector)
+    np_pool_bgr = [[f[:, :, ::-1] for f in fr] for fr in np_pool] if a.bgr_views else np_pool
+    boxes_list = [boxes[k] for k in range(B)]
+
+    def step_plugin(i):
+        frames = np_pool[i % pool_n]
+        out = det_stage.run({"imgs": frames, "frames": list(range(B)), "ori_imgs": np_pool_bgr[i % pool_n]})
+        n_det = sum(len(s) for s in out["scores"])
+        n_feat = 0
+        if with_reid:
+            feats = extractor.from_frames(np_pool_bgr[i % pool_n], boxes_list)
+            n_feat = sum(f.shape[0] for f in feats)
+        return n_det, n_feat
+
+    for i in range(max(3, min(a.warmup, 4))):
+        step_plugin(i)
     barrier()
     t0 = time.perf_counter()
-    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ee0.record(pipe.copy_stream)
-    n_det, n_feat = run_e2e(a.steps)
-    ee1.record(ys)
+    n_det = n_feat = 0
+    for i in range(a.steps):
+        d_, f_ = step_plugin(i)
+        n_det += d_; n_feat += f_
+    torch.cuda.synchronize()
+    ms_e2e = 1e3 * (time.perf_counter() - t0) / a.steps
     barrier()
-    ms_e2e = max(ee0.elapsed_time(ee1), 1e3 * (time.perf_counter() - t0)) / a.steps
 
-    # per-kernel pass: CUDA events around every conv launch (same streams), for the roofline of the dominant kernel
-    conv_ms, other_ms = 0.0, 0.0
-    for plan in (yolo.plan, next(iter(reid._plans.values()))["plan"]):
-        n = len(plan.steps)
-        reps = 3
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n + 1)] for _ in range(reps)]
-        for r in range(reps):
-            ev[r][0].record(plan.stream)
-            for j, fn in enumerate(plan.steps):
-                fn(plan.stream)
-                ev[r][j + 1].record(plan.stream)
+    # ---- the reference's own granularity: one frame per call ------------------------------------------------------
+    b1 = None
+    if not a.quick and world == 1:
+        one = [np_pool[0][0]]
+        one_bgr = [np_pool_bgr[0][0]]
+        for _ in range(5):
+            det_stage.run({"imgs": one, "frames": [0], "ori_imgs": one_bgr})
+            if with_reid:
+                extractor.from_frames(one_bgr, boxes_list[:1])
         torch.cuda.synchronize()
-        per = np.array([[ev[r][j].elapsed_time(ev[r][j + 1]) for j in range(n)] for r in range(1, reps)]).mean(0)
-        for j in range(n):
-            if plan.step_flops[j] > 0:
-                conv_ms += per[j]
-            else:
-                other_ms += per[j]
-    reid_plan = next(iter(reid._plans.values()))["plan"]
-    conv_flops = yolo.plan.conv_flops + reid_plan.conv_flops
-    launches = yolo.plan.graph.num_kernels + reid_plan.graph.num_kernels
+        nfr = 64
+        t0 = time.perf_counter()
+        for k in range(nfr):
+            fr = [np_pool[k % pool_n][k % B]]
+            det_stage.run({"imgs": fr, "frames": [k], "ori_imgs": fr})
+            if with_reid:
+                extractor.from_frames(fr, boxes_list[k % B:k % B + 1])
+        torch.cuda.synchronize()
+        b1 = nfr / (time.perf_counter() - t0)
 
-    # max over ranks, counters all-gather (the only collective of the path)
-    from vehicle_counting_b200.sharding import gather_counters, max_over_ranks
+    # ---- pipelined host path (pinned tensors in / out, double buffered) -------------------------------------------
+    pipe = FramePipeline(yolo, reid)
+    ms_pipe = None
+    if True:
+        def run_pipe(nsteps):
+            for i in range(nsteps):
+                pipe.submit(host_pool[i % pool_n], rois_np, seg_sizes=seg if with_reid else None)
+                if pipe.submitted - pipe.collected == 2:
+                    pipe.collect()
+            while pipe.collected < pipe.submitted:
+                pipe.collect()
+        run_pipe(3)
+        barrier()
+        t0 = time.perf_counter()
+        run_pipe(a.steps)
+        torch.cuda.synchronize()
+        ms_pipe = 1e3 * (time.perf_counter() - t0) / a.steps
+        barrier()
+
+    # ---- per-kernel pass: CUDA events around every launch, for the roofline of the dominant kernel ----------------
+    plans = [yolo.plan] + ([next(iter(reid._plans.values()))["plan"]] if with_reid else [])
+    times = per_launch_times(plans)
+    conv_ms = sum(t[0] for t in times)
+    other_ms = sum(t[1] for t in times)
+    conv_flops = sum(p.conv_flops for p in plans)
+    launches = sum(p.graph.num_kernels for p in plans if p.graph is not None)
+
     ms_dev, ms_e2e = max_over_ranks([ms_dev, ms_e2e], device=dev)
     per_rank = gather_counters([a.steps * B, n_det, n_feat], device=dev)
     totals = [sum(c[i] for c in per_rank) for i in range(3)]
 
     peaks = _peaks()
-    # DRAM bytes of the conv launches of one step, from the committed ncu launch list of this very command at the default workload
-    # (profiles/r01_launch_summary.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the conv kernels of a step)
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_launch_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_launch_summary.json")) as f:
             ls = json.load(f)
-        if (a.model, a.size, B, R_) == ("yolov5m", 640, 64, 64):
+        if ls.get("workload") == [a.model, H, W, B, R_, a.reid_bn]:
             traffic = int(ls["conv_kernels"]["dram_bytes_per_step"])
-            traffic_src = "profiles/r01_launch_summary.json (ncu, batch 64)"
+            traffic_src = "profiles/r02_launch_summary.json (ncu launch list of this command)"
     except Exception:
         pass
     out = None
@@ -295,24 +410,50 @@ def run_ours(a) -> dict:
         fps = world * B / (ms_dev / 1e3)
         fps_e2e = world * B / (ms_e2e / 1e3)
         ach = conv_flops / (conv_ms / 1e3) / 1e12
+        yolo_tf = yolo.plan.conv_flops / (times[0][0] / 1e3) / 1e12
+        h2d = B * H * W * 3 * (2 if with_reid else 1)               # the detector's RGB batch and the tracker stage's BGR batch
+        d2h = yolo.det_host.numel() * 4 + yolo.det_count_host.numel() * 4 + ncrops * 512 * 4
         out = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
                "data": "synthetic", "config": workload_config(a, B), "clocks": clocks,
-               "e2e": {"value": fps_e2e, "unit": UNIT, "ms_per_step": ms_e2e,
-                       "h2d_bytes_per_step": int(B * S * S * 3 + rois_np.nbytes),
-                       "d2h_bytes_per_step": int(yolo.det_host.numel() * 4 + yolo.det_count_host.numel() * 4 + ncrops * 512 * 4)},
+               "e2e": {"value": fps_e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "path": "ImageDetect.run(batch of numpy frames) -> dict of lists; Extractor.from_frames(numpy BGR frames, float64 boxes) -> numpy embeddings"},
                "gpu_launches": int(launches * a.steps),
-               "roofline": {"kernel": "conv_umma_kernel (all conv launches of one step)", "bound": "tensor", "achieved": ach,
+               "roofline": {"kernel": "conv_umma / conv_umma_2cta / conv_patch (all conv launches of one step)", "bound": "tensor", "achieved": ach,
                             "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"],
-                            "frac_of_burst": ach / peaks["tflops_burst"], "peak_source": peaks["source"], "traffic": traffic, "traffic_source": traffic_src,
-                            "conv_gflop_per_step": conv_flops / 1e9, "conv_ms_per_step": conv_ms, "other_kernels_ms_per_step": other_ms,
+                            "frac_of_burst": ach / peaks["tflops_burst"], "peak_source": peaks["source"], "traffic": traffic,
+                            "traffic_source": traffic_src, "conv_gflop_per_step": conv_flops / 1e9, "conv_ms_per_step": conv_ms,
+                            "other_kernels_ms_per_step": other_ms,
+                            "yolo_frac": yolo_tf / peaks["tflops_sustained"], "yolo_tflops": yolo_tf, "yolo_conv_ms_per_step": times[0][0],
                             "whole_step_tensor_frac": conv_flops / (ms_dev / 1e3) / 1e12 / peaks["tflops_sustained"]},
                "counters": {"frames": totals[0], "detections": totals[1], "crops": totals[2], "detections_last_step_rank0": det_total},
                "kernels_per_step": int(launches)}
+        if with_reid:
+            out["roofline"]["reid_tflops"] = plans[1].conv_flops / (times[1][0] / 1e3) / 1e12
+            out["roofline"]["reid_ms_per_step"] = times[1][0] + times[1][1]
+        if ms_pipe is not None:
+            out["e2e_pipelined"] = {"value": world * B / (ms_pipe / 1e3), "unit": UNIT, "ms_per_step": ms_pipe,
+                                    "path": "FramePipeline.submit/collect (pinned tensors, uploads overlap compute)"}
+        if b1 is not None:
+            out["dropin_b1"] = {"value": b1, "unit": UNIT, "path": "one frame per call: ImageDetect.run([frame]) + one ReID call for its boxes"}
+        if folded is not None:
+            out["folded_bn"] = {"value": world * B / (folded / 1e3), "unit": UNIT, "ms_per_step": folded,
+                                "reid_ms_per_step": folded_times[0] + folded_times[1],
+                                "note": "BatchNorm folded with running statistics: faster, but not what the reference computes"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return out
+
+
+CONFIGS = {
+    # name: (config_name, model, h, w, batch, rois)
+    "default": ("BASELINE configs[3] per-GPU shard", "yolov5m", 640, 640, 64, 64),
+    "1": ("BASELINE configs[1]: detect only", "yolov5s", 640, 640, 32, 0),
+    "2": ("BASELINE configs[2]", "yolov5m", 1024, 1024, 32, 64),
+    "4": ("BASELINE configs[4] detector at the reference's inference shape (size=640)", "yolov5l", 384, 640, 64, 64),
+    "4b": ("BASELINE configs[4] detector at size=1280", "yolov5l", 736, 1280, 16, 64),
+}
 
 
 def main():
@@ -321,15 +462,26 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="yolov5m")
-    ap.add_argument("--size", type=int, default=640)
-    ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
-    ap.add_argument("--rois", type=int, default=64, help="ReID crops per frame")
+    ap.add_argument("--config", default="default", choices=sorted(CONFIGS), help="BASELINE.json configuration preset")
+    ap.add_argument("--model", default=None)
+    ap.add_argument("--size", type=int, default=None, help="square inference size (overrides the preset)")
+    ap.add_argument("--batch", type=int, default=None, help="frames per step per GPU")
+    ap.add_argument("--rois", type=int, default=None, help="ReID crops per frame (0 = detect only)")
+    ap.add_argument("--reid-bn", default="train", choices=["train", "eval"],
+                    help="train = the reference's BatchNorm (batch statistics per call); eval = folded running statistics")
     ap.add_argument("--obj-bias", type=float, default=-3.0, help="synthetic Detect objectness bias (controls #candidates)")
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the secondary measurements (folded BN, one-frame-per-call)")
+    ap.add_argument("--bgr-views", action="store_true", help="hand the tracker stage reversed-channel VIEWS of the frames (as cv2 would not)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    name, model, h, w, batch, rois = CONFIGS[a.config]
+    a.config_name = name
+    a.model = a.model or model
+    a.h, a.w = (a.size, a.size) if a.size else (h, w)
+    a.batch = a.batch or batch
+    a.rois = rois if a.rois is None else a.rois
     rank = int(os.environ.get("RANK", "0"))
 
     if a.impl == "reference":
@@ -354,11 +506,11 @@ def main():
     if rank == 0 and out is not None:
         if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not a.no_cpu_baseline:
             frames = 2
-            dt, st = cpu_reference_step(a.model, a.size, frames, a.rois, None)
-            dts = [cpu_reference_step(a.model, a.size, frames, a.rois, st)[0] for _ in range(3)]
+            dt, st = cpu_reference_step(a.model, a.h, a.w, frames, a.rois, None, a.reid_bn)
+            dts = [cpu_reference_step(a.model, a.h, a.w, frames, a.rois, st, a.reid_bn)[0] for _ in range(3)]
             v = frames / (sum(dts) / len(dts))
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                   "sample": f"3 x {frames} frames (YOLOv5 {a.model} {a.size}x{a.size} fp32 oracle + {a.rois} ReID crops/frame), torch CPU"}
+                                   "sample": f"3 x {frames} frames (YOLOv5 {a.model} {a.h}x{a.w} fp32 oracle + {a.rois} ReID crops/frame, BatchNorm {a.reid_bn}), torch CPU"}
         print(json.dumps(out), flush=True)
 
 

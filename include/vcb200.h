@@ -225,6 +225,20 @@ int vcb_bn_apply(const float* x, int32_t c, int32_t rows, const int32_t* row_seg
                  const float* shift, const void* residual, int32_t res_pitch, int32_t act, void* y,
                  int32_t y_pitch, vcb_stream_t stream);
 
+/* Train-mode BatchNorm over fp16 pre-BN tensors with DEVICE-resident segment tables (replayable inside a CUDA graph): crops are
+ * grouped in segments = one reference Extractor call each (all detections of one class in one frame, feature_extractor.py:42-47).
+ *   seg_of_crop: int32 [n], values in [0, num_seg]; num_seg marks padding crops (kept out of the real statistics)
+ *   seg_crops:   int32 [num_seg + 1], crops per segment
+ *   sums:        double [num_seg + 1][c][2] = per (segment, channel) sum and sum of squares; the caller zeroes it before
+ *                vcb_bn_seg_stats_f16, which accumulates into it (x: fp16 [n][hw][c], c = 8 * power of two <= 512)
+ * vcb_bn_seg_apply_f16: y = act(x * scale + shift (+ residual)), scale = gamma / sqrt(var + eps) (biased variance),
+ * shift = beta - mean * scale; act = VCB_ACT_NONE | VCB_ACT_RELU; pool != 0 additionally applies MaxPool2d(3, 2, padding=1)
+ * (model.py:57) to the activated h x w map, y then holds [n][ceil(h/2)][ceil(w/2)] pixels (no residual in that case). */
+int vcb_bn_seg_stats_f16(const void* x, int32_t c, int32_t hw, int32_t n, const int32_t* seg_of_crop, double* sums, vcb_stream_t stream);
+int vcb_bn_seg_apply_f16(const void* x, int32_t c, int32_t h, int32_t w, int32_t n, const int32_t* seg_of_crop, const int32_t* seg_crops,
+                         const double* sums, const float* gamma, const float* beta, float eps, const void* residual, int32_t res_pitch,
+                         int32_t act, int32_t pool, void* y, int32_t y_pitch, vcb_stream_t stream);
+
 /* ---- whole-path executor: the calls above, issued once on a capturing stream, become one CUDA
  *      graph that is replayed per batch (tensor maps and shapes are baked in as kernel parameters) --- */
 typedef struct VcbGraph VcbGraph;

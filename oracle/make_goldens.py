@@ -12,6 +12,7 @@ Outputs
   tests/golden/yolo_golden.npz     oracle (restatement) outputs on a seeded 2-frame 64x96 clip for
                                    yolov5n: raw heads + post-NMS rows (guards the oracle against drift;
                                    upstream itself is not importable -> "parity unpinned")
+  tests/golden/videotracker_golden.npz  rows of the REFERENCE's modules/track.py VideoTracker.run over a 10-frame sequence
   oracle/_ref/reid_ckpt.npz        fp32 repack of ckpt.t7's `net_dict` (derived artefact, git-ignored,
                                    travels to the GPU box with the working tree)
 """
@@ -105,6 +106,39 @@ def make_yolo():
     print("yolo golden dets:", [d.shape[0] for d in dets])
 
 
+def make_videotracker():
+    """The REFERENCE's own VideoTracker.run (modules/track.py:8-70: one DeepSort per class, per-class fan-out, Extractor in
+    train mode as shipped) on 10 frames: a textured 240x320 frame that scrolls 3 px per step with nine boxes of three classes
+    riding on it.  Rows: x1, y1, x2, y2, track_id, label."""
+    ref_shim.install()
+    from modules.track import VideoTracker  # type: ignore
+    rng = np.random.default_rng(21)
+    H, W, T = 240, 320, 10
+    base = rng.integers(0, 256, (H // 8, W // 8, 3)).astype(np.float32)
+    frame = np.clip(np.kron(base, np.ones((8, 8, 1), np.float32)) + rng.normal(0, 10, (H, W, 3)), 0, 255).astype(np.uint8)
+    cfg = {"MAX_DIST": 0.2, "MIN_CONFIDENCE": 0.25, "NMS_MAX_OVERLAP": 0.5, "MAX_IOU_DISTANCE": 0.6, "MAX_AGE": 30, "N_INIT": 3,
+           "NN_BUDGET": 60}                                   # configs/cam_configs.yaml: cam_04
+    nc = 3
+    vt = VideoTracker(nc, {"tracking_config": cfg}, {"num_frames": T}, ref_shim.REID_CKPT)
+    tl0 = np.array([[20, 30], [100, 20], [180, 40], [30, 130], [120, 120], [200, 140], [60, 70], [150, 80], [230, 30]], np.float64)
+    size = np.array([[50, 70], [40, 60], [60, 50], [70, 80], [45, 45], [55, 75], [35, 50], [65, 40], [50, 60]], np.float64)
+    labels = np.array([0, 0, 0, 0, 2, 2, 2, 1, 0])
+    scores = np.linspace(0.9, 0.4, 9)
+    boxes_log, rows, shifts = [], [], []
+    for t in range(T):
+        shift = 3 * t
+        fr = np.roll(frame, shift, axis=1)
+        boxes = np.concatenate([tl0 + np.array([shift, 0.5 * t]), size], 1)     # xywh top-left, as ImageDetect returns them
+        out = vt.run(fr, boxes.copy(), labels.copy(), scores.copy())
+        r = np.concatenate([np.asarray(out["boxes"], np.int64).reshape(-1, 4), np.asarray(out["tracks"], np.int64).reshape(-1, 1),
+                            np.asarray(out["labels"], np.int64).reshape(-1, 1)], 1)
+        rows.append(r); boxes_log.append(boxes); shifts.append(shift)
+    np.savez_compressed(os.path.join(GOLD, "videotracker_golden.npz"), frame=frame, shift=np.array(shifts), boxes=np.stack(boxes_log),
+                        labels=labels, scores=scores, num_classes=np.array(nc), row_counts=np.array([r.shape[0] for r in rows]),
+                        rows=np.concatenate(rows, 0), **{"cfg_" + k: np.array(v) for k, v in cfg.items()})
+    print("videotracker golden rows per frame:", [r.shape[0] for r in rows])
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     if not ref_shim.available():
@@ -112,6 +146,7 @@ def main():
     make_reid()
     make_deepsort()
     make_yolo()
+    make_videotracker()
 
 
 if __name__ == "__main__":

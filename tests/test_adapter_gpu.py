@@ -24,7 +24,7 @@ def test_image_detect_chain_contract_and_oracle_agreement(lib, monkeypatch):
     imgs = list(z["imgs"])                                           # 2 RGB uint8 frames of the CPU golden set
     model = Y.build("yolov5n", seed=0, obj_bias=-1.0)
     # the wrapper builds its network through get_model(args, config): hand it the oracle's seeded weights
-    monkeypatch.setattr(NY, "load_yolov5_state_dict", lambda path: model.state_dict())
+    monkeypatch.setattr(NY, "load_yolov5_checkpoint", lambda path: (model.state_dict(), None))
     args = types.SimpleNamespace(weight="seeded-yolov5n.pt", mapping=None, mapping_dict=None)
     det = ImageDetect(args, _cfg())
     det.model.model.size = max(imgs[0].shape[:2])                    # AutoShape size= (the goldens were made at the frame size)
@@ -61,13 +61,13 @@ def test_image_detect_empty_frames_and_class_mapping(lib, monkeypatch):
     z = np.load(os.path.join(GOLD, "yolo_golden.npz"))
     imgs = list(z["imgs"])
     quiet = Y.build("yolov5n", seed=0, obj_bias=-30.0)               # nothing passes the confidence threshold
-    monkeypatch.setattr(NY, "load_yolov5_state_dict", lambda path: quiet.state_dict())
+    monkeypatch.setattr(NY, "load_yolov5_checkpoint", lambda path: (quiet.state_dict(), None))
     det = ImageDetect(types.SimpleNamespace(weight="w.pt", mapping=None, mapping_dict=None), _cfg())
     out = det.run({"imgs": imgs})
     for b in range(len(imgs)):                                       # networks/yolo.py:92-97: three empty arrays
         assert out["boxes"][b].shape == (0,) and out["labels"][b].shape == (0,) and out["scores"][b].shape == (0,)
     loud = Y.build("yolov5n", seed=0, obj_bias=-1.0)
-    monkeypatch.setattr(NY, "load_yolov5_state_dict", lambda path: loud.state_dict())
+    monkeypatch.setattr(NY, "load_yolov5_checkpoint", lambda path: (loud.state_dict(), None))
     plain = ImageDetect(types.SimpleNamespace(weight="w2.pt", mapping=None, mapping_dict=None), _cfg()).run({"imgs": imgs})
     seen = sorted({int(c) for l in plain["labels"] for c in l})
     assert seen, "the seeded network must detect something on the golden frames"

@@ -104,6 +104,8 @@ _SIGNATURES = {
     "vcb_avgpool_l2norm": ([_VP, _I32, _I32, _I32, _I32, _VP, _VP], _I32),
     "vcb_bn_train_stats": ([_VP, _I32, _VP, _I32, _VP, _VP, _F, _VP, _VP, _VP], _I32),
     "vcb_bn_apply": ([_VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _I32, _VP], _I32),
+    "vcb_bn_seg_stats_f16": ([_VP, _I32, _I32, _I32, _VP, _VP, _VP], _I32),
+    "vcb_bn_seg_apply_f16": ([_VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _F, _VP, _I32, _I32, _I32, _VP, _I32, _VP], _I32),
     "vcb_graph_begin": ([_VP], _I32),
     "vcb_graph_end": ([_VP, C.POINTER(_VP)], _I32),
     "vcb_graph_launch": ([_VP, _VP], _I32),

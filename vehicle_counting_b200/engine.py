@@ -520,7 +520,7 @@ class ReidEngine:
     `Extractor.__call__` each (all detections of one class in one frame)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], capacity: int = 64, *, device="cuda:0", bn_mode: str = "eval",
-                 a_mode: int = L.A_AUTO):
+                 a_mode: int = L.A_AUTO, max_segments: int = 128):
         assert bn_mode in ("eval", "train")
         # folded-BN path: fused crop -> stem conv -> ReLU -> max-pool ($VCB_REID_FUSED_STEM=0 keeps the three separate kernels)
         self.fused_stem = os.environ.get("VCB_REID_FUSED_STEM", "1") != "0"
@@ -540,6 +540,13 @@ class ReidEngine:
         self.rois_host = torch.zeros(capacity, 5, dtype=torch.int32).pin_memory()
         self.features = torch.zeros(capacity, 512, dtype=torch.float32, device=self.device)
         self.features_host = torch.zeros(capacity, 512, dtype=torch.float32).pin_memory()
+        # train-mode BatchNorm: segment tables (one segment = one reference Extractor call), filled per call
+        self.max_segments = max_segments
+        cap_b = self._bucket(capacity)
+        self.seg_of_crop = torch.zeros(cap_b, dtype=torch.int32, device=self.device)
+        self.seg_host = torch.zeros(cap_b, dtype=torch.int32).pin_memory()
+        self.seg_crops = torch.zeros(max_segments + 1, dtype=torch.int32, device=self.device)
+        self.seg_crops_host = torch.zeros(max_segments + 1, dtype=torch.int32).pin_memory()
         self.conv_flops_per_crop = 0.0
 
     def _bucket(self, n: int) -> int:
@@ -567,6 +574,22 @@ class ReidEngine:
         pinned, dev = self._frame_bufs[key]
         self.stream.synchronize()                               # the previous upload from this pinned buffer has been consumed
         np.copyto(pinned.numpy(), frames_np)
+        with torch.cuda.stream(self.stream):
+            dev.copy_(pinned, non_blocking=True)
+        return dev
+
+    def stage_frame_list(self, frames: Sequence[np.ndarray]) -> torch.Tensor:
+        """stage_frames for a list of equally sized HWC uint8 frames (gathered into the pinned buffer by a thread pool)"""
+        from .hostcopy import copy_frames
+        key = (len(frames),) + tuple(frames[0].shape[:2])
+        if key not in self._frame_bufs:
+            if len(self._frame_bufs) >= 4:
+                self._frame_bufs.pop(next(iter(self._frame_bufs)))
+            self._frame_bufs[key] = (torch.empty(key + (3,), dtype=torch.uint8).pin_memory(),
+                                     torch.empty(key + (3,), dtype=torch.uint8, device=self.device))
+        pinned, dev = self._frame_bufs[key]
+        self.stream.synchronize()
+        copy_frames(pinned.numpy(), frames)
         with torch.cuda.stream(self.stream):
             dev.copy_(pinned, non_blocking=True)
         return dev
@@ -653,76 +676,94 @@ class ReidEngine:
         from collections import OrderedDict
         return {"plan": plan, "graphs": OrderedDict()}
 
-    # -- train-mode (reference-faithful) pass, launched eagerly ----------------------------------
-    def _run_train(self, frames: torch.Tensor, n: int, seg_sizes: Sequence[int]) -> None:
-        dev, sd, st = self.device, self.sd, self.stream
-        fh, fw = frames.shape[1], frames.shape[2]
-        nseg = len(seg_sizes)
-        cache = self._plans.setdefault(("train", n), {})
-        if not cache:
-            cache["w"] = {}
+    # -- train-mode (reference-faithful) plan: conv -> segment statistics -> normalise, graph-captured per bucket ------------
+    def _build_train(self, nb: int) -> dict:
+        """BatchNorm with the statistics of each reference call (segment).  Every BN layer is three launches over static
+        buffers: the convolution writes the pre-BN tensor as fp16, vcb_bn_seg_stats_f16 accumulates per-(segment, channel)
+        sums, vcb_bn_seg_apply_f16 normalises (+ residual, ReLU; the stem's also max-pools).  The segment tables are device
+        buffers filled per call, so one CUDA graph per bucket serves every segmentation."""
+        dev, sd = self.device, self.sd
+        plan = _Plan(dev)
+        plan.stream = self.stream
+        wc = self._wcache
+        S = self.max_segments + 1
 
-            def pack(name, w, bias, d):
-                cache["w"][name] = ops.pack_conv_weights(d, w.to(device=dev, dtype=torch.float32),
-                                                         None if bias is None else bias.to(device=dev, dtype=torch.float32))
-        seg = np.asarray(seg_sizes, np.int64)
+        def buf(h, c):
+            return torch.zeros(nb, h, h, c, dtype=torch.float16, device=dev)
 
-        def seg_arrays(hw):
-            start = torch.from_numpy(np.concatenate([[0], np.cumsum(seg * hw)]).astype(np.int32)).to(dev)
-            row_seg = torch.from_numpy(np.repeat(np.arange(nseg, dtype=np.int32), seg * hw)).to(dev)
-            return start, row_seg
+        def f32(name):
+            key = "t:" + name
+            if key not in wc:
+                wc[key] = sd[name].to(device=dev, dtype=torch.float32).contiguous()
+            return wc[key]
 
-        def conv_raw(x: TRef, wname, bias_name, co, k, s, p, a_mode):
-            w = sd[wname]
+        rd = L.RoiDesc()
+        rd.num_rois, rd.out_size, rd.out_channels = nb, REID_SIZE, 16
+        for c in range(3):
+            rd.mean[c] = REID_MEAN[c]; rd.inv_std[c] = 1.0 / REID_STD[c]
+        plan.keep += [rd]
+        cur_ = self._cur
+        n_bn = 1 + sum(3 if down else 2 for _, _, _, down in REID_BLOCKS)
+        sums = torch.zeros(n_bn, S, 512, 2, dtype=torch.float64, device=dev)
+        plan.keep += [sums]
+
+        def zero_sums(st):
+            with torch.cuda.stream(st):
+                sums.zero_()
+        plan.add(zero_sums, "zero BN sums")
+        x0 = buf(REID_SIZE, 16)
+        plan.add(lambda st: ops.roi_resize_norm(rd, cur_[0], cur_[1], cur_[2], self.rois, x0, stream=st), "roi crop+resize+norm")
+        bn_i = [0]
+
+        def conv_bn(x: TRef, wname, bias_name, bnp, co, k, s, p, act, residual: Optional[TRef], pool=False, flops=None) -> TRef:
+            w = sd[wname].to(device=dev, dtype=torch.float32)
             if w.shape[1] != x.c:
                 w = _pad_cin(w, x.c)
-            d = ops.make_conv_desc(n, x.h, x.w, int(w.shape[1]), co, k, s, p, cin_pitch=x.pitch, cout_pitch=co, act=L.ACT_NONE,
-                                   out_dtype=L.F32, a_mode=a_mode)
-            ho, wo = ops.conv_out_hw(d)
-            if wname not in cache["w"]:
-                cache["w"][wname] = ops.pack_conv_weights(d, w.to(device=dev, dtype=torch.float32),
-                                                          None if bias_name is None else sd[bias_name].to(device=dev, dtype=torch.float32),
-                                                          stream=st)
-            wp, bp = cache["w"][wname]
-            raw = torch.empty(n, ho, wo, co, dtype=torch.float32, device=dev)
-            ops.conv2d(d, x.ptr, wp, bp, raw, stream=st)
-            return raw, ho
+            b = None if bias_name is None else sd[bias_name].to(device=dev, dtype=torch.float32)
+            osz = (x.h + 2 * p - k) // s + 1
+            raw = TRef(buf(osz, co), 0, co)
+            plan.conv(x, nb, w, b, raw, k, s, p, L.ACT_NONE, a_mode=self.a_mode, wcache=wc, wkey="t:" + wname, flops=flops)
+            sl = sums[bn_i[0]]
+            bn_i[0] += 1
+            g, be = f32(bnp + ".weight"), f32(bnp + ".bias")
+            plan.add(lambda st, raw=raw, sl=sl: ops.bn_seg_stats_f16(raw.buf, co, osz * osz, nb, self.seg_of_crop, sl, stream=st), f"bn stats c={co}")
+            out_sz = (osz + 1) // 2 if pool else osz
+            y = TRef(buf(out_sz, co), 0, co)
+            plan.add(lambda st, raw=raw, sl=sl, y=y: ops.bn_seg_apply_f16(
+                raw.buf, co, osz, osz, nb, self.seg_of_crop, self.seg_crops, sl, g, be, REID_BN_EPS,
+                None if residual is None else residual.ptr, 0 if residual is None else residual.pitch, act, 1 if pool else 0, y.buf, co,
+                stream=st), f"bn apply c={co}" + (" +pool" if pool else ""))
+            return y
 
-        def bn_act(raw, osz, bnp, act, residual: Optional[TRef]):
-            co = raw.shape[-1]
-            rows = n * osz * osz
-            start, row_seg = seg_arrays(osz * osz)
-            scale = torch.empty(nseg, co, device=dev); shift = torch.empty(nseg, co, device=dev)
-            g = sd[bnp + ".weight"].to(device=dev, dtype=torch.float32); b = sd[bnp + ".bias"].to(device=dev, dtype=torch.float32)
-            ops.bn_train_stats(raw, co, start, nseg, g, b, REID_BN_EPS, scale, shift, stream=st)
-            y = torch.empty(n, osz, osz, co, dtype=torch.float16, device=dev)
-            ops.bn_apply(raw, co, rows, row_seg, scale, shift, None if residual is None else residual.ptr,
-                         0 if residual is None else residual.pitch, act, y, co, stream=st)
-            return TRef(y, 0, co)
+        cur = conv_bn(TRef(x0, 0, 16), "conv.0.weight", "conv.0.bias", "conv.1", 64, 3, 1, 1, L.ACT_RELU, None, pool=True,
+                      flops=2.0 * nb * 2500 * 64 * 27)
+        for prefix, ci, co, down in REID_BLOCKS:
+            s_ = 2 if down else 1
+            t = conv_bn(cur, prefix + ".conv1.weight", None, prefix + ".bn1", co, 3, s_, 1, L.ACT_RELU, None)
+            sc = conv_bn(cur, prefix + ".downsample.0.weight", None, prefix + ".downsample.1", co, 1, 2, 0, L.ACT_NONE, None) if down else cur
+            cur = conv_bn(t, prefix + ".conv2.weight", None, prefix + ".bn2", co, 3, 1, 1, L.ACT_RELU, sc)
+        assert cur.h == 4
+        feats = self.features
+        plan.add(lambda st, cur=cur: ops.avgpool_l2norm(cur.buf, 512, nb, 16, 512, feats, stream=st), "avgpool+l2norm")
+        self.conv_flops_per_crop = plan.conv_flops / nb
+        from collections import OrderedDict
+        return {"plan": plan, "graphs": OrderedDict()}
 
-        with torch.cuda.stream(st):
-            rd = L.RoiDesc()
-            rd.num_rois, rd.out_size, rd.out_channels = n, REID_SIZE, 16
-            for c in range(3):
-                rd.mean[c] = REID_MEAN[c]; rd.inv_std[c] = 1.0 / REID_STD[c]
-            x0 = torch.zeros(n, REID_SIZE, REID_SIZE, 16, dtype=torch.float16, device=dev)
-            ops.roi_resize_norm(rd, frames, fh, fw, self.rois, x0, stream=st)
-            raw, osz = conv_raw(TRef(x0, 0, 16), "conv.0.weight", "conv.0.bias", 64, 3, 1, 1, self.a_mode)
-            s0 = bn_act(raw, osz, "conv.1", L.ACT_RELU, None)
-            cur = TRef(torch.empty(n, 25, 25, 64, dtype=torch.float16, device=dev), 0, 64)
-            ops.maxpool(s0.buf, 64, cur.buf, 64, n, 50, 50, 64, 3, 2, 1, stream=st)
-            for prefix, ci, co, down in REID_BLOCKS:
-                s = 2 if down else 1
-                raw, osz = conv_raw(cur, prefix + ".conv1.weight", None, co, 3, s, 1, self.a_mode)
-                t = bn_act(raw, osz, prefix + ".bn1", L.ACT_RELU, None)
-                if down:
-                    rawd, _ = conv_raw(cur, prefix + ".downsample.0.weight", None, co, 1, 2, 0, self.a_mode)
-                    sc = bn_act(rawd, osz, prefix + ".downsample.1", L.ACT_NONE, None)
-                else:
-                    sc = cur
-                raw2, _ = conv_raw(t, prefix + ".conv2.weight", None, co, 3, 1, 1, self.a_mode)
-                cur = bn_act(raw2, osz, prefix + ".bn2", L.ACT_RELU, sc)
-            ops.avgpool_l2norm(cur.buf, 512, n, 16, 512, self.features, stream=st)
+    def _set_segments(self, n: int, nb: int, seg_sizes: Sequence[int]) -> None:
+        nseg = len(seg_sizes)
+        if nseg > self.max_segments:
+            raise ValueError(f"{nseg} BatchNorm segments in one call; this engine was built for at most {self.max_segments}")
+        assert sum(seg_sizes) == n, (seg_sizes, n)
+        soc = self.seg_host.numpy()
+        soc[:n] = np.repeat(np.arange(nseg, dtype=np.int32), np.asarray(seg_sizes, np.int64))
+        soc[n:nb] = nseg                                  # padding crops of the bucket: their own (ignored) segment
+        cnt = self.seg_crops_host.numpy()
+        cnt[:] = 0
+        cnt[:nseg] = np.asarray(seg_sizes, np.int32)
+        cnt[nseg] = nb - n
+        with torch.cuda.stream(self.stream):
+            self.seg_of_crop.copy_(self.seg_host, non_blocking=True)
+            self.seg_crops.copy_(self.seg_crops_host, non_blocking=True)
 
     # -- per-call API --------------------------------------------------------------------------
     def run(self, frames: torch.Tensor, rois, n: Optional[int] = None, seg_sizes: Optional[Sequence[int]] = None,
@@ -740,13 +781,16 @@ class ReidEngine:
         assert n is not None
         if n == 0:
             return self.features[:0]
-        if self.bn_mode == "train":
-            self._run_train(frames, n, list(seg_sizes) if seg_sizes is not None else [n])
-            return self.features[:n]
         nb = self._bucket(n)
+        if self.bn_mode == "train":
+            segs = tuple(int(k) for k in seg_sizes) if seg_sizes is not None else (n,)
+            if (n, nb, segs) != getattr(self, "_seg_key", None):      # same segmentation as the previous call: tables already on the device
+                self.stream.synchronize()      # the pinned segment tables of the previous call have been consumed
+                self._set_segments(n, nb, list(segs))
+                self._seg_key = (n, nb, segs)
         ent = self._plans.get(nb)
         if ent is None:
-            ent = self._plans[nb] = self._build_eval(nb)
+            ent = self._plans[nb] = self._build_train(nb) if self.bn_mode == "train" else self._build_eval(nb)
         plan = ent["plan"]
         self._cur[0], self._cur[1], self._cur[2] = frames.data_ptr(), int(frames.shape[1]), int(frames.shape[2])
         if not use_graph:

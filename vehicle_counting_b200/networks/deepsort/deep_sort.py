@@ -22,11 +22,13 @@ __all__ = ["DeepSort", "Extractor"]
 _ENGINES: Dict[Tuple[str, str, int], ReidEngine] = {}      # (weights path, bn_mode, device) -> shared engine
 
 
-def _shared_engine(model_path: str, bn_mode: str, capacity: int = 512) -> ReidEngine:
+def _shared_engine(model_path: str, bn_mode: str, capacity: Optional[int] = None) -> ReidEngine:
     """The reference builds one Extractor (one copy of the net) per class tracker (modules/track.py:16 ->
     80 copies for COCO); the weights are identical, so all instances share one engine."""
     dev = torch.cuda.current_device()
     key = (model_path, bn_mode, dev)
+    if capacity is None:
+        capacity = int(os.environ.get("VCB_REID_CAPACITY", "512"))       # crops per engine pass (batched callers raise it)
     if key not in _ENGINES:
         sd = synth_reid_state_dict(0) if model_path.startswith("synthetic") else load_reid_state_dict(model_path)
         _ENGINES[key] = ReidEngine(sd, capacity=capacity, device=f"cuda:{dev}", bn_mode=bn_mode)
@@ -78,6 +80,40 @@ class Extractor:
         rois = np.concatenate([np.zeros((n, 1), np.int32), np.asarray(rois_xyxy, np.int32)], 1)
         self.engine.run(dev, rois, seg_sizes=[n])
         return self.engine.download(n)
+
+
+    def from_frames(self, frames: Sequence[np.ndarray], boxes_xyxy: Sequence[np.ndarray]) -> List[np.ndarray]:
+        """Batched form of the per-frame call chain DeepSort.update -> _get_features -> Extractor (deep_sort.py:25-31, :119-129)
+        for a list of equally sized BGR frames: `boxes_xyxy[i]` are float64 xyxy boxes of frame i, the crop rectangles follow the
+        reference rule, all crops go through ONE engine pass (train-mode BatchNorm: one statistics segment per frame = one
+        reference call per frame) and the embeddings come back as one float32 [n_i, 512] array per frame."""
+        h, w = frames[0].shape[:2]
+        rois, seg = [], []
+        for i, b in enumerate(boxes_xyxy):
+            b = np.asarray(b, np.float64).reshape(-1, 4)
+            bw, bh = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+            cx, cy = b[:, 0] + bw / 2, b[:, 1] + bh / 2
+            # deep_sort.py:89-95: int() truncation (towards zero) of centre -/+ half size, clipped to the frame
+            x1 = np.maximum(np.trunc(cx - bw / 2).astype(np.int64), 0); x2 = np.minimum(np.trunc(cx + bw / 2).astype(np.int64), w - 1)
+            y1 = np.maximum(np.trunc(cy - bh / 2).astype(np.int64), 0); y2 = np.minimum(np.trunc(cy + bh / 2).astype(np.int64), h - 1)
+            if ((x2 <= x1) | (y2 <= y1)).any():
+                raise ValueError("empty crop (the reference fails inside cv2.resize here)")
+            rois.append(np.stack([np.full(len(b), i, np.int64), x1, y1, x2, y2], 1))
+            seg.append(len(b))
+        rois = np.concatenate(rois, 0).astype(np.int32)
+        n = len(rois)
+        eng = self.engine
+        if n > eng.capacity:
+            raise ValueError(f"{n} crops in one call; the shared ReID engine holds {eng.capacity}")
+        dev = eng.stage_frame_list(frames)
+        seg_nz = [k for k in seg if k > 0]
+        eng.run(dev, rois, seg_sizes=seg_nz)
+        feats = eng.download(n)
+        out, off = [], 0
+        for k in seg:
+            out.append(feats[off:off + k])
+            off += k
+        return out
 
 
 class DeepSort:

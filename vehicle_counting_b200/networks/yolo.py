@@ -20,6 +20,7 @@ from torch import nn
 
 from .. import ops
 from ..engine import YoloEngine
+from ..hostcopy import copy_frames
 from ..weights import load_yolov5_checkpoint, synth_yolov5_state_dict
 
 COCO_NAMES = ['person', 'bicycle', 'car', 'motorcycle', 'airplane', 'bus', 'train', 'truck', 'boat', 'traffic light',
@@ -136,9 +137,7 @@ class YoloBackbone(BaseBackbone):
                 self._pinned[key] = torch.empty(len(imgs), h0, w0, 3, dtype=torch.uint8).pin_memory()
                 self._raw_dev[key] = torch.empty(len(imgs), h0, w0, 3, dtype=torch.uint8, device=eng.frames.device)
             host, raw = self._pinned[key], self._raw_dev[key]
-            hv = host.numpy()
-            for i, im in enumerate(imgs):
-                hv[i] = im
+            copy_frames(host.numpy(), imgs)
             dh, dw = (h1 - h0 // 2) / 2, (w1 - w0 // 2) / 2
             top, left = int(round(dh - 0.1)), int(round(dw - 0.1))
             with torch.cuda.stream(eng.plan.stream):
@@ -146,9 +145,12 @@ class YoloBackbone(BaseBackbone):
             ops.letterbox_half(raw, len(imgs), h0, w0, eng.frames, h1, w1, top, left, 114, stream=eng.plan.stream)
         else:
             host = self._pinned[(len(imgs), h1, w1)]
-            hv = host.numpy()
-            for i, im in enumerate(imgs):
-                hv[i] = im if im.shape[:2] == (h1, w1) else _letterbox(im, (h1, w1))
+            if all(im.shape[:2] == (h1, w1) for im in imgs):
+                copy_frames(host.numpy(), imgs)
+            else:
+                hv = host.numpy()
+                for i, im in enumerate(imgs):
+                    hv[i] = im if im.shape[:2] == (h1, w1) else _letterbox(im, (h1, w1))
             eng.upload(host)
         eng.forward()
         # the optional class filter (yolo.py:64) runs inside the decode kernel, before the max_nms / max_det cuts

@@ -125,6 +125,16 @@ def bn_apply(x, c, rows, row_seg, scale, shift, residual, res_pitch, act, y, y_p
                                   L.ptr(residual), res_pitch, act, L.ptr(y), y_pitch, _st(stream)), "vcb_bn_apply")
 
 
+def bn_seg_stats_f16(x, c, hw, n, seg_of_crop, sums, stream=None) -> None:
+    L.check(L.load().vcb_bn_seg_stats_f16(L.ptr(x), c, hw, n, L.ptr(seg_of_crop), L.ptr(sums), _st(stream)), "vcb_bn_seg_stats_f16")
+
+
+def bn_seg_apply_f16(x, c, h, w, n, seg_of_crop, seg_crops, sums, gamma, beta, eps, residual, res_pitch, act, pool, y, y_pitch,
+                     stream=None) -> None:
+    L.check(L.load().vcb_bn_seg_apply_f16(L.ptr(x), c, h, w, n, L.ptr(seg_of_crop), L.ptr(seg_crops), L.ptr(sums), L.ptr(gamma), L.ptr(beta),
+                                          eps, L.ptr(residual), res_pitch, act, pool, L.ptr(y), y_pitch, _st(stream)), "vcb_bn_seg_apply_f16")
+
+
 # ------------------------------------------------------------------------------------------ detect / nms
 def detect_decode(desc: L.DetectDesc, cand_box, cand_score, cand_cls, cand_index, cand_count, stream=None) -> None:
     L.check(L.load().vcb_detect_decode(C.byref(desc), L.ptr(cand_box), L.ptr(cand_score), L.ptr(cand_cls), L.ptr(cand_index),

@@ -44,7 +44,7 @@ class FramePipeline:
         for e in self.stage_free:
             e.record(yolo.plan.stream)
 
-    def submit(self, frames_pinned: torch.Tensor, rois: Optional[np.ndarray] = None) -> None:
+    def submit(self, frames_pinned: torch.Tensor, rois: Optional[np.ndarray] = None, seg_sizes=None) -> None:
         assert self.submitted - self.collected < 2, "two batches are already in flight: call collect() first"
         k = self.submitted & 1
         ys = self.yolo.plan.stream
@@ -72,7 +72,7 @@ class FramePipeline:
             rs.wait_stream(ys)
             with torch.cuda.stream(rs):
                 self.reid.rois.copy_(self.rois_dev[k], non_blocking=True)
-            self.reid.run(self.yolo.frames, None, n=n)
+            self.reid.run(self.yolo.frames, None, n=n, seg_sizes=seg_sizes)
             with torch.cuda.stream(rs):
                 self.feat_host[k][:n].copy_(self.reid.features[:n], non_blocking=True)
             ys.wait_stream(rs)
