@@ -13,6 +13,8 @@ Outputs
                                    yolov5n: raw heads + post-NMS rows (guards the oracle against drift;
                                    upstream itself is not importable -> "parity unpinned")
   tests/golden/videotracker_golden.npz  rows of the REFERENCE's modules/track.py VideoTracker.run over a 10-frame sequence
+  tests/golden/pipeline_golden.{npz,csv}  the CSV written by the REFERENCE's unmodified CountingPipeline.run on a synthetic FFV1 clip
+                                   (detector = CPU oracle plugged in for networks.get_model) + the clip's base frame
   oracle/_ref/reid_ckpt.npz        fp32 repack of ckpt.t7's `net_dict` (derived artefact, git-ignored,
                                    travels to the GPU box with the working tree)
 """
@@ -139,6 +141,101 @@ def make_videotracker():
     print("videotracker golden rows per frame:", [r.shape[0] for r in rows])
 
 
+PIPE_CFG = dict(T=8, H=320, W=320, step=4, model="yolov5n", obj_bias=-6.0,
+                tracking={"MAX_DIST": 0.2, "MIN_CONFIDENCE": 0.25, "NMS_MAX_OVERLAP": 0.5, "MAX_IOU_DISTANCE": 0.6, "MAX_AGE": 30, "N_INIT": 3,
+                          "NN_BUDGET": 60})
+
+
+def drop_small_boxes(dets, min_side: float = 4.0):
+    """A seeded random network also emits sub-pixel boxes; their crops are empty and the reference's Extractor dies inside
+    cv2.resize (it has no guard).  Both sides of the pipeline golden drop boxes with a side under `min_side` pixels."""
+    out = []
+    for d in dets:
+        if d["bboxes"].size:
+            k = (d["bboxes"][:, 2] >= min_side) & (d["bboxes"][:, 3] >= min_side)
+            d = {"bboxes": d["bboxes"][k], "classes": d["classes"][k], "scores": d["scores"][k]}
+            if not k.any():
+                d = {"bboxes": np.array(()), "classes": np.array(()), "scores": np.array(())}
+        out.append(d)
+    return out
+
+
+def pipeline_clip_frames(base: np.ndarray, T: int, step: int):
+    """the synthetic clip: the textured base frame scrolling `step` pixels per frame (BGR, as cv2 stores them in the file)"""
+    return [np.roll(base, step * t, axis=1) for t in range(T)]
+
+
+def write_pipeline_inputs(dirname: str, base: np.ndarray, T: int, step: int):
+    """cam_04.avi (FourCC FFV1: lossless through cv2) + cam_04.json (a zone covering the frame, two directions)"""
+    import json
+    import cv2
+    os.makedirs(dirname, exist_ok=True)
+    h, w = base.shape[:2]
+    path = os.path.join(dirname, "cam_04.avi")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), 10, (w, h))
+    assert vw.isOpened()
+    for f in pipeline_clip_frames(base, T, step):
+        vw.write(f)
+    vw.release()
+    zone = {"shapes": [{"label": "zone", "points": [[2.5, 2.5], [w - 2.5, 2.5], [w - 2.5, h - 2.5], [2.5, h - 2.5]]},
+                       {"label": "direction01", "points": [[10.0, h / 2], [w - 10.0, h / 2]]},
+                       {"label": "direction02", "points": [[w - 10.0, h / 2], [10.0, h / 2]]}]}
+    with open(os.path.join(dirname, "cam_04.json"), "w") as fh:
+        json.dump(zone, fh)
+    return path
+
+
+def make_pipeline():
+    """J1: the UNMODIFIED reference driver modules/__init__.py:CountingPipeline.run -- its own VideoLoader (cv2 on a
+    FFV1 cam_04.avi), ImageDetect, Detector, VideoTracker (80 DeepSort instances, shipped ckpt.t7, BatchNorm as shipped),
+    VideoCounting and CSV writer -- with ONE substitution: `networks.get_model` returns the CPU oracle of the detector network
+    (upstream YOLOv5 cannot be fetched here), seeded weights.  The CSV it writes is the golden the GPU mirror is compared with."""
+    import tempfile
+    import types
+    import torch.nn as nn
+    ref_shim.install()
+    c = PIPE_CFG
+    rng = np.random.default_rng(33)
+    base_lo = rng.integers(0, 256, (c["H"] // 16, c["W"] // 16, 3)).astype(np.float32)
+    base = np.clip(np.kron(base_lo, np.ones((16, 16, 1), np.float32)) + rng.normal(0, 8, (c["H"], c["W"], 3)), 0, 255).astype(np.uint8)
+    tmp = tempfile.mkdtemp(prefix="vcb_pipeline_")
+    clip = write_pipeline_inputs(tmp, base, c["T"], c["step"])
+    model = yolov5.build(c["model"], seed=0, obj_bias=c["obj_bias"])
+
+    class OracleBackbone(nn.Module):             # the surface networks/yolo.py:YoloBackbone offers the stages
+        def __init__(self):
+            super().__init__()
+            self.net = model
+            self.class_names = [f"class{i}" for i in range(80)]
+
+        def detect(self, batch, device):
+            return drop_small_boxes(yolov5.yolo_backbone_detect(self.net, batch, size=640, conf=0.25, iou=0.45, max_det=300))
+
+    import networks  # type: ignore  (the reference's package)
+    import modules.detect as ref_detect  # type: ignore
+    ref_detect.get_model = lambda args, config: OracleBackbone()
+    from modules import CountingPipeline  # type: ignore
+    args = types.SimpleNamespace(weight="seeded", input_path=clip, output_path=os.path.join(tmp, "out"), mapping=None, mapping_dict=None)
+    config = types.SimpleNamespace(model_name=c["model"], min_iou=0.45, min_conf=0.25, max_det=300, image_size=[640, 640], keep_ratio=True)
+    cam_config = types.SimpleNamespace(zone_path=tmp, checkpoint=ref_shim.REID_CKPT, cam={"cam_04": {"tracking_config": c["tracking"]}})
+    pipe = CountingPipeline(args, config, cam_config)
+    try:
+        pipe.run()
+    except Exception as e:                       # the overlay video rendered AFTER the CSV needs drawing deps stubbed out here
+        print("[make_pipeline] note: post-CSV overlay step failed:", type(e).__name__, str(e)[:120])
+    csv_path = os.path.join(tmp, "out", "cam_04.csv")
+    assert os.path.isfile(csv_path), "the reference driver did not reach the CSV writer"
+    import pandas as pd
+    df = pd.read_csv(csv_path)
+    print("pipeline golden: rows", len(df), "tracks", df.track_id.nunique(), "labels", sorted(df.label.unique().tolist()))
+    with open(csv_path) as fh:
+        text = fh.read()
+    with open(os.path.join(GOLD, "pipeline_golden.csv"), "w") as fh:
+        fh.write(text)
+    np.savez_compressed(os.path.join(GOLD, "pipeline_golden.npz"), base=base, T=np.array(c["T"]), step=np.array(c["step"]),
+                        obj_bias=np.array(c["obj_bias"]), **{"cfg_" + k: np.array(v) for k, v in c["tracking"].items()})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     if not ref_shim.available():
@@ -147,6 +244,7 @@ def main():
     make_deepsort()
     make_yolo()
     make_videotracker()
+    make_pipeline()
 
 
 if __name__ == "__main__":

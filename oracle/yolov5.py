@@ -72,6 +72,21 @@ YAML_V6 = [
 ]
 
 
+# models/yolov5s.yaml of the v5.0 release (checkpoints <= v5.0): Focus stem, C3 x9 at P3, SPP before the last backbone C3
+YAML_V5 = [
+    (-1, 1, "Focus", (64, 3)),           # 0  P1/2
+    (-1, 1, "Conv", (128, 3, 2)),        # 1  P2/4
+    (-1, 3, "C3", (128,)),               # 2
+    (-1, 1, "Conv", (256, 3, 2)),        # 3  P3/8
+    (-1, 9, "C3", (256,)),               # 4
+    (-1, 1, "Conv", (512, 3, 2)),        # 5  P4/16
+    (-1, 9, "C3", (512,)),               # 6
+    (-1, 1, "Conv", (1024, 3, 2)),       # 7  P5/32
+    (-1, 1, "SPP", (1024, (5, 9, 13))),  # 8
+    (-1, 3, "C3", (1024, False)),        # 9
+] + YAML_V6[10:]
+
+
 def make_divisible(x: float, divisor: int) -> int:
     """utils/general.py make_divisible [upstream]: ceil to a multiple of divisor."""
     return int(math.ceil(x / divisor) * divisor)
@@ -194,18 +209,23 @@ class DetectionModel(nn.Module):
     """models/yolo.py Model + parse_model [upstream v6.0]; `self.model` keeps upstream's module
     numbering so `state_dict()` keys are `model.{i}.…` exactly like a v6.0 checkpoint."""
 
-    def __init__(self, name: str = "yolov5s", nc: int = 80, ch: int = 3):
+    def __init__(self, name: str = "yolov5s", nc: int = 80, ch: int = 3, version: str = "v6"):
         super().__init__()
         gd, gw = MODEL_SCALES[name]
+        self.version = version
         self.name, self.nc = name, nc
         layers, self.froms, outs = [], [], []
 
         def cin(f, i):
             return (ch if i == 0 else outs[i - 1]) if f == -1 else outs[f]
 
-        for i, (f, n, m, args) in enumerate(YAML_V6):
+        for i, (f, n, m, args) in enumerate(YAML_V6 if version == "v6" else YAML_V5):
             n = max(round(n * gd), 1) if n > 1 else n
-            if m in ("Conv", "C3", "SPPF"):
+            if m in ("Focus", "SPP"):
+                c1 = cin(f, i)
+                c2 = make_divisible(args[0] * gw, 8)
+                mod = Focus(c1, c2, args[1]) if m == "Focus" else SPP(c1, c2, args[1])
+            elif m in ("Conv", "C3", "SPPF"):
                 c1 = cin(f, i)
                 c2 = make_divisible(args[0] * gw, 8)
                 if m == "Conv":
@@ -296,8 +316,8 @@ def seeded_init_(model: DetectionModel, seed: int = 0, obj_bias: float = -4.0, c
     return model
 
 
-def build(name: str = "yolov5s", seed: int = 0, nc: int = 80, **kw) -> DetectionModel:
-    return seeded_init_(DetectionModel(name, nc), seed, **kw)
+def build(name: str = "yolov5s", seed: int = 0, nc: int = 80, version: str = "v6", **kw) -> DetectionModel:
+    return seeded_init_(DetectionModel(name, nc, version=version), seed, **kw)
 
 
 def fp16_storage_twin(model: DetectionModel) -> DetectionModel:

@@ -114,3 +114,27 @@ def test_crop_rule_matches_reference():
         b = np.array([[x1, y1, x1 + rng.uniform(1, 120), y1 + rng.uniform(1, 120)]])
         xywh = ds._xyxy_to_xywh(b)
         assert ds._xywh_to_xyxy(xywh[0]) == R.crop_box(b[0], 320, 240)
+
+
+def test_v5_blocks_equal_their_v6_expressions():
+    """Focus == 3x3 conv over the space-to-depth input in the ingest's channel order (engine.focus_weights_to_s2d); SPP(5, 9, 13)
+    == the SPPF cascade of 5x5 max-pools (what vcb_sppf_pool computes)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import yolov5 as Y
+    from vehicle_counting_b200.engine import focus_weights_to_s2d, infer_model_name, infer_version
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, 12, 16, generator=g)
+    w = torch.randn(8, 12, 3, 3, generator=g)
+    focus = F.conv2d(torch.cat((x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]), 1), w, None, 1, 1)
+    n, _, h, wd = x.shape
+    s2d = x.view(n, 3, h // 2, 2, wd // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(n, 12, h // 2, wd // 2)     # channel (dy*2+dx)*3+c
+    mine = F.conv2d(s2d, focus_weights_to_s2d(w)[:, :12], None, 1, 1)
+    assert torch.allclose(focus, mine, atol=1e-5)
+    y = torch.randn(2, 4, 13, 9, generator=g)
+    mp = lambda t, k: F.max_pool2d(t, k, 1, k // 2)
+    assert torch.equal(mp(y, 9), mp(mp(y, 5), 5)) and torch.equal(mp(y, 13), mp(mp(mp(y, 5), 5), 5))
+    m5 = Y.build("yolov5n", seed=0, version="v5")
+    sd = m5.state_dict()
+    assert infer_version(sd) == "v5" and infer_model_name(sd) == "yolov5n"
+    assert infer_version(Y.build("yolov5n", seed=0).state_dict()) == "v6"

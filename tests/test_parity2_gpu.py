@@ -64,23 +64,52 @@ def _backbone(model, **kw):
     return YoloBackbone(None, 0.45, 0.25, 300, state_dict=model.state_dict(), **kw)
 
 
+def _check_scale_coords_exact(net, imgs, size):
+    """The engine's rows must be oracle.scale_coords (upstream scale_coords + clip_coords: (x - pad) / gain, clamp to the ORIGINAL
+    frame) of the rows the oracle's greedy NMS keeps from the engine's own candidates -- identical inputs, so this isolates the
+    rescaling arithmetic with its real gain / pad values.  Returns the number of rows checked."""
+    from oracle import yolov5 as Y
+    eng = next(iter(net._engines.values()))
+    det = eng.det.cpu().numpy(); cnt = eng.det_count.cpu().numpy()
+    n_cand = eng.cand_count.cpu().numpy()
+    ci = eng.cand_index.cpu().numpy(); cs = eng.cand_score.cpu().numpy(); cb = eng.cand_box.cpu().numpy(); cc = eng.cand_cls.cpu().numpy()
+    rows = 0
+    for b, im in enumerate(imgs):
+        k = n_cand[b]
+        order = np.lexsort((ci[b, :k], -cs[b, :k]))
+        boxes = cb[b, :k][order] + (cc[b, :k][order].astype(np.float32) * np.float32(eng.max_wh))[:, None]
+        keep = Y.greedy_nms(boxes, np.arange(len(order), 0, -1, dtype=np.float32), eng.iou)[:eng.max_det]
+        sel = order[keep]
+        assert cnt[b] == len(sel), (b, cnt[b], len(sel))
+        want = Y.scale_coords((eng.h, eng.w), torch.from_numpy(cb[b, sel].copy()), im.shape[:2]).numpy()
+        np.testing.assert_allclose(det[b, :cnt[b], :4], want, rtol=0, atol=2e-3)        # fp32 (x - pad) / gain on both sides
+        np.testing.assert_array_equal(det[b, :cnt[b], 4], cs[b, sel])
+        h0, w0 = im.shape[:2]
+        d = det[b, :cnt[b]]
+        assert (d[:, [0, 2]] >= 0).all() and (d[:, [0, 2]] <= w0).all() and (d[:, [1, 3]] >= 0).all() and (d[:, [1, 3]] <= h0).all()
+        rows += int(cnt[b])
+    return rows
+
+
+# End-to-end row agreement with the oracle on these textured frames is a RATE: the seeded random network fires hundreds of heavily
+# overlapping boxes, so one IoU that lands on the other side of 0.45 re-routes a whole NMS cascade.  Yardstick measured on the CPU
+# (no CUDA involved): the oracle's own fp16-storage twin agrees with the fp32 oracle on 80-87 % of the rows by the same criterion.
+E2E_MIN_RATE = 0.7
+
+
 def test_scale_coords_1280x720_device_letterbox_vs_oracle(lib):
     """gain = 0.5, pad = (0, 12): boxes come back in 1280x720 pixels, clipped to the frame (upstream scale_coords / clip_coords)."""
     from oracle import yolov5 as Y
     torch.set_num_threads(max(os.cpu_count() or 1, 1))
     rng = np.random.default_rng(11)
     imgs = [_textured(rng, 720, 1280) for _ in range(2)]
-    model = Y.build("yolov5n", seed=0, obj_bias=-1.0)
+    model = Y.build("yolov5n", seed=0, obj_bias=-5.0)
     net = _backbone(model)
     got = net.detect({"imgs": imgs})
     assert (384, 640) in [(k[1], k[2]) for k in net._engines], "1280x720 must run at the reference's 384x640 inference shape"
+    assert _check_scale_coords_exact(net, imgs, 640) > 50
     want = Y.yolo_backbone_detect(Y.fp16_storage_twin(model), {"imgs": imgs}, size=640)
-    n_firm, n_hit, worst = _rows_agree(got, want)
-    assert worst < 2.0, worst                      # pixels of the 1280x720 frame (1 px of the inference frame)
-    for g in got:
-        if g["bboxes"].size:
-            b = g["bboxes"]
-            assert (b[:, 0] >= 0).all() and (b[:, 1] >= 0).all() and (b[:, 0] + b[:, 2] <= 1280 + 1e-6).all() and (b[:, 1] + b[:, 3] <= 720 + 1e-6).all()
+    _rows_agree(got, want, min_rate=E2E_MIN_RATE)
 
 
 def test_mixed_size_image_list_vs_oracle(lib):
@@ -90,16 +119,12 @@ def test_mixed_size_image_list_vs_oracle(lib):
     torch.set_num_threads(max(os.cpu_count() or 1, 1))
     rng = np.random.default_rng(12)
     imgs = [_textured(rng, 480, 640), _textured(rng, 360, 640), _textured(rng, 640, 400), _textured(rng, 200, 300)]
-    model = Y.build("yolov5n", seed=0, obj_bias=-1.0)
+    model = Y.build("yolov5n", seed=0, obj_bias=-5.0)
     net = _backbone(model, size=320)
     got = net.detect({"imgs": imgs})
+    assert _check_scale_coords_exact(net, imgs, 320) > 50
     want = Y.yolo_backbone_detect(Y.fp16_storage_twin(model), {"imgs": imgs}, size=320)
-    n_firm, n_hit, worst = _rows_agree(got, want)
-    assert worst < 3.0, worst                      # original pixels; gains down to 0.5
-    for g, im in zip(got, imgs):
-        if g["bboxes"].size:
-            b = g["bboxes"]
-            assert (b[:, 0] + b[:, 2] <= im.shape[1] + 1e-6).all() and (b[:, 1] + b[:, 3] <= im.shape[0] + 1e-6).all()
+    _rows_agree(got, want, min_rate=E2E_MIN_RATE)
 
 
 @pytest.mark.parametrize("hw", [(384, 640), (736, 1280)])
@@ -234,3 +259,28 @@ def test_video_tracker_rows_match_the_reference_golden(lib):
         np.testing.assert_array_equal(np.asarray(out["boxes"]).reshape(-1, 4), want[:, :4])
         total += k
     assert total > 0
+
+
+def test_v5_checkpoint_focus_spp_heads_vs_oracle(lib):
+    """north_star names the <= v5.0 building blocks (Focus stem, SPP): a v5.0-layout state_dict (model.0.conv.conv.*, SPP at
+    model.8, nine C3 repeats at P3) runs through the same kernels -- Focus == the space-to-depth stem with a channel permutation,
+    SPP(5, 9, 13) == the SPPF cascade -- and matches the oracle's v5.0 graph."""
+    from oracle import yolov5 as Y
+    from vehicle_counting_b200.engine import YoloEngine
+    torch.set_num_threads(max(os.cpu_count() or 1, 1))
+    model = Y.build("yolov5s", seed=0, obj_bias=-2.0, version="v5")
+    rng = np.random.default_rng(18)
+    imgs = [rng.integers(0, 256, (160, 224, 3), dtype=np.uint8) for _ in range(2)]
+    _, _, raw_ref = Y.autoshape_forward(model, imgs, size=224, return_raw=True)
+    dets_twin, _, raw_twin = Y.autoshape_forward(Y.fp16_storage_twin(model), imgs, size=224, return_raw=True)
+    eng = YoloEngine(model.state_dict(), 2, 160, 224)
+    assert eng.version == "v5" and eng.name == "yolov5s"
+    eng.upload(torch.from_numpy(np.stack(imgs)).pin_memory()); eng.forward()
+    det, cnt = eng.download()
+    for li in range(3):
+        got = eng.logits[li].float().cpu()[..., :3 * eng.no].permute(0, 3, 1, 2)
+        rel32 = ((got - raw_ref[li]).norm() / raw_ref[li].norm()).item()
+        rel16 = ((got - raw_twin[li]).norm() / raw_twin[li].norm()).item()
+        assert rel32 < 7e-3 and rel16 < 3e-3, (li, rel32, rel16)
+    n_ref = sum(d.shape[0] for d in dets_twin)
+    assert abs(int(cnt.sum()) - n_ref) <= max(3, n_ref // 10), (cnt.tolist(), n_ref)

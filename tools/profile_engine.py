@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--reid", type=int, default=0, help="crops for the ReID plan (0 = skip)")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--mode", default="auto", choices=["auto", "gather"])
+    ap.add_argument("--reid-bn", default="eval", choices=["eval", "train"])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "profile_engine.json"))
     a = ap.parse_args()
     from vehicle_counting_b200 import _lib as L
@@ -73,11 +74,13 @@ def main():
                    "labels": plan.labels, "step_flops": plan.step_flops}
     if a.reid:
         rsd = synth_reid_state_dict(0)
-        r = ReidEngine(rsd, capacity=a.reid, bn_mode="eval", a_mode=a_mode)
+        r = ReidEngine(rsd, capacity=a.reid, bn_mode=a.reid_bn, a_mode=a_mode, max_segments=max(a.reid // 64, 8))
+        seg = [64] * (a.reid // 64) if a.reid % 64 == 0 else [a.reid]
         rng = np.random.default_rng(0)
         wh = rng.uniform(32, 256, (a.reid, 2)); tl = rng.uniform(0, 1, (a.reid, 2)) * (a.size - wh)
         rois = np.concatenate([np.zeros((a.reid, 1)), tl, tl + wh], 1).astype(np.int32)
-        r.run(eng.frames, rois); torch.cuda.synchronize()
+        rois[:, 0] = np.arange(a.reid) % a.batch
+        r.run(eng.frames, rois, seg_sizes=seg); torch.cuda.synchronize()
         key = next(iter(r._plans)); rp = r._plans[key]["plan"]
         per_r = time_steps(rp, "reid")
         with torch.cuda.stream(r.stream):
@@ -88,7 +91,7 @@ def main():
         torch.cuda.synchronize()
         ms_r = e0.elapsed_time(e1) / 10
         print(f"reid n={a.reid}: eager sum {per_r.sum():.3f} ms, graph {ms_r:.3f} ms -> {rp.conv_flops / ms_r / 1e9:.1f} TFLOP/s")
-        for i in np.argsort(-per_r)[:14]:
+        for i in np.argsort(-per_r)[:60 if a.reid_bn == "train" else 14]:
             fl = rp.step_flops[i]
             print(f"  step {i:3d}: {per_r[i] * 1e3:8.1f} us  {fl / per_r[i] / 1e9 if fl else 0:7.1f} TF/s  {rp.labels[i]}")
         res["reid"] = {"n": a.reid, "ms_graph": ms_r, "eager_ms": per_r.tolist(), "conv_flops": rp.conv_flops,

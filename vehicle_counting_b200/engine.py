@@ -43,6 +43,14 @@ LAYERS_V6 = [
     (-1, 3, "C3", (512, False)), (-1, 1, "Conv", (512, 3, 2, 1)), ((-1, 10), 1, "Cat", ()),
     (-1, 3, "C3", (1024, False)), ((17, 20, 23), 1, "Detect", ()),
 ]
+# checkpoints <= v5.0 (north_star: "CSP/Focus conv stacks ... SPP"): Focus stem (space-to-depth + 3x3 conv == the s2d stem path
+# below with a channel permutation), nine C3 repeats at P3, SPP(5, 9, 13) before the last backbone C3 (== the SPPF cascade:
+# mp9 = mp5 o mp5, mp13 = mp5 o mp5 o mp5, exactly)
+LAYERS_V5 = [
+    (-1, 1, "Focus", (64, 3)), (-1, 1, "Conv", (128, 3, 2, 1)), (-1, 3, "C3", (128, True)),
+    (-1, 1, "Conv", (256, 3, 2, 1)), (-1, 9, "C3", (256, True)), (-1, 1, "Conv", (512, 3, 2, 1)),
+    (-1, 9, "C3", (512, True)), (-1, 1, "Conv", (1024, 3, 2, 1)), (-1, 1, "SPP", (1024, 5)), (-1, 3, "C3", (1024, False)),
+] + LAYERS_V6[10:]
 YOLO_BN_EPS = 1e-3     # upstream initialize_weights() sets eps=1e-3 on every BatchNorm2d
 
 
@@ -50,9 +58,25 @@ def _ceil8(x: float) -> int:
     return int(math.ceil(x / 8) * 8)
 
 
+def infer_version(sd: Dict[str, torch.Tensor]) -> str:
+    """'v5' for checkpoints with the Focus stem (model.0.conv.conv.weight), else 'v6'"""
+    return "v5" if "model.0.conv.conv.weight" in sd else "v6"
+
+
+def focus_weights_to_s2d(w: torch.Tensor) -> torch.Tensor:
+    """Focus concatenates the four pixel phases as (dy, dx) = (0,0), (1,0), (0,1), (1,1) [upstream models/common.py Focus]; the
+    s2d ingest stores them as (dy*2 + dx).  [cout, 12, 3, 3] -> [cout, 16, 3, 3] in the ingest's channel order."""
+    co = w.shape[0]
+    out = torch.zeros(co, 16, 3, 3, dtype=w.dtype, device=w.device)
+    for dy in range(2):
+        for dx in range(2):
+            out[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = w[:, (dx * 2 + dy) * 3:(dx * 2 + dy) * 3 + 3]
+    return out
+
+
 def infer_model_name(sd: Dict[str, torch.Tensor]) -> str:
-    """Recover (depth, width) multiples from a v6.0 state_dict: stem width and C3 repeat count."""
-    c0 = sd["model.0.conv.weight"].shape[0]
+    """Recover (depth, width) multiples from a state_dict: stem width and C3 repeat count."""
+    c0 = sd["model.0.conv.conv.weight" if infer_version(sd) == "v5" else "model.0.conv.weight"].shape[0]
     n2 = len({k.split(".")[3] for k in sd if k.startswith("model.2.m.")})
     for name, (gd, gw) in MODEL_SCALES.items():
         if _ceil8(64 * gw) == c0 and max(round(3 * gd), 1) == n2:
@@ -214,6 +238,8 @@ class YoloEngine:
         self.classes = None if classes is None else sorted(int(c) for c in classes)     # upstream non_max_suppression(classes=...)
         self.a_mode = a_mode
         self.fuse_c3 = os.environ.get("VCB_C3_FUSE", "1") != "0"      # C3: cv1|cv2 as one GEMM, bottlenecks in place
+        self.version = infer_version(state_dict)
+        self.layers = LAYERS_V5 if self.version == "v5" else LAYERS_V6
         gd, gw = MODEL_SCALES[self.name]
         det_w = state_dict["model.24.m.0.weight"]
         self.nc = det_w.shape[0] // 3 - 5
@@ -249,12 +275,12 @@ class YoloEngine:
 
     def _build(self, sd, gd, gw) -> None:
         B, dev, plan = self.batch, self.device, self.plan
-        nl = len(LAYERS_V6)
+        LAYERS = self.layers
         # 1. channel / spatial bookkeeping
         ch: List[int] = []
         hw: List[Tuple[int, int]] = []
         reps: List[int] = []
-        for i, (f, n, kind, args) in enumerate(LAYERS_V6):
+        for i, (f, n, kind, args) in enumerate(LAYERS):
             def cin(j):
                 return (3 if i == 0 else ch[i - 1]) if j == -1 else ch[j]
 
@@ -266,7 +292,10 @@ class YoloEngine:
                 c2, k, s, p = _ceil8(args[0] * gw), args[1], args[2], args[3]
                 hh, ww = shp(f)
                 ch.append(c2); hw.append(((hh + 2 * p - k) // s + 1, (ww + 2 * p - k) // s + 1))
-            elif kind in ("C3", "SPPF"):
+            elif kind == "Focus":
+                hh, ww = shp(f)
+                ch.append(_ceil8(args[0] * gw)); hw.append((hh // 2, ww // 2))
+            elif kind in ("C3", "SPPF", "SPP"):
                 ch.append(_ceil8(args[0] * gw)); hw.append(shp(f))
             elif kind == "Up":
                 ch.append(cin(f)); hw.append((shp(f)[0] * 2, shp(f)[1] * 2))
@@ -277,7 +306,7 @@ class YoloEngine:
         # 2. homes: an output that feeds a Cat lives inside the Cat's buffer (concat-free)
         cat_buf: Dict[int, torch.Tensor] = {}
         home: Dict[int, TRef] = {}
-        for i, (f, n, kind, args) in enumerate(LAYERS_V6):
+        for i, (f, n, kind, args) in enumerate(LAYERS):
             if kind != "Cat":
                 continue
             cat_buf[i] = self._buf(hw[i][0], hw[i][1], ch[i])
@@ -288,7 +317,7 @@ class YoloEngine:
                 home[src] = TRef(cat_buf[i], off, ch[src])
                 off += ch[src]
             home[i] = TRef(cat_buf[i], 0, ch[i])
-        for i, (f, n, kind, args) in enumerate(LAYERS_V6):
+        for i, (f, n, kind, args) in enumerate(LAYERS):
             if i not in home and kind not in ("Detect",):
                 home[i] = TRef(self._buf(hw[i][0], hw[i][1], ch[i]), 0, ch[i])
         self.layer_out = home
@@ -315,7 +344,7 @@ class YoloEngine:
 
         # $VCB_SILU=tanh: one-MUFU SiLU (h + h*tanh(h)); default: ex2 + rcp
         SILU = L.ACT_SILU_TANH if os.environ.get("VCB_SILU", "exp") == "tanh" else L.ACT_SILU
-        for i, (f, n, kind, args) in enumerate(LAYERS_V6):
+        for i, (f, n, kind, args) in enumerate(LAYERS):
             pre = f"model.{i}"
             if kind == "Conv":
                 k, s, p = args[1], args[2], args[3]
@@ -370,7 +399,12 @@ class YoloEngine:
                         cur = dst
                 w_, b_ = fold_conv_bn(sd, pre + ".cv3", YOLO_BN_EPS, dev)
                 plan.conv(TRef(cat, 0, 2 * c_), B, w_, b_, home[i], 1, 1, 0, SILU, a_mode=self.a_mode)
-            elif kind == "SPPF":
+            elif kind == "Focus":
+                w_, b_ = fold_conv_bn(sd, pre + ".conv", YOLO_BN_EPS, dev)
+                assert tuple(w_.shape[1:]) == (12, 3, 3), "Focus(c1=3, k=3) expected"
+                plan.conv(src_of(i, f), B, focus_weights_to_s2d(w_), b_, home[i], 3, 1, 1, SILU,
+                          a_mode=L.A_ROWWIN if self.stem_rowwin else self.a_mode, flops=2.0 * B * hw[0][0] * hw[0][1] * w_.shape[0] * 12 * 9)
+            elif kind in ("SPPF", "SPP"):
                 x = src_of(i, f)
                 c_ = x.c // 2
                 hh, ww = hw[i]
