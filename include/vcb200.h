@@ -117,6 +117,13 @@ int vcb_frames_to_f16_s2d_wpad(const uint8_t* frames, void* out, int32_t n, int3
  * placed at (top, left), pad_value elsewhere; bit-identical to cv2 for this ratio (1280x720 -> 640x360 inside 384x640) */
 int vcb_letterbox_half_u8(const uint8_t* src, int32_t n, int32_t h0, int32_t w0, uint8_t* dst, int32_t h1, int32_t w1,
                           int32_t top, int32_t left, int32_t pad_value, vcb_stream_t stream);
+/* letterbox with ANY ratio, bit-identical to cv2.resize(INTER_LINEAR) on uint8 + copyMakeBorder: OpenCV's 11-bit fixed-point
+ * bilinear.  The resized image is new_h x new_w at (top, left) of the h1 x w1 frame; xtab / ytab are DEVICE int32 [new_w | new_h][4]
+ * = source index 0, source index 1, weight 0, weight 1 (weights scaled by 2048, built on the host the way OpenCV builds them --
+ * vehicle_counting_b200/networks/yolo.py cv2_linear_table).  Same-size frame batches of any resolution then need no host resize. */
+int vcb_letterbox_bilinear_u8(const uint8_t* src, int32_t n, int32_t h0, int32_t w0, uint8_t* dst, int32_t h1, int32_t w1, int32_t top,
+                              int32_t left, int32_t new_h, int32_t new_w, const int32_t* xtab, const int32_t* ytab, int32_t pad_value,
+                              vcb_stream_t stream);
 /* nearest x2 upsample of a channel slice into a channel slice (nn.Upsample(None, 2, 'nearest')) */
 int vcb_upsample2x(const void* src, int32_t src_pitch, void* dst, int32_t dst_pitch, int32_t n, int32_t h,
                    int32_t w, int32_t c, vcb_stream_t stream);

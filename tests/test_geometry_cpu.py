@@ -72,3 +72,26 @@ def test_every_reid_layer_has_a_launch_geometry():
             for kw in (dict(act=L.ACT_RELU), dict(act=L.ACT_RELU, res_mode=L.RES_BEFORE_ACT, res_pitch=cout), dict(act=L.ACT_NONE, out_dtype=L.F32)):
                 d = ops.make_conv_desc(crops, hw, hw, cin, cout, k, s, p, **kw)
                 ops.conv_packed_sizes(d)
+
+
+def test_cv2_linear_table_reproduces_cv2_resize():
+    """networks/yolo.py cv2_linear_table + the fixed-point passes of csrc/pointwise.cu letterbox_bilinear_kernel, evaluated in NumPy,
+    against cv2.resize(INTER_LINEAR) on uint8: bit-identical for down- and up-scaling ratios."""
+    import cv2
+    import numpy as np
+    from vehicle_counting_b200.networks.yolo import cv2_linear_table
+    rng = np.random.default_rng(0)
+    cases = [(720, 1280, 360, 640), (720, 1280, 414, 736), (1080, 1920, 360, 640), (200, 300, 213, 320), (100, 150, 320, 480),
+             (240, 320, 640, 853), (37, 53, 640, 917), (1000, 30, 640, 19), (480, 640, 480, 640)]
+    for _ in range(40):
+        sh, sw = (int(v) for v in rng.integers(20, 900, 2))
+        r = 640 / max(sh, sw)
+        cases.append((sh, sw, max(int(round(sh * r)), 1), max(int(round(sw * r)), 1)))
+    for sh, sw, dh, dw in cases:
+        src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        xt, yt = cv2_linear_table(dw, sw, False).astype(np.int64), cv2_linear_table(dh, sh, True).astype(np.int64)
+        S = src.astype(np.int64)
+        H = S[:, xt[:, 0]] * xt[None, :, 2, None] + S[:, xt[:, 1]] * xt[None, :, 3, None]
+        out = (((yt[:, 2, None, None] * (H[yt[:, 0]] >> 4)) >> 16) + ((yt[:, 3, None, None] * (H[yt[:, 1]] >> 4)) >> 16) + 2) >> 2
+        np.testing.assert_array_equal(np.clip(out, 0, 255).astype(np.uint8), cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR),
+                                      err_msg=str((sh, sw, dh, dw)))

@@ -368,3 +368,34 @@ def test_adapter_device_letterbox_matches_host_letterbox(lib):
     assert torch.equal(eng.frames, frames_dev)                    # the network saw the same bytes on both paths
     np.testing.assert_array_equal(cnt_dev, cnt_host)
     np.testing.assert_array_equal(det_dev, det_host)
+
+
+def test_letterbox_bilinear_is_bit_identical_to_cv2(lib):
+    """vcb_letterbox_bilinear_u8 (OpenCV's 11-bit fixed-point bilinear restated on the device) against upstream's host letterbox
+    (cv2.resize INTER_LINEAR + copyMakeBorder 114): down-scaling, up-scaling, non-integer ratios, pad-only; and through the
+    YoloBackbone adapter (same bytes in the engine's input as with the host path)."""
+    from oracle import yolov5 as Y
+    from vehicle_counting_b200 import ops
+    from vehicle_counting_b200.networks import yolo as NY
+    rng = np.random.default_rng(21)
+    for (h0, w0, size) in ((1080, 1920, 640), (720, 1280, 1280), (480, 640, 640), (200, 300, 320), (333, 517, 640), (100, 150, 480)):
+        g = size / max(h0, w0)
+        h1, w1 = (NY._make_divisible(v * g, 32) for v in (h0, w0))
+        frames = rng.integers(0, 256, (2, h0, w0, 3), dtype=np.uint8)
+        want = np.stack([Y.letterbox(f, (h1, w1)) for f in frames])
+        r = min(h1 / h0, w1 / w0)
+        nw, nh = int(round(w0 * r)), int(round(h0 * r))
+        top, left = int(round((h1 - nh) / 2 - 0.1)), int(round((w1 - nw) / 2 - 0.1))
+        xt = torch.from_numpy(NY.cv2_linear_table(nw, w0, False)).to(DEV)
+        yt = torch.from_numpy(NY.cv2_linear_table(nh, h0, True)).to(DEV)
+        dst = torch.full((2, h1, w1, 3), 7, dtype=torch.uint8, device=DEV)
+        ops.letterbox_bilinear(torch.from_numpy(frames).to(DEV), 2, h0, w0, dst, h1, w1, top, left, nh, nw, xt, yt, 114)
+        np.testing.assert_array_equal(dst.cpu().numpy(), want, err_msg=str((h0, w0, h1, w1)))
+    # adapter: 1080p frames reach the engine as the host letterbox would deliver them
+    from vehicle_counting_b200.weights import synth_yolov5_state_dict
+    imgs = [rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8) for _ in range(2)]
+    net = NY.YoloBackbone(None, 0.45, 0.25, 300, state_dict=synth_yolov5_state_dict("yolov5n", seed=0, obj_bias=1.0))
+    net.detect_raw(imgs)
+    eng = net._engine(2, 384, 640)
+    want = np.stack([NY._letterbox(im, (384, 640)) for im in imgs])
+    np.testing.assert_array_equal(eng.frames.cpu().numpy(), want)

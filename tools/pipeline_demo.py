@@ -26,13 +26,14 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--tracks", type=int, default=64)
     ap.add_argument("--bn", default="eval", choices=["eval", "train"])
+    ap.add_argument("--size", type=int, default=640, help="AutoShape size: 640 -> 384x640 (the reference), 1280 -> 736x1280")
     a = ap.parse_args()
     from vehicle_counting_b200.modules import VideoTracker
     from vehicle_counting_b200.networks.yolo import YoloBackbone
     from vehicle_counting_b200.weights import synth_yolov5_state_dict
     rng = np.random.default_rng(0)
     H, W, n = 720, 1280, a.tracks
-    net = YoloBackbone(None, 0.45, 0.25, 300, state_dict=synth_yolov5_state_dict(a.model, seed=0, obj_bias=-3.0))
+    net = YoloBackbone(None, 0.45, 0.25, 300, state_dict=synth_yolov5_state_dict(a.model, seed=0, obj_bias=-3.0), size=a.size)
     cam = {"tracking_config": {"MAX_DIST": 0.3, "MIN_CONFIDENCE": 0.3, "NMS_MAX_OVERLAP": 0.5, "MAX_IOU_DISTANCE": 0.7, "MAX_AGE": 30,
                                "N_INIT": 3, "NN_BUDGET": 50}}
     vt = VideoTracker(3, cam, {"num_frames": a.frames}, "synthetic", bn_mode=a.bn)
@@ -63,7 +64,7 @@ def main():
     t_det, t_trk, rows = run(a.frames, True)
     torch.cuda.synchronize()
     tot = t_det + t_trk
-    print(json.dumps({"pipeline": f"{a.model} 1280x720 -> 384x640 detect (batch {a.batch}) + VideoTracker ({n} boxes, 3 classes, bn {a.bn})",
+    print(json.dumps({"pipeline": f"{a.model} 1280x720 -> {'384x640' if a.size == 640 else '736x1280'} detect (batch {a.batch}) + VideoTracker ({n} boxes, 3 classes, bn {a.bn})",
                       "frames": a.frames, "fps": a.frames / tot, "detect_ms_per_frame": 1e3 * t_det / a.frames,
                       "track_ms_per_frame": 1e3 * t_trk / a.frames, "rows": rows}))
 

@@ -4,6 +4,7 @@ import csv, json, re, sys
 from collections import defaultdict
 
 src, dst, steps = sys.argv[1], sys.argv[2], int(sys.argv[3])
+workload = json.loads(sys.argv[4]) if len(sys.argv) > 4 else None     # [model, h, w, batch, rois, reid_bn]: bench.py matches it
 rows = [r for r in csv.reader(open(src)) if len(r) >= 15 and r[0].isdigit()]
 per = defaultdict(dict)
 name = {}
@@ -19,7 +20,7 @@ for i, m in per.items():
     a["dram_write_MB"] += m.get("dram__bytes_write.sum", 0.0) / 1e6
     a["tensor_pct_x_us"] += m.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) * us
 tot = sum(a["us"] for a in agg.values())
-out = {"source": src, "steps_captured": steps, "launches": len(per), "total_us": round(tot, 1), "by_kernel": []}
+out = {"source": src, "workload": workload, "steps_captured": steps, "launches": len(per), "total_us": round(tot, 1), "by_kernel": []}
 for k, a in sorted(agg.items(), key=lambda x: -x[1]["us"]):
     out["by_kernel"].append({"kernel": k, "launches": a["launches"], "total_us": round(a["us"], 1), "share": round(a["us"] / tot, 4),
                              "dram_read_MB_per_step": round(a["dram_read_MB"] / steps, 1), "dram_write_MB_per_step": round(a["dram_write_MB"] / steps, 1),

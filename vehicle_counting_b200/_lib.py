@@ -91,6 +91,7 @@ _SIGNATURES = {
     "vcb_frames_to_f16_s2d": ([_VP, _VP, _I32, _I32, _I32, _VP], _I32),
     "vcb_frames_to_f16_s2d_wpad": ([_VP, _VP, _I32, _I32, _I32, _VP], _I32),
     "vcb_letterbox_half_u8": ([_VP, _I32, _I32, _I32, _VP, _I32, _I32, _I32, _I32, _I32, _VP], _I32),
+    "vcb_letterbox_bilinear_u8": ([_VP, _I32, _I32, _I32, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP, _VP, _I32, _VP], _I32),
     "vcb_upsample2x": ([_VP, _I32, _VP, _I32, _I32, _I32, _I32, _I32, _VP], _I32),
     "vcb_sppf_pool": ([_VP, _I32, _I32, _I32, _I32, _I32, _VP], _I32),
     "vcb_maxpool": ([_VP, _I32, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP], _I32),

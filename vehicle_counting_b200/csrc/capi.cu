@@ -14,6 +14,7 @@ int frames_to_f16c4(const uint8_t*, void*, int, int, int, cudaStream_t);
 int frames_to_f16_s2d(const uint8_t*, void*, int, int, int, cudaStream_t);
 int frames_to_f16_s2d_wpad(const uint8_t*, void*, int, int, int, cudaStream_t);
 int letterbox_half(const uint8_t*, int, int, int, uint8_t*, int, int, int, int, int, cudaStream_t);
+int letterbox_bilinear(const uint8_t*, int, int, int, uint8_t*, int, int, int, int, int, int, const int*, const int*, int, cudaStream_t);
 int upsample2x(const void*, int, void*, int, int, int, int, int, cudaStream_t);
 int sppf_pool(void*, int, int, int, int, int, cudaStream_t);
 int maxpool(const void*, int, void*, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -183,6 +184,12 @@ int vcb_letterbox_half_u8(const uint8_t* src, int32_t n, int32_t h0, int32_t w0,
                           int32_t left, int32_t pad_value, vcb_stream_t st) {
   const int rc = require_init(); if (rc) return rc;
   return letterbox_half(src, n, h0, w0, dst, h1, w1, top, left, pad_value, (cudaStream_t)st);
+}
+int vcb_letterbox_bilinear_u8(const uint8_t* src, int32_t n, int32_t h0, int32_t w0, uint8_t* dst, int32_t h1, int32_t w1, int32_t top,
+                              int32_t left, int32_t new_h, int32_t new_w, const int32_t* xtab, const int32_t* ytab, int32_t pad_value,
+                              vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return letterbox_bilinear(src, n, h0, w0, dst, h1, w1, top, left, new_h, new_w, xtab, ytab, pad_value, (cudaStream_t)st);
 }
 int vcb_upsample2x(const void* src, int32_t sp, void* dst, int32_t dp, int32_t n, int32_t h, int32_t w, int32_t c, vcb_stream_t st) {
   const int rc = require_init(); if (rc) return rc;

@@ -182,6 +182,53 @@ int letterbox_half(const uint8_t* src, int n, int h0, int w0, uint8_t* dst, int 
   return check_cuda(cudaGetLastError(), "letterbox_half launch");
 }
 
+// ---------------------------------------------------------------- letterbox, any ratio: cv2.resize(INTER_LINEAR) on uint8, bit for bit
+// OpenCV resizes 8-bit images in fixed point (resize.cpp: INTER_RESIZE_COEF_BITS = 11): per destination column / row two source
+// indices and two 11-bit weights (computed on the host exactly as OpenCV does, in float32: networks/yolo.py cv2_linear_table),
+// a horizontal pass in int32, and the vertical pass ((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2.  xtab / ytab:
+// int32 [new_w | new_h][4] = index0, index1, weight0, weight1.  One thread per output pixel; pixels outside the resized image
+// get the pad value (copyMakeBorder(114)).  Replaces the host cv2 pass of upstream's letterbox for same-size frame batches.
+__global__ void letterbox_bilinear_kernel(const uint8_t* __restrict__ src, int n, int h0, int w0, uint8_t* __restrict__ dst, int h1, int w1,
+                                          int top, int left, int nh, int nw, const int4* __restrict__ xtab, const int4* __restrict__ ytab,
+                                          int pad) {
+  const long long total = (long long)n * h1 * w1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w1);
+    long long t = i / w1;
+    const int y = (int)(t % h1);
+    const int b = (int)(t / h1);
+    const int sy = y - top, sx = x - left;
+    uint8_t* o = dst + i * 3;
+    if ((unsigned)sy < (unsigned)nh && (unsigned)sx < (unsigned)nw) {
+      const int4 xt = __ldg(xtab + sx), yt = __ldg(ytab + sy);
+      const uint8_t* img = src + (long long)b * h0 * w0 * 3;
+      const uint8_t* r0 = img + (long long)yt.x * w0 * 3;
+      const uint8_t* r1 = img + (long long)yt.y * w0 * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int a0 = (int)r0[xt.x * 3 + c] * xt.z + (int)r0[xt.y * 3 + c] * xt.w;
+        const int a1 = (int)r1[xt.x * 3 + c] * xt.z + (int)r1[xt.y * 3 + c] * xt.w;
+        int v = (((yt.z * (a0 >> 4)) >> 16) + ((yt.w * (a1 >> 4)) >> 16) + 2) >> 2;
+        v = v < 0 ? 0 : (v > 255 ? 255 : v);
+        o[c] = (uint8_t)v;
+      }
+    } else {
+      o[0] = o[1] = o[2] = (uint8_t)pad;
+    }
+  }
+}
+
+int letterbox_bilinear(const uint8_t* src, int n, int h0, int w0, uint8_t* dst, int h1, int w1, int top, int left, int nh, int nw,
+                       const int* xtab, const int* ytab, int pad, cudaStream_t st) {
+  if (!src || !dst || !xtab || !ytab || n <= 0 || h0 <= 0 || w0 <= 0 || h1 <= 0 || w1 <= 0 || nh <= 0 || nw <= 0 || top < 0 || left < 0 ||
+      top + nh > h1 || left + nw > w1 || pad < 0 || pad > 255 || ((uintptr_t)xtab & 15) || ((uintptr_t)ytab & 15))
+    return set_error(VCB_ERR_INVALID, "letterbox_bilinear: bad argument (the resized image must fit at (top, left); tables 16-byte aligned)");
+  const long long total = (long long)n * h1 * w1;
+  letterbox_bilinear_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, n, h0, w0, dst, h1, w1, top, left, nh, nw,
+                                                                   reinterpret_cast<const int4*>(xtab), reinterpret_cast<const int4*>(ytab), pad);
+  return check_cuda(cudaGetLastError(), "letterbox_bilinear launch");
+}
+
 // ---------------------------------------------------------------- nearest x2 upsample into a channel slice
 __global__ void upsample2x_kernel(const uint4* __restrict__ src, int src_pitch8, uint4* __restrict__ dst, int dst_pitch8, int n,
                                   int h, int w, int c8) {
@@ -441,14 +488,24 @@ __global__ void __launch_bounds__(256) bn_seg_stats_f16_kernel(const uint4* __re
   for (int k = 0; k < 8; ++k) { a[k] = 0.f; b[k] = 0.f; }
   const uint4* base = x + (long long)crop * hw * c8;
   if (rl < lanes) {
-    for (int r = rl; r < hw; r += lanes) {
-      const uint4 v = __ldg(base + (long long)r * c8 + cv);
-      const __half2* h = reinterpret_cast<const __half2*>(&v);
+    // four rows per trip: four independent 16-byte loads in flight per thread (the kernel is a pure HBM stream; one load per
+    // trip left it at ~49 % of the copy bandwidth, profiles/r02_train_bn.md)
+    for (int r0 = rl; r0 < hw; r0 += 4 * lanes) {
+      uint4 v[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = __half22float2(h[k]);
-        a[2 * k] += f.x; a[2 * k + 1] += f.y;
-        b[2 * k] = fmaf(f.x, f.x, b[2 * k]); b[2 * k + 1] = fmaf(f.y, f.y, b[2 * k + 1]);
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * lanes;
+        v[u] = r < hw ? __ldg(base + (long long)r * c8 + cv) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(h[k]);
+          a[2 * k] += f.x; a[2 * k + 1] += f.y;
+          b[2 * k] = fmaf(f.x, f.x, b[2 * k]); b[2 * k + 1] = fmaf(f.y, f.y, b[2 * k + 1]);
+        }
       }
     }
   }

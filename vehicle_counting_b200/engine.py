@@ -151,9 +151,10 @@ class _Plan:
         self.keep: list = []          # tensors that must outlive the plan (weights, descriptors)
         self.graph: Optional[ops.Graph] = None
         self.stream = torch.cuda.Stream(device=device)
-        # $VCB_TILE_REV=1: consecutive convolutions walk their tiles in opposite directions, so a layer starts on the part of
-        # its input that its producer wrote last (still in the 126 MB L2) instead of the part written first (evicted)
-        self.alternate = os.environ.get("VCB_TILE_REV", "0") == "1"
+        # consecutive convolutions walk their tiles in opposite directions, so a layer starts on the part of its input that its
+        # producer wrote last (still in the 126 MB L2) instead of the part written first (evicted): +1.5-2.5 % on the whole step
+        # (profiles/r02_ab_switches.md); $VCB_TILE_REV=0 turns it off
+        self.alternate = os.environ.get("VCB_TILE_REV", "1") == "1"
         self._rev = False
 
     def add(self, fn: Callable[[object], None], label: str = "op", flops: float = 0.0) -> None:

@@ -80,6 +80,28 @@ def _letterbox(im: np.ndarray, new_shape: Tuple[int, int]) -> np.ndarray:
     return im
 
 
+def cv2_linear_table(dst_n: int, src_n: int, vertical: bool) -> np.ndarray:
+    """The per-column (per-row) table of cv2.resize(INTER_LINEAR) for 8-bit images [OpenCV imgproc/resize.cpp, 11-bit fixed point]:
+    int32 [dst_n, 4] = source index 0, source index 1, weight 0, weight 1 (x 2048).  Restated operation by operation: the scale is
+    1 / (dst / src) in double, the source coordinate is rounded to float32 before the floor, the weights are float32 products
+    rounded half-to-even; columns clamp the coordinate AND zero the fraction at the borders, rows only clamp the two row indices
+    (so a border row blends the same source row with both weights).  tests/test_geometry_cpu.py checks the table against
+    cv2.resize on 50 size pairs; csrc/pointwise.cu letterbox_bilinear_kernel consumes it."""
+    scale = 1.0 / (float(dst_n) / float(src_n))
+    d = np.arange(dst_n, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    if not vertical:
+        lo, hi = s < 0, s >= src_n - 1
+        f[lo] = 0; s[lo] = 0
+        f[hi] = 0; s[hi] = src_n - 1
+    one, k = np.float32(1.0), np.float32(2048.0)
+    a0 = np.rint(((one - f) * k).astype(np.float32))
+    a1 = np.rint((f * k).astype(np.float32))
+    return np.stack([np.clip(s, 0, src_n - 1), np.clip(s + 1, 0, src_n - 1), a0, a1], 1).astype(np.int32)
+
+
 class YoloBackbone(BaseBackbone):
     def __init__(self, weight, min_iou, min_conf, max_det, filter_classes=None, size: int = 640, device: Optional[str] = None,
                  state_dict: Optional[Dict[str, torch.Tensor]] = None, class_names: Optional[Sequence[str]] = None, **kwargs):
@@ -104,6 +126,7 @@ class YoloBackbone(BaseBackbone):
         self._engines: Dict[Tuple[int, int, int], YoloEngine] = {}
         self._pinned: Dict[tuple, torch.Tensor] = {}
         self._raw_dev: Dict[tuple, torch.Tensor] = {}
+        self._lb_tables: Dict[tuple, Tuple[torch.Tensor, torch.Tensor, tuple]] = {}      # (h0, w0, h1, w1) -> device tables + geometry
         # a parameter so that `.parameters()` / `.to()` behave like the reference module (detect.py:27-28)
         self._anchor = nn.Parameter(torch.zeros(1), requires_grad=False)
 
@@ -143,6 +166,27 @@ class YoloBackbone(BaseBackbone):
             with torch.cuda.stream(eng.plan.stream):
                 raw.copy_(host, non_blocking=True)
             ops.letterbox_half(raw, len(imgs), h0, w0, eng.frames, h1, w1, top, left, 114, stream=eng.plan.stream)
+        elif all(s == shape0[0] for s in shape0) and (h0, w0) != (h1, w1) and os.environ.get("VCB_DEVICE_LETTERBOX", "1") != "0":
+            # same-size frames at any other ratio: raw frames go up, cv2's fixed-point bilinear + the 114 border run on the device
+            # (vcb_letterbox_bilinear_u8: bit-identical to the host cv2 path below)
+            key = ("raw", len(imgs), h0, w0)
+            if key not in self._pinned:
+                self._pinned[key] = torch.empty(len(imgs), h0, w0, 3, dtype=torch.uint8).pin_memory()
+                self._raw_dev[key] = torch.empty(len(imgs), h0, w0, 3, dtype=torch.uint8, device=eng.frames.device)
+            tkey = (h0, w0, h1, w1)
+            if tkey not in self._lb_tables:
+                nw, nh = int(round(w0 * r)), int(round(h0 * r))
+                dh, dw = (h1 - nh) / 2, (w1 - nw) / 2
+                geo = (int(round(dh - 0.1)), int(round(dw - 0.1)), nh, nw)
+                xt = torch.from_numpy(cv2_linear_table(nw, w0, False)).to(eng.frames.device)
+                yt = torch.from_numpy(cv2_linear_table(nh, h0, True)).to(eng.frames.device)
+                self._lb_tables[tkey] = (xt, yt, geo)
+            xt, yt, (top, left, nh, nw) = self._lb_tables[tkey]
+            host, raw = self._pinned[key], self._raw_dev[key]
+            copy_frames(host.numpy(), imgs)
+            with torch.cuda.stream(eng.plan.stream):
+                raw.copy_(host, non_blocking=True)
+            ops.letterbox_bilinear(raw, len(imgs), h0, w0, eng.frames, h1, w1, top, left, nh, nw, xt, yt, 114, stream=eng.plan.stream)
         else:
             host = self._pinned[(len(imgs), h1, w1)]
             if all(im.shape[:2] == (h1, w1) for im in imgs):

@@ -162,6 +162,12 @@ def letterbox_half(src_u8, n, h0, w0, dst_u8, h1, w1, top, left, pad=114, stream
             "vcb_letterbox_half_u8")
 
 
+def letterbox_bilinear(src_u8, n, h0, w0, dst_u8, h1, w1, top, left, new_h, new_w, xtab, ytab, pad=114, stream=None) -> None:
+    """any-ratio letterbox on the device, bit-identical to cv2.resize(INTER_LINEAR) + copyMakeBorder (tables: cv2_linear_table)"""
+    L.check(L.load().vcb_letterbox_bilinear_u8(L.ptr(src_u8), n, h0, w0, L.ptr(dst_u8), h1, w1, top, left, new_h, new_w, L.ptr(xtab),
+                                               L.ptr(ytab), pad, _st(stream)), "vcb_letterbox_bilinear_u8")
+
+
 def roi_stem_patches(desc: L.RoiDesc, frames_u8, fh, fw, rois, patches, stream=None) -> None:
     """crop/resize/normalise as roi_resize_norm, written as the fused stem's im2col operand [n][25][128][32] fp16"""
     L.check(L.load().vcb_roi_stem_patches(C.byref(desc), L.ptr(frames_u8), fh, fw, L.ptr(rois), L.ptr(patches), _st(stream)),
