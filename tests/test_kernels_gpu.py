@@ -329,6 +329,62 @@ def test_reid_fused_stem_matches_unfused_reference(lib):
     assert (got - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
 
 
+def test_reid_fused_stem_train_mode_bn_matches_torch(lib):
+    """The fused stem under train-mode BatchNorm (model.py:52-60 with the reference's batch statistics, one segment per
+    Extractor call): vcb_reid_stem_stats + vcb_bn_seg_finalize + vcb_reid_stem_pool_bn against F.batch_norm(training=True) per
+    segment on the same fp16 crop."""
+    import torch.nn.functional as F
+    from oracle import reid as R
+    from vehicle_counting_b200 import ops, _lib as L
+    rng = np.random.default_rng(6)
+    fh, fw = 240, 320
+    frames = torch.from_numpy(rng.integers(0, 256, (2, fh, fw, 3), dtype=np.uint8)).to(DEV)
+    n, nb = 37, 64                                             # 37 real crops in a bucket of 64: padding crops form their own segment
+    seg_sizes = [5, 1, 20, 11]
+    wh = rng.uniform(8, 200, (nb, 2)); tl = rng.uniform(0, 1, (nb, 2)) * (np.array([fw, fh]) - wh)
+    rois_np = np.concatenate([rng.integers(0, 2, (nb, 1)), tl, tl + wh], 1).astype(np.int32)
+    rois_np[n:] = 0
+    rois = torch.from_numpy(rois_np).to(DEV)
+    rd = L.RoiDesc()
+    rd.num_rois, rd.out_size, rd.out_channels = nb, 50, 4
+    for c in range(3):
+        rd.mean[c] = R.NORM_MEAN[c]; rd.inv_std[c] = 1.0 / R.NORM_STD[c]
+    x = torch.zeros(nb, 50, 50, 4, dtype=torch.float16, device=DEV)
+    ops.roi_resize_norm(rd, frames, fh, fw, rois, x)
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(64, 3, 3, 3, generator=g) * 0.3
+    b = torch.randn(64, generator=g) * 0.2
+    gamma = torch.rand(64, generator=g) + 0.5
+    beta = torch.randn(64, generator=g) * 0.1
+    wp, bp = ops.pack_reid_stem_weights(w.to(DEV), b.to(DEV))
+    nseg = len(seg_sizes)
+    soc = np.full(nb, nseg, np.int32); soc[:n] = np.repeat(np.arange(nseg), seg_sizes)
+    cnt = np.zeros(nseg + 1, np.int32); cnt[:nseg] = seg_sizes; cnt[nseg] = nb - n
+    soc_d, cnt_d = torch.from_numpy(soc).to(DEV), torch.from_numpy(cnt).to(DEV)
+    sums = torch.zeros(nseg + 1, 64, 2, dtype=torch.float64, device=DEV)
+    affine = torch.zeros(nseg + 1, 64, 2, dtype=torch.float32, device=DEV)
+    patches = torch.zeros(nb, 25, 128, 32, dtype=torch.float16, device=DEV)
+    out = torch.full((nb, 25, 25, 64), -5.0, dtype=torch.float16, device=DEV)
+    ops.roi_stem_patches(rd, frames, fh, fw, rois, patches)
+    ops.reid_stem_stats(patches, wp, bp, nb, soc_d, sums)
+    ops.bn_seg_finalize(sums, cnt_d, nseg + 1, 64, 2500, gamma.to(DEV), beta.to(DEV), bp, 1e-5, affine)
+    ops.reid_stem_pool_bn(patches, wp, affine, soc_d, out, nb)
+    torch.cuda.synchronize()
+    assert tuple(lib_fault()) == (0, 0, 0, 0)
+    conv = F.conv2d(x[:n, ..., :3].float().cpu().permute(0, 3, 1, 2), wp[:, :27].float().cpu().view(64, 3, 3, 3).permute(0, 3, 1, 2), b, 1, 1)
+    got_sums = sums.cpu()
+    off = 0
+    for si, k in enumerate(seg_sizes):
+        c_ = conv[off:off + k].double()
+        np.testing.assert_allclose(got_sums[si, :, 0].numpy(), c_.sum((0, 2, 3)).numpy(), rtol=2e-4, atol=2e-2)
+        np.testing.assert_allclose(got_sums[si, :, 1].numpy(), (c_ * c_).sum((0, 2, 3)).numpy(), rtol=2e-4, atol=2e-2)
+        y = F.relu(F.batch_norm(conv[off:off + k], None, None, gamma, beta, True, 0.0, 1e-5))
+        ref = F.max_pool2d(y.half().float(), 3, 2, 1).permute(0, 2, 3, 1)
+        err = (out[off:off + k].float().cpu() - ref).abs().max().item()
+        assert err <= 4e-3 * max(1.0, ref.abs().max().item()), (si, k, err)
+        off += k
+
+
 def lib_fault():
     from vehicle_counting_b200 import _lib as L
     return L.last_fault()

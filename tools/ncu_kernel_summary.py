@@ -13,7 +13,8 @@ want = {"gpu__time_duration.sum": "duration", "dram__bytes_read.sum": "dram_read
         "l1tex__m_xbar2l1tex_read_bytes.sum": "l2_to_sm_bytes", "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
         "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct", "launch__grid_size": "grid", "launch__block_size": "block",
         "launch__registers_per_thread": "regs"}
-mult = {"nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+mult = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6,
+        "Gbyte": 1e9}
 for r in rows[hdr + 2:]:
     if len(r) != len(names):
         continue

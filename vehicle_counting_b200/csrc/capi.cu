@@ -31,6 +31,9 @@ int roi_resize_norm(const VcbRoiDesc&, const uint8_t*, int, int, const int*, voi
 int boxes_to_rois(const double*, const int*, int, int, int, int*, cudaStream_t);
 int roi_stem_patches(const VcbRoiDesc&, const uint8_t*, int, int, const int*, void*, cudaStream_t);
 int reid_stem_pool(const void*, const void*, const float*, void*, int, cudaStream_t);
+int reid_stem_stats(const void*, const void*, const float*, int, const int*, double*, cudaStream_t);
+int reid_stem_pool_bn(const void*, const void*, const float*, const int*, void*, int, cudaStream_t);
+int bn_seg_finalize(const double*, const int*, int, int, int, const float*, const float*, const float*, float, float*, cudaStream_t);
 
 static thread_local char g_err[512] = "";
 
@@ -246,6 +249,19 @@ int vcb_bn_apply(const float* x, int32_t c, int32_t rows, const int32_t* row_seg
   return bn_apply(x, c, rows, row_seg, scale, shift, residual, res_pitch, act, y, y_pitch, (cudaStream_t)st);
 }
 
+int vcb_reid_stem_stats(const void* patches, const void* w_packed, const float* bias, int32_t num_rois, const int32_t* seg_of_crop,
+                        double* sums, vcb_stream_t st) {
+  return reid_stem_stats(patches, w_packed, bias, num_rois, seg_of_crop, sums, (cudaStream_t)st);
+}
+int vcb_reid_stem_pool_bn(const void* patches, const void* w_packed, const float* affine, const int32_t* seg_of_crop, void* out,
+                          int32_t num_rois, vcb_stream_t st) {
+  return reid_stem_pool_bn(patches, w_packed, affine, seg_of_crop, out, num_rois, (cudaStream_t)st);
+}
+int vcb_bn_seg_finalize(const double* sums, const int32_t* seg_crops, int32_t num_seg_plus1, int32_t c, int32_t hw, const float* gamma,
+                        const float* beta, const float* bias, float eps, float* affine, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return bn_seg_finalize(sums, seg_crops, num_seg_plus1, c, hw, gamma, beta, bias, eps, affine, (cudaStream_t)st);
+}
 int vcb_bn_seg_stats_f16(const void* x, int32_t c, int32_t hw, int32_t n, const int32_t* seg_of_crop, double* sums, vcb_stream_t st) {
   const int rc = require_init(); if (rc) return rc;
   return bn_seg_stats_f16(x, c, hw, n, seg_of_crop, sums, (cudaStream_t)st);

@@ -108,9 +108,25 @@ __global__ void __launch_bounds__(256) roi_stem_patches_kernel(const VcbRoiDesc 
 }
 
 // weights fp16 [64][32] (K-major, k = (r*3+s)*3+c, zero padded), bias fp32 [64]; out fp16 [num_rois][25][25][64]
-__global__ void __launch_bounds__(kStemThreads, 2)
+// MODE 0: BatchNorm folded into the weights / bias (eval statistics): conv + bias -> ReLU -> max-pool.
+// Train-mode BatchNorm (the reference as shipped: statistics of one Extractor call = one SEGMENT of crops) runs the SAME kernel
+// twice instead of writing the 50x50x64 pre-BN map (1.3 GB per 4096 crops) to HBM and reading it back twice:
+// MODE 1: statistics only -- per-(segment, channel) sum and sum of squares of conv + bias over the 50x50 outputs (each counted
+//         once: the interior 10x10 of a block's 11x11 tile), accumulated in registers across the CTA's tiles and flushed with
+//         double atomics when the segment changes; nothing else is written.
+// MODE 2: conv -> per-segment scale / shift (vcb_bn_seg_finalize: gamma / sqrt(var + eps), bias and mean folded into the shift)
+//         -> ReLU -> max-pool.  The stem conv is 1 % of the network's FLOPs, so computing it twice is cheaper than the traffic.
+// MODE 1 / 2 give every CTA a CONTIGUOUS range of tiles (crops), so a segment change is rare.
+template <int MODE>
+__global__ void __launch_bounds__(kStemThreads, MODE == 1 ? 1 : 2)
 reid_stem_pool_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ bias,
-                      __half* __restrict__ out, int num_tiles, KernelFault* fault) {
+                      __half* __restrict__ out, int num_tiles, KernelFault* fault, const int* __restrict__ seg_of_crop,
+                      double* __restrict__ sums, const float* __restrict__ affine) {
+  // tile walk: strided (MODE 0) or a contiguous range per CTA
+  const int per_cta = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t_begin = MODE == 0 ? (int)blockIdx.x : (int)blockIdx.x * per_cta;
+  const int t_end = MODE == 0 ? num_tiles : min(num_tiles, t_begin + per_cta);
+  const int t_step = MODE == 0 ? (int)gridDim.x : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -150,7 +166,7 @@ reid_stem_pool_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_arrive_expect_tx(w_bar, 4096u);
       tma_load_2d(&tmap_w, w_bar, w_smem, 0, 0);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
         const int st = it % kStemStages;
         mbar_wait(empty_bar(st), ((it / kStemStages) & 1u) ^ 1u, fault, FAULT_EMPTY_WAIT, 500 + st);
         mbar_arrive_expect_tx(full_bar(st), (uint32_t)kStemTileBytes);
@@ -164,7 +180,7 @@ reid_stem_pool_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const uint64_t w_desc = desc_hi | (uint64_t)((w_smem & 0x3FFFF) >> 4);
       mbar_wait(w_bar, 0u, fault, FAULT_FULL_WAIT, 510);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
         const int st = it % kStemStages;
         const uint32_t acc = it % kStemAccs;
         mbar_wait(tempty_bar(acc), ((it / kStemAccs) & 1u) ^ 1u, fault, FAULT_TMEM_EMPTY_WAIT, 520 + (int)acc);
@@ -179,19 +195,60 @@ reid_stem_pool_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       }
     }
   } else {
-    // ---- epilogue + pooling (256 threads)
+    // ---- epilogue (256 threads)
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;                       // GEMM row = position ti*11 + tj of the 11x11 conv tile
     const int ti = row / 11, tj = row - ti * 11;
     const int sw = row & 7;
-    float bv[32];
+    float* scratch = reinterpret_cast<float*>(stage_gen);                // 32 KiB: [128 rows][64 channels] fp32 (MODE 1 flush)
+    float* aff_s = bias_s + kStemN;                                        // MODE 2: [64][2] scale, shift of the current segment
+    float bv[MODE == 2 ? 1 : 32];
+    if (MODE != 2) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) bv[i] = bias_s[half * 32 + i];
+      for (int i = 0; i < 32; ++i) bv[i] = bias_s[half * 32 + i];
+    }
+    float s1[MODE == 1 ? 32 : 1], s2[MODE == 1 ? 32 : 1];
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+    }
+    int cur_seg = -1;
+    // MODE 1: add this CTA's per-thread partial sums of segment `seg` to the global table (all 256 epilogue threads call it)
+    auto flush = [&](int seg) {
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) scratch[row * 64 + ((half * 32 + i + row) & 63)] = pass == 0 ? s1[i] : s2[i];   // skewed: conflict-free
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (threadIdx.x < 64) {
+          const int ch = threadIdx.x;
+          double a = 0.0;
+          for (int r = 0; r < 128; ++r) a += (double)scratch[r * 64 + ((ch + r) & 63)];
+          atomicAdd(sums + ((long long)seg * kStemN + ch) * 2 + pass, a);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+    };
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
       const uint32_t acc = it % kStemAccs;
       const int roi = tile / kStemBlocks, blk = tile - roi * kStemBlocks;
       const int by = blk / 5, bx = blk - by * 5;
+      if (MODE != 0) {
+        const int seg = __ldg(seg_of_crop + roi);
+        if (seg != cur_seg) {                              // CTA-uniform: every thread sees the same tile sequence
+          if (MODE == 1) {
+            if (cur_seg >= 0) flush(cur_seg);
+          } else {
+            asm volatile("bar.sync 2, 256;" ::: "memory");      // everyone is done with the previous segment's table
+            if (threadIdx.x < 128) aff_s[threadIdx.x] = __ldg(affine + (long long)seg * 128 + threadIdx.x);
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+          }
+          cur_seg = seg;
+        }
+      }
       mbar_wait(tfull_bar(acc), (it / kStemAccs) & 1u, fault, FAULT_TMEM_FULL_WAIT, 540 + (int)acc);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + acc * (uint32_t)kStemN + (uint32_t)(half * 32) + ((uint32_t)(q * 32) << 16);
@@ -201,22 +258,37 @@ reid_stem_pool_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(acc));
+      if (MODE == 1) {
+        // every conv output of the crop exactly once: rows 1..10 x columns 1..10 of the 11x11 tile (row 0 / column 0 belong to the
+        // neighbouring block, or are padding)
+        if (row < 121 && ti >= 1 && tj >= 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a = __uint_as_float(v0[i]) + bv[i], b = __uint_as_float(v1[i]) + bv[16 + i];
+            s1[i] += a; s2[i] = fmaf(a, a, s2[i]);
+            s1[16 + i] += b; s2[16 + i] = fmaf(b, b, s2[16 + i]);
+          }
+        }
+        continue;
+      }
       // rows that are padding for the pool (conv row/column -1, rows >= 121) contribute zeros
       const bool valid = row < 121 && !(by == 0 && ti == 0) && !(bx == 0 && tj == 0);
       uint32_t h2[16];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float a = valid ? fmaxf(__uint_as_float(v0[2 * i]) + bv[2 * i], 0.0f) : 0.0f;
-        const float b = valid ? fmaxf(__uint_as_float(v0[2 * i + 1]) + bv[2 * i + 1], 0.0f) : 0.0f;
-        const __half2 t = __floats2half2_rn(a, b);
+      for (int i = 0; i < 16; ++i) {
+        float a, b;
+        const uint32_t* v = i < 8 ? v0 : v1;
+        const int c0 = (i < 8 ? 0 : 16) + 2 * (i & 7);
+        if (MODE == 2) {
+          const float4 k = *reinterpret_cast<const float4*>(aff_s + (half * 32 + c0) * 2);     // scale, shift, scale, shift (broadcast)
+          a = fmaf(__uint_as_float(v[2 * (i & 7)]), k.x, k.y);
+          b = fmaf(__uint_as_float(v[2 * (i & 7) + 1]), k.z, k.w);
+        } else {
+          a = __uint_as_float(v[2 * (i & 7)]) + bv[MODE == 2 ? 0 : c0];
+          b = __uint_as_float(v[2 * (i & 7) + 1]) + bv[MODE == 2 ? 0 : c0 + 1];
+        }
+        const __half2 t = __floats2half2_rn(valid ? fmaxf(a, 0.0f) : 0.0f, valid ? fmaxf(b, 0.0f) : 0.0f);
         h2[i] = *reinterpret_cast<const uint32_t*>(&t);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float a = valid ? fmaxf(__uint_as_float(v1[2 * i]) + bv[16 + 2 * i], 0.0f) : 0.0f;
-        const float b = valid ? fmaxf(__uint_as_float(v1[2 * i + 1]) + bv[16 + 2 * i + 1], 0.0f) : 0.0f;
-        const __half2 t = __floats2half2_rn(a, b);
-        h2[8 + i] = *reinterpret_cast<const uint32_t*>(&t);
       }
       // staged tile: row pitch 128 B (64 channels), 16-byte chunk c stored at (c ^ (row & 7)): conflict-free both ways
       const uint32_t buf = stage0 + (it & 1u) * 16384u;
@@ -248,6 +320,7 @@ reid_stem_pool_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(m);
       }
     }
+    if (MODE == 1 && cur_seg >= 0) flush(cur_seg);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -255,7 +328,7 @@ reid_stem_pool_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 }
 
 constexpr size_t kStemSmemBytes = 1024 + kStemStages * kStemTileBytes + 4096 + 2 * 16384 + 8 * (2 * kStemStages + 2 * kStemAccs + 1) + 16 +
-                                  kStemN * 4 + 64;
+                                  kStemN * 4 + kStemN * 8 + 64;
 
 int roi_stem_patches(const VcbRoiDesc& d, const uint8_t* frames, int fh, int fw, const int* rois, void* patches, cudaStream_t st) {
   if (d.num_rois < 0 || d.out_size != 50 || !frames || !rois || !patches || fh <= 0 || fw <= 0 || ((uintptr_t)patches & 15))
@@ -265,16 +338,45 @@ int roi_stem_patches(const VcbRoiDesc& d, const uint8_t* frames, int fh, int fw,
   return check_cuda(cudaGetLastError(), "roi_stem_patches launch");
 }
 
-int reid_stem_pool(const void* patches, const void* w_packed, const float* bias, void* out, int num_rois, cudaStream_t st) {
+// scale / shift table of the stem's BatchNorm for MODE 2: sums hold the statistics of conv + bias over hw outputs per crop;
+// y = gamma * (conv + bias - mean) / sqrt(var + eps) + beta = conv * scale + (beta + (bias - mean) * scale)
+__global__ void bn_seg_finalize_kernel(const double* __restrict__ sums, const int* __restrict__ seg_crops, int num_seg1, int c, int hw,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ bias, float eps,
+                                       float* __restrict__ affine) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_seg1 * c) return;
+  const int seg = i / c, ch = i - seg * c;
+  const double cnt = (double)seg_crops[seg] * (double)hw;
+  const double mean = cnt > 0 ? sums[(long long)i * 2] / cnt : 0.0;
+  double var = cnt > 0 ? sums[(long long)i * 2 + 1] / cnt - mean * mean : 0.0;
+  if (var < 0) var = 0;
+  const float k = gamma[ch] * (float)(1.0 / sqrt(var + (double)eps));
+  affine[(long long)i * 2] = k;
+  affine[(long long)i * 2 + 1] = beta[ch] + ((bias ? bias[ch] : 0.0f) - (float)mean) * k;
+}
+
+int bn_seg_finalize(const double* sums, const int* seg_crops, int num_seg1, int c, int hw, const float* gamma, const float* beta,
+                    const float* bias, float eps, float* affine, cudaStream_t st) {
+  if (!sums || !seg_crops || !gamma || !beta || !affine || num_seg1 <= 0 || c <= 0 || hw <= 0)
+    return set_error(VCB_ERR_INVALID, "bn_seg_finalize: bad argument");
+  const int total = num_seg1 * c;
+  bn_seg_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(sums, seg_crops, num_seg1, c, hw, gamma, beta, bias, eps, affine);
+  return check_cuda(cudaGetLastError(), "bn_seg_finalize launch");
+}
+
+template <int MODE>
+static int launch_stem(const void* patches, const void* w_packed, const float* bias, void* out, int num_rois, const int* seg_of_crop,
+                       double* sums, const float* affine, cudaStream_t st) {
   int rc = require_init();
   if (rc != VCB_OK) return rc;
-  if (num_rois < 0 || !patches || !w_packed || !bias || !out || ((uintptr_t)patches & 15) || ((uintptr_t)w_packed & 15) || ((uintptr_t)out & 15))
-    return set_error(VCB_ERR_INVALID, "reid_stem_pool: bad argument");
+  if (num_rois < 0 || !patches || !w_packed || ((uintptr_t)patches & 15) || ((uintptr_t)w_packed & 15) || ((uintptr_t)out & 15) ||
+      (MODE != 2 && !bias) || (MODE != 1 && !out) || (MODE != 0 && !seg_of_crop) || (MODE == 1 && !sums) || (MODE == 2 && !affine))
+    return set_error(VCB_ERR_INVALID, "reid_stem: bad argument");
   if (num_rois == 0) return VCB_OK;
-  if ((long long)num_rois * kStemBlocks * kStemRows > 0x7fffff00LL) return set_error(VCB_ERR_INVALID, "reid_stem_pool: too many crops");
+  if ((long long)num_rois * kStemBlocks * kStemRows > 0x7fffff00LL) return set_error(VCB_ERR_INVALID, "reid_stem: too many crops");
   static bool attr_set = false;
   if (!attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(reid_stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmemBytes);
+    const cudaError_t e = cudaFuncSetAttribute(reid_stem_pool_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStemSmemBytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(reid stem)");
     attr_set = true;
   }
@@ -300,10 +402,23 @@ int reid_stem_pool(const void* patches, const void* w_packed, const float* bias,
                                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(VCB_ERR_CUDA, "cuTensorMapEncodeTiled(stem weights) failed: %d", (int)r);
   }
-  const int max_ctas = state().num_sms * 2;
+  const int max_ctas = state().num_sms * (MODE == 1 ? 1 : 2);
   const int grid = num_tiles < max_ctas ? num_tiles : max_ctas;
-  reid_stem_pool_kernel<<<grid, kStemThreads, kStemSmemBytes, st>>>(ta, tw, bias, reinterpret_cast<__half*>(out), num_tiles, state().fault_dev);
-  return check_cuda(cudaGetLastError(), "reid_stem_pool launch");
+  reid_stem_pool_kernel<MODE><<<grid, kStemThreads, kStemSmemBytes, st>>>(ta, tw, bias, reinterpret_cast<__half*>(out), num_tiles,
+                                                                         state().fault_dev, seg_of_crop, sums, affine);
+  return check_cuda(cudaGetLastError(), "reid_stem launch");
+}
+
+int reid_stem_pool(const void* patches, const void* w_packed, const float* bias, void* out, int num_rois, cudaStream_t st) {
+  return launch_stem<0>(patches, w_packed, bias, out, num_rois, nullptr, nullptr, nullptr, st);
+}
+int reid_stem_stats(const void* patches, const void* w_packed, const float* bias, int num_rois, const int* seg_of_crop, double* sums,
+                    cudaStream_t st) {
+  return launch_stem<1>(patches, w_packed, bias, nullptr, num_rois, seg_of_crop, sums, nullptr, st);
+}
+int reid_stem_pool_bn(const void* patches, const void* w_packed, const float* affine, const int* seg_of_crop, void* out, int num_rois,
+                      cudaStream_t st) {
+  return launch_stem<2>(patches, w_packed, nullptr, out, num_rois, seg_of_crop, nullptr, affine, st);
 }
 
 }  // namespace vcb

@@ -746,8 +746,6 @@ class ReidEngine:
             with torch.cuda.stream(st):
                 sums.zero_()
         plan.add(zero_sums, "zero BN sums")
-        x0 = buf(REID_SIZE, 16)
-        plan.add(lambda st: ops.roi_resize_norm(rd, cur_[0], cur_[1], cur_[2], self.rois, x0, stream=st), "roi crop+resize+norm")
         bn_i = [0]
 
         def conv_bn(x: TRef, wname, bias_name, bnp, co, k, s, p, act, residual: Optional[TRef], pool=False, flops=None) -> TRef:
@@ -770,8 +768,35 @@ class ReidEngine:
                 stream=st), f"bn apply c={co}" + (" +pool" if pool else ""))
             return y
 
-        cur = conv_bn(TRef(x0, 0, 16), "conv.0.weight", "conv.0.bias", "conv.1", 64, 3, 1, 1, L.ACT_RELU, None, pool=True,
-                      flops=2.0 * nb * 2500 * 64 * 27)
+        stem_flops = 2.0 * nb * 2500 * 64 * 27
+        if self.fused_stem:
+            # the fused stem kernel twice over the same im2col patches (csrc/reid_stem.cu MODE 1 / MODE 2): statistics of conv + bias
+            # per segment, then conv -> per-segment scale / shift -> ReLU -> max-pool.  The 50x50x64 pre-BN map (1.3 GB per 4096
+            # crops, written once and read twice by the three-launch form below) never exists.
+            patches = torch.zeros(nb, 25, 128, 32, dtype=torch.float16, device=dev)
+            if "t:stem_packed" not in wc:
+                wc["t:stem_packed"] = ops.pack_reid_stem_weights(sd["conv.0.weight"].to(device=dev, dtype=torch.float32),
+                                                                 sd["conv.0.bias"].to(device=dev, dtype=torch.float32))
+            wp, bp = wc["t:stem_packed"]
+            affine = torch.zeros(S, 64, 2, dtype=torch.float32, device=dev)
+            g0, b0 = f32("conv.1.weight"), f32("conv.1.bias")
+            cur = TRef(buf(25, 64), 0, 64)
+            sl0 = sums[bn_i[0]]
+            bn_i[0] += 1
+            plan.keep += [patches, affine]
+            plan.add(lambda st: ops.roi_stem_patches(rd, cur_[0], cur_[1], cur_[2], self.rois, patches, stream=st),
+                     "roi crop+resize+norm -> stem patches")
+            plan.add(lambda st: ops.reid_stem_stats(patches, wp, bp, nb, self.seg_of_crop, sl0, stream=st), "stem conv: BN statistics only")
+            plan.add(lambda st: ops.bn_seg_finalize(sl0, self.seg_crops, S, 64, 2500, g0, b0, bp, REID_BN_EPS, affine, stream=st), "bn finalize")
+            plan.conv_flops += stem_flops
+            plan.num_convs += 1
+            plan.add(lambda st, cur=cur: ops.reid_stem_pool_bn(patches, wp, affine, self.seg_of_crop, cur.buf, nb, stream=st),
+                     f"stem conv3x3 3->64 + BN(train) + ReLU + maxpool3x3s2 (fused) M={nb * 2500}", stem_flops)
+        else:
+            x0 = buf(REID_SIZE, 16)
+            plan.add(lambda st: ops.roi_resize_norm(rd, cur_[0], cur_[1], cur_[2], self.rois, x0, stream=st), "roi crop+resize+norm")
+            cur = conv_bn(TRef(x0, 0, 16), "conv.0.weight", "conv.0.bias", "conv.1", 64, 3, 1, 1, L.ACT_RELU, None, pool=True,
+                          flops=stem_flops)
         for prefix, ci, co, down in REID_BLOCKS:
             s_ = 2 if down else 1
             t = conv_bn(cur, prefix + ".conv1.weight", None, prefix + ".bn1", co, 3, s_, 1, L.ACT_RELU, None)

@@ -125,6 +125,21 @@ def bn_apply(x, c, rows, row_seg, scale, shift, residual, res_pitch, act, y, y_p
                                   L.ptr(residual), res_pitch, act, L.ptr(y), y_pitch, _st(stream)), "vcb_bn_apply")
 
 
+def reid_stem_stats(patches, w_packed, bias, num_rois, seg_of_crop, sums, stream=None) -> None:
+    L.check(L.load().vcb_reid_stem_stats(L.ptr(patches), L.ptr(w_packed), L.ptr(bias), num_rois, L.ptr(seg_of_crop), L.ptr(sums), _st(stream)),
+            "vcb_reid_stem_stats")
+
+
+def bn_seg_finalize(sums, seg_crops, num_seg_plus1, c, hw, gamma, beta, bias, eps, affine, stream=None) -> None:
+    L.check(L.load().vcb_bn_seg_finalize(L.ptr(sums), L.ptr(seg_crops), num_seg_plus1, c, hw, L.ptr(gamma), L.ptr(beta), L.ptr(bias), eps,
+                                         L.ptr(affine), _st(stream)), "vcb_bn_seg_finalize")
+
+
+def reid_stem_pool_bn(patches, w_packed, affine, seg_of_crop, out, num_rois, stream=None) -> None:
+    L.check(L.load().vcb_reid_stem_pool_bn(L.ptr(patches), L.ptr(w_packed), L.ptr(affine), L.ptr(seg_of_crop), L.ptr(out), num_rois,
+                                           _st(stream)), "vcb_reid_stem_pool_bn")
+
+
 def bn_seg_stats_f16(x, c, hw, n, seg_of_crop, sums, stream=None) -> None:
     L.check(L.load().vcb_bn_seg_stats_f16(L.ptr(x), c, hw, n, L.ptr(seg_of_crop), L.ptr(sums), _st(stream)), "vcb_bn_seg_stats_f16")
 
