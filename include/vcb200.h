@@ -238,9 +238,11 @@ int vcb_bn_apply(const float* x, int32_t c, int32_t rows, const int32_t* row_seg
  *   seg_crops:   int32 [num_seg + 1], crops per segment
  *   sums:        double [num_seg + 1][c][2] = per (segment, channel) sum and sum of squares; the caller zeroes it before
  *                vcb_bn_seg_stats_f16, which accumulates into it (x: fp16 [n][hw][c], c = 8 * power of two <= 512)
- * vcb_bn_seg_apply_f16: y = act(x * scale + shift (+ residual)), scale = gamma / sqrt(var + eps) (biased variance),
- * shift = beta - mean * scale; act = VCB_ACT_NONE | VCB_ACT_RELU; pool != 0 additionally applies MaxPool2d(3, 2, padding=1)
- * (model.py:57) to the activated h x w map, y then holds [n][ceil(h/2)][ceil(w/2)] pixels (no residual in that case). */
+ * vcb_bn_seg_finalize (below): sums -> affine fp32 [num_seg + 1][c][2] = scale, shift; scale = gamma / sqrt(var + eps) (biased
+ *                variance), shift = beta - mean * scale (+ an optional conv bias that was NOT part of x: see the fused stem)
+ * vcb_bn_seg_apply_f16: y = act(x * scale[seg] + shift[seg] (+ residual)); act = VCB_ACT_NONE | VCB_ACT_RELU; pool != 0
+ * additionally applies MaxPool2d(3, 2, padding=1) (model.py:57) to the activated h x w map, y then holds
+ * [n][ceil(h/2)][ceil(w/2)] pixels (no residual in that case). */
 /* The fused stem under train-mode BatchNorm, in two passes over the same im2col patches (the 50x50x64 pre-BN map never exists):
  *   vcb_reid_stem_stats    accumulates sum / sum of squares of conv + bias per (segment, channel) into sums[num_seg + 1][64][2]
  *   vcb_bn_seg_finalize    sums -> affine fp32 [num_seg + 1][c][2] = scale, shift with the conv bias and the mean folded into the shift
@@ -252,9 +254,8 @@ int vcb_bn_seg_finalize(const double* sums, const int32_t* seg_crops, int32_t nu
 int vcb_reid_stem_pool_bn(const void* patches, const void* w_packed, const float* affine, const int32_t* seg_of_crop, void* out,
                           int32_t num_rois, vcb_stream_t stream);
 int vcb_bn_seg_stats_f16(const void* x, int32_t c, int32_t hw, int32_t n, const int32_t* seg_of_crop, double* sums, vcb_stream_t stream);
-int vcb_bn_seg_apply_f16(const void* x, int32_t c, int32_t h, int32_t w, int32_t n, const int32_t* seg_of_crop, const int32_t* seg_crops,
-                         const double* sums, const float* gamma, const float* beta, float eps, const void* residual, int32_t res_pitch,
-                         int32_t act, int32_t pool, void* y, int32_t y_pitch, vcb_stream_t stream);
+int vcb_bn_seg_apply_f16(const void* x, int32_t c, int32_t h, int32_t w, int32_t n, const int32_t* seg_of_crop, const float* affine,
+                         const void* residual, int32_t res_pitch, int32_t act, int32_t pool, void* y, int32_t y_pitch, vcb_stream_t stream);
 
 /* ---- whole-path executor: the calls above, issued once on a capturing stream, become one CUDA
  *      graph that is replayed per batch (tensor maps and shapes are baked in as kernel parameters) --- */

@@ -385,6 +385,48 @@ def test_reid_fused_stem_train_mode_bn_matches_torch(lib):
         off += k
 
 
+@pytest.mark.parametrize("c,h,n,seg_sizes,res,pool", [(64, 25, 70, [5, 1, 40, 24], True, False), (512, 4, 300, [64, 64, 64, 64, 44], True, False),
+                                                     (256, 7, 130, [130], False, False), (64, 50, 9, [4, 5], False, True)])
+def test_bn_seg_stats_finalize_apply_match_torch(lib, c, h, n, seg_sizes, res, pool):
+    """train-mode BatchNorm over segments (one reference Extractor call each): vcb_bn_seg_stats_f16 -> vcb_bn_seg_finalize ->
+    vcb_bn_seg_apply_f16 against F.batch_norm(training=True) per segment on the same fp16 tensor; blocks that span several crops
+    and several segments, padding crops, residual add, the pooled stem form."""
+    import torch.nn.functional as F
+    from vehicle_counting_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(c + h)
+    nb = n + 7                                                 # padding crops -> segment index len(seg_sizes)
+    x = (torch.randn(nb, h, h, c, generator=g) * 1.5 + torch.randn(c, generator=g)).half()
+    r = torch.randn(nb, h, h, c, generator=g).half() if res else None
+    gamma = torch.rand(c, generator=g) + 0.5
+    beta = torch.randn(c, generator=g) * 0.2
+    nseg = len(seg_sizes)
+    soc = np.full(nb, nseg, np.int32); soc[:n] = np.repeat(np.arange(nseg), seg_sizes)
+    cnt = np.zeros(nseg + 1, np.int32); cnt[:nseg] = seg_sizes; cnt[nseg] = nb - n
+    xd, soc_d, cnt_d = x.to(DEV), torch.from_numpy(soc).to(DEV), torch.from_numpy(cnt).to(DEV)
+    sums = torch.zeros(nseg + 1, c, 2, dtype=torch.float64, device=DEV)
+    aff = torch.zeros(nseg + 1, c, 2, dtype=torch.float32, device=DEV)
+    ho = (h + 1) // 2 if pool else h
+    y = torch.zeros(nb, ho, ho, c, dtype=torch.float16, device=DEV)
+    ops.bn_seg_stats_f16(xd, c, h * h, nb, soc_d, sums)
+    ops.bn_seg_finalize(sums, cnt_d, nseg + 1, c, h * h, gamma.to(DEV), beta.to(DEV), None, 1e-5, aff)
+    ops.bn_seg_apply_f16(xd, c, h, h, nb, soc_d, aff, None if r is None else r.to(DEV), c if res else 0, L.ACT_RELU, 1 if pool else 0, y, c)
+    torch.cuda.synchronize()
+    off = 0
+    for si, k in enumerate(seg_sizes):
+        xs = x[off:off + k].float().permute(0, 3, 1, 2)
+        np.testing.assert_allclose(sums[si, :, 0].cpu().numpy(), xs.double().sum((0, 2, 3)).numpy(), rtol=1e-5, atol=1e-2)
+        np.testing.assert_allclose(sums[si, :, 1].cpu().numpy(), (xs.double() ** 2).sum((0, 2, 3)).numpy(), rtol=1e-5, atol=1e-2)
+        ref = F.batch_norm(xs, None, None, gamma, beta, True, 0.0, 1e-5)
+        if res:
+            ref = ref + r[off:off + k].float().permute(0, 3, 1, 2)
+        ref = F.relu(ref)
+        if pool:
+            ref = F.max_pool2d(ref, 3, 2, 1)
+        err = (y[off:off + k].float().cpu() - ref.permute(0, 2, 3, 1)).abs().max().item()
+        assert err <= 3e-3 * max(1.0, ref.abs().max().item()), (si, err)
+        off += k
+
+
 def lib_fault():
     from vehicle_counting_b200 import _lib as L
     return L.last_fault()

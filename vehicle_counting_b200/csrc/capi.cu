@@ -22,7 +22,7 @@ int avgpool_l2norm(const void*, int, int, int, int, float*, cudaStream_t);
 int bn_train_stats(const float*, int, const int*, int, const float*, const float*, float, float*, float*, cudaStream_t);
 int bn_apply(const float*, int, int, const int*, const float*, const float*, const void*, int, int, void*, int, cudaStream_t);
 int bn_seg_stats_f16(const void*, int, int, int, const int*, double*, cudaStream_t);
-int bn_seg_apply_f16(const void*, int, int, int, int, const int*, const int*, const double*, const float*, const float*, float, const void*, int, int, int, void*, int, cudaStream_t);
+int bn_seg_apply_f16(const void*, int, int, int, int, const int*, const float*, const void*, int, int, int, void*, int, cudaStream_t);
 int detect_decode(const VcbDetectDesc&, float*, float*, int*, int*, int*, cudaStream_t);
 int nms(const VcbNmsDesc&, const float*, const float*, const int*, const int*, const int*, unsigned long long*, float*, int*,
         cudaStream_t);
@@ -266,12 +266,10 @@ int vcb_bn_seg_stats_f16(const void* x, int32_t c, int32_t hw, int32_t n, const 
   const int rc = require_init(); if (rc) return rc;
   return bn_seg_stats_f16(x, c, hw, n, seg_of_crop, sums, (cudaStream_t)st);
 }
-int vcb_bn_seg_apply_f16(const void* x, int32_t c, int32_t h, int32_t w, int32_t n, const int32_t* seg_of_crop, const int32_t* seg_crops,
-                         const double* sums, const float* gamma, const float* beta, float eps, const void* residual, int32_t res_pitch,
-                         int32_t act, int32_t pool, void* y, int32_t y_pitch, vcb_stream_t st) {
+int vcb_bn_seg_apply_f16(const void* x, int32_t c, int32_t h, int32_t w, int32_t n, const int32_t* seg_of_crop, const float* affine,
+                         const void* residual, int32_t res_pitch, int32_t act, int32_t pool, void* y, int32_t y_pitch, vcb_stream_t st) {
   const int rc = require_init(); if (rc) return rc;
-  return bn_seg_apply_f16(x, c, h, w, n, seg_of_crop, seg_crops, sums, gamma, beta, eps, residual, res_pitch, act, pool, y, y_pitch,
-                          (cudaStream_t)st);
+  return bn_seg_apply_f16(x, c, h, w, n, seg_of_crop, affine, residual, res_pitch, act, pool, y, y_pitch, (cudaStream_t)st);
 }
 
 // ---- CUDA graph capture ------------------------------------------------------------------------

@@ -477,20 +477,36 @@ int bn_apply(const float* x, int c, int rows, const int* row_seg, const float* s
 // bytes per element instead of the 4 + 4 + 4 + 2 of the fp32 path above; both kernels take device-resident segment tables, so
 // the whole pass is a replayable CUDA graph.  sums: double [num_seg + 1][c][2] (sum, sum of squares), zeroed by the caller.
 // grid = crops; block = 256 threads = (c / 8 channel vectors) x row lanes.
-__global__ void __launch_bounds__(256) bn_seg_stats_f16_kernel(const uint4* __restrict__ x, int c8, int hw, const int* __restrict__ seg_of_crop,
-                                                                double* __restrict__ sums) {
+__global__ void __launch_bounds__(256) bn_seg_stats_f16_kernel(const uint4* __restrict__ x, int c8, int hw, int n, int cpb,
+                                                                const int* __restrict__ seg_of_crop, double* __restrict__ sums) {
+  // A block walks `cpb` consecutive crops (>= ~128 KiB of data) and keeps its partial sums in registers while the segment stays
+  // the same: one flush (shared-memory reduction + c * 2 fp64 atomics) per segment per block instead of per crop -- the deep
+  // layers (16-49 pixels per crop, 256-512 channels) were bound by their 4 M atomics per launch (profiles/r02_train_bn.md).
   __shared__ float red[256 * 16];
-  const int crop = blockIdx.x;
   const int lanes = 256 / c8;                       // row lanes (c8 is a power of two <= 64)
   const int cv = threadIdx.x % c8, rl = threadIdx.x / c8;
   float a[8], b[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { a[k] = 0.f; b[k] = 0.f; }
-  const uint4* base = x + (long long)crop * hw * c8;
-  if (rl < lanes) {
-    // four rows per trip: four independent 16-byte loads in flight per thread (the kernel is a pure HBM stream; one load per
-    // trip left it at ~49 % of the copy bandwidth, profiles/r02_train_bn.md)
-    for (int r0 = rl; r0 < hw; r0 += 4 * lanes) {
+  const int crop0 = blockIdx.x * cpb, crop1 = min(n, crop0 + cpb);
+  int cur = crop0 < n ? seg_of_crop[crop0] : -1;
+  auto flush = [&](int seg) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { red[threadIdx.x * 16 + k] = a[k]; red[threadIdx.x * 16 + 8 + k] = b[k]; a[k] = 0.f; b[k] = 0.f; }
+    __syncthreads();
+    for (int t = threadIdx.x; t < c8 * 16; t += 256) {      // value t of the block: (channel vector, slot) = (t / 16, t % 16)
+      const int v = t >> 4, slot = t & 15;
+      double acc = 0.0;
+      for (int l = 0; l < lanes; ++l) acc += (double)red[(l * c8 + v) * 16 + slot];
+      atomicAdd(sums + ((long long)seg * (c8 * 8) + v * 8 + (slot & 7)) * 2 + (slot >> 3), acc);
+    }
+  };
+  for (int crop = crop0; crop < crop1; ++crop) {
+    const int seg = seg_of_crop[crop];
+    if (seg != cur) { flush(cur); cur = seg; }
+    const uint4* base = x + (long long)crop * hw * c8;
+    for (int r0 = rl; r0 < hw; r0 += 4 * lanes) {           // four independent 16-byte loads in flight per thread
       uint4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -509,44 +525,21 @@ __global__ void __launch_bounds__(256) bn_seg_stats_f16_kernel(const uint4* __re
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { red[threadIdx.x * 16 + k] = a[k]; red[threadIdx.x * 16 + 8 + k] = b[k]; }
-  __syncthreads();
-  // thread t < c8 * 16 finishes value t of the crop: (channel vector, slot) = (t / 16, t % 16)
-  const int seg = seg_of_crop[crop];
-  for (int t = threadIdx.x; t < c8 * 16; t += 256) {
-    const int v = t >> 4, slot = t & 15;
-    double acc = 0.0;
-    for (int l = 0; l < lanes; ++l) acc += (double)red[(l * c8 + v) * 16 + slot];
-    const int ch = v * 8 + (slot & 7);
-    atomicAdd(sums + ((long long)seg * (c8 * 8) + ch) * 2 + (slot >> 3), acc);
-  }
+  if (cur >= 0) flush(cur);
 }
 
-// y(fp16, pitch) = act(x * scale[seg] + shift[seg] (+ residual)) with scale / shift derived in the block from the segment sums
-// (BatchNorm2d training mode: biased variance, eps).  pool != 0: the 3x3 / stride 2 / pad 1 max-pool of model.py:57 applied to
-// the normalised, activated map (h x w -> ceil(h/2) x ceil(w/2)); the stem's 50x50x64 map is then never written.
-__global__ void __launch_bounds__(256) bn_seg_apply_f16_kernel(const uint4* __restrict__ x, int c8, int h, int w, const int* __restrict__ seg_of_crop,
-                                                                const int* __restrict__ seg_crops, const double* __restrict__ sums,
-                                                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+// y(fp16, pitch) = act(x * scale[seg] + shift[seg] (+ residual)), scale / shift from the table vcb_bn_seg_finalize wrote
+// (BatchNorm2d training mode: biased variance, eps).  A block walks `cpb` consecutive crops and reloads the table row into shared
+// memory only when the segment changes.  pool != 0: the 3x3 / stride 2 / pad 1 max-pool of model.py:57 applied to the normalised,
+// activated map (h x w -> ceil(h/2) x ceil(w/2)).
+__global__ void __launch_bounds__(256) bn_seg_apply_f16_kernel(const uint4* __restrict__ x, int c8, int h, int w, int n, int cpb,
+                                                                const int* __restrict__ seg_of_crop, const float2* __restrict__ affine,
                                                                 const uint4* __restrict__ residual, int res_pitch8, int act, int pool,
                                                                 uint4* __restrict__ y, int y_pitch8) {
   __shared__ float sc[512], sh[512];
-  const int crop = blockIdx.x;
   const int c = c8 * 8, hw = h * w;
-  const int seg = seg_of_crop[crop];
-  const double cnt = (double)seg_crops[seg] * (double)hw;
-  for (int ch = threadIdx.x; ch < c; ch += 256) {
-    const double s1 = sums[((long long)seg * c + ch) * 2], s2 = sums[((long long)seg * c + ch) * 2 + 1];
-    const double mean = cnt > 0 ? s1 / cnt : 0.0;
-    double var = cnt > 0 ? s2 / cnt - mean * mean : 0.0;
-    if (var < 0) var = 0;
-    const float k = gamma[ch] * (float)(1.0 / sqrt(var + (double)eps));
-    sc[ch] = k;
-    sh[ch] = beta[ch] - (float)mean * k;
-  }
-  __syncthreads();
-  const uint4* xb = x + (long long)crop * hw * c8;
+  const int crop0 = blockIdx.x * cpb, crop1 = min(n, crop0 + cpb);
+  int cur = -1;
   auto norm8 = [&](const uint4& v, int cv, float* f) {
     const __half2* hh = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
@@ -556,78 +549,101 @@ __global__ void __launch_bounds__(256) bn_seg_apply_f16_kernel(const uint4* __re
       f[2 * k + 1] = fmaf(t.y, sc[cv * 8 + 2 * k + 1], sh[cv * 8 + 2 * k + 1]);
     }
   };
-  if (!pool) {
-    const int total = hw * c8;
-    for (int i = threadIdx.x; i < total; i += 256) {
-      const int r = i / c8, cv = i - r * c8;
-      float f[8];
-      norm8(__ldg(xb + i), cv, f);
-      const long long row = (long long)crop * hw + r;
-      if (residual != nullptr) {
-        const uint4 rv = __ldg(residual + row * res_pitch8 + cv);
-        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const float2 t = __half22float2(rh[k]); f[2 * k] += t.x; f[2 * k + 1] += t.y; }
+  for (int crop = crop0; crop < crop1; ++crop) {
+    const int seg = seg_of_crop[crop];
+    if (seg != cur) {                                     // block-uniform
+      __syncthreads();
+      for (int ch = threadIdx.x; ch < c; ch += 256) {
+        const float2 k = __ldg(affine + (long long)seg * c + ch);
+        sc[ch] = k.x; sh[ch] = k.y;
       }
-      if (act == VCB_ACT_RELU) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
-      }
-      uint4 o;
-      __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
-      y[row * y_pitch8 + cv] = o;
+      __syncthreads();
+      cur = seg;
     }
-  } else {
-    const int ho = (h + 1) / 2, wo = (w + 1) / 2;
-    const int total = ho * wo * c8;
-    for (int i = threadIdx.x; i < total; i += 256) {
-      const int cv = i % c8, pq = i / c8;
-      const int oy = pq / wo, ox = pq - oy * wo;
-      float m[8];
+    const uint4* xb = x + (long long)crop * hw * c8;
+    if (!pool) {
+      const int total = hw * c8;
+      for (int i = threadIdx.x; i < total; i += 256) {
+        const int r = i / c8, cv = i - r * c8;
+        float f[8];
+        norm8(__ldg(xb + i), cv, f);
+        const long long row = (long long)crop * hw + r;
+        if (residual != nullptr) {
+          const uint4 rv = __ldg(residual + row * res_pitch8 + cv);
+          const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) m[k] = -3.0e38f;
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = 2 * oy + dy;
-        if ((unsigned)yy >= (unsigned)h) continue;
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int xx = 2 * ox + dx;
-          if ((unsigned)xx >= (unsigned)w) continue;
-          float f[8];
-          norm8(__ldg(xb + (long long)(yy * w + xx) * c8 + cv), cv, f);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], act == VCB_ACT_RELU ? fmaxf(f[k], 0.0f) : f[k]);
+          for (int k = 0; k < 4; ++k) { const float2 t = __half22float2(rh[k]); f[2 * k] += t.x; f[2 * k + 1] += t.y; }
         }
-      }
-      // rounding to fp16 is monotonic, so the rounded maximum equals the maximum of the rounded (stored) activations
-      uint4 o;
-      __half2* oh = reinterpret_cast<__half2*>(&o);
+        if (act == VCB_ACT_RELU) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(m[2 * k], m[2 * k + 1]);
-      y[((long long)crop * ho * wo + pq) * y_pitch8 + cv] = o;
+          for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+        y[row * y_pitch8 + cv] = o;
+      }
+    } else {
+      const int ho = (h + 1) / 2, wo = (w + 1) / 2;
+      const int total = ho * wo * c8;
+      for (int i = threadIdx.x; i < total; i += 256) {
+        const int cv = i % c8, pq = i / c8;
+        const int oy = pq / wo, ox = pq - oy * wo;
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = -3.0e38f;
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = 2 * oy + dy;
+          if ((unsigned)yy >= (unsigned)h) continue;
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = 2 * ox + dx;
+            if ((unsigned)xx >= (unsigned)w) continue;
+            float f[8];
+            norm8(__ldg(xb + (long long)(yy * w + xx) * c8 + cv), cv, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], act == VCB_ACT_RELU ? fmaxf(f[k], 0.0f) : f[k]);
+          }
+        }
+        // rounding to fp16 is monotonic, so the rounded maximum equals the maximum of the rounded (stored) activations
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(m[2 * k], m[2 * k + 1]);
+        y[((long long)crop * ho * wo + pq) * y_pitch8 + cv] = o;
+      }
     }
   }
+}
+
+static int crops_per_block(int n, int hw, int c) {
+  long long per_crop = (long long)hw * c * 2;
+  int cpb = (int)(131072 / (per_crop > 0 ? per_crop : 1));
+  if (cpb < 1) cpb = 1;
+  if (cpb > 32) cpb = 32;
+  while (cpb > 1 && (n + cpb - 1) / cpb < 2 * 148) cpb >>= 1;       // keep at least two blocks per SM
+  return cpb;
 }
 
 int bn_seg_stats_f16(const void* x, int c, int hw, int n, const int* seg_of_crop, double* sums, cudaStream_t st) {
   const int c8 = c / 8;
   if (!x || !seg_of_crop || !sums || n <= 0 || hw <= 0 || c <= 0 || (c & 7) || c8 > 64 || (c8 & (c8 - 1)) || ((uintptr_t)x & 15))
     return set_error(VCB_ERR_INVALID, "bn_seg_stats_f16: bad argument (c must be 8 * a power of two, <= 512)");
-  bn_seg_stats_f16_kernel<<<n, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), c8, hw, seg_of_crop, sums);
+  const int cpb = crops_per_block(n, hw, c);
+  bn_seg_stats_f16_kernel<<<(n + cpb - 1) / cpb, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), c8, hw, n, cpb, seg_of_crop, sums);
   return check_cuda(cudaGetLastError(), "bn_seg_stats_f16 launch");
 }
 
-int bn_seg_apply_f16(const void* x, int c, int h, int w, int n, const int* seg_of_crop, const int* seg_crops, const double* sums,
-                     const float* gamma, const float* beta, float eps, const void* residual, int res_pitch, int act, int pool, void* y,
-                     int y_pitch, cudaStream_t st) {
-  if (!x || !seg_of_crop || !seg_crops || !sums || !gamma || !beta || !y || n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c & 7) || c > 512 ||
-      (y_pitch & 7) || (residual && (res_pitch & 7)) || ((uintptr_t)x & 15) || ((uintptr_t)y & 15) || ((uintptr_t)residual & 15) ||
+int bn_seg_apply_f16(const void* x, int c, int h, int w, int n, const int* seg_of_crop, const float* affine, const void* residual,
+                     int res_pitch, int act, int pool, void* y, int y_pitch, cudaStream_t st) {
+  if (!x || !seg_of_crop || !affine || !y || n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c & 7) || c > 512 || (y_pitch & 7) ||
+      (residual && (res_pitch & 7)) || ((uintptr_t)x & 15) || ((uintptr_t)y & 15) || ((uintptr_t)residual & 15) || ((uintptr_t)affine & 7) ||
       (pool && residual) || (act != VCB_ACT_NONE && act != VCB_ACT_RELU))
     return set_error(VCB_ERR_INVALID, "bn_seg_apply_f16: bad argument");
-  bn_seg_apply_f16_kernel<<<n, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), c / 8, h, w, seg_of_crop, seg_crops, sums, gamma, beta, eps,
-                                             reinterpret_cast<const uint4*>(residual), res_pitch / 8, act, pool, reinterpret_cast<uint4*>(y),
-                                             y_pitch / 8);
+  const int cpb = crops_per_block(n, h * w, c);
+  bn_seg_apply_f16_kernel<<<(n + cpb - 1) / cpb, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), c / 8, h, w, n, cpb, seg_of_crop,
+                                                              reinterpret_cast<const float2*>(affine), reinterpret_cast<const uint4*>(residual),
+                                                              res_pitch / 8, act, pool, reinterpret_cast<uint4*>(y), y_pitch / 8);
   return check_cuda(cudaGetLastError(), "bn_seg_apply_f16 launch");
 }
 

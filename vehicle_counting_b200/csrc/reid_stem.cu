@@ -147,7 +147,7 @@ reid_stem_pool_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x < kStemN) bias_s[threadIdx.x] = __ldg(bias + threadIdx.x);
+  if (MODE != 2 && threadIdx.x < kStemN) bias_s[threadIdx.x] = __ldg(bias + threadIdx.x);      // MODE 2: the bias lives in the shift
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStemStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < kStemAccs; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
@@ -201,7 +201,8 @@ reid_stem_pool_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const int ti = row / 11, tj = row - ti * 11;
     const int sw = row & 7;
     float* scratch = reinterpret_cast<float*>(stage_gen);                // 32 KiB: [128 rows][64 channels] fp32 (MODE 1 flush)
-    float* aff_s = bias_s + kStemN;                                        // MODE 2: [64][2] scale, shift of the current segment
+    // MODE 2: [64][2] scale, shift of the current segment, read as float4 -> 16-byte aligned (the slack is in kStemSmemBytes)
+    float* aff_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bias_s + kStemN) + 15) & ~(uintptr_t)15);
     float bv[MODE == 2 ? 1 : 32];
     if (MODE != 2) {
 #pragma unroll

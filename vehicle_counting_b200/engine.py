@@ -762,10 +762,14 @@ class ReidEngine:
             plan.add(lambda st, raw=raw, sl=sl: ops.bn_seg_stats_f16(raw.buf, co, osz * osz, nb, self.seg_of_crop, sl, stream=st), f"bn stats c={co}")
             out_sz = (osz + 1) // 2 if pool else osz
             y = TRef(buf(out_sz, co), 0, co)
-            plan.add(lambda st, raw=raw, sl=sl, y=y: ops.bn_seg_apply_f16(
-                raw.buf, co, osz, osz, nb, self.seg_of_crop, self.seg_crops, sl, g, be, REID_BN_EPS,
-                None if residual is None else residual.ptr, 0 if residual is None else residual.pitch, act, 1 if pool else 0, y.buf, co,
-                stream=st), f"bn apply c={co}" + (" +pool" if pool else ""))
+            aff = torch.zeros(S, co, 2, dtype=torch.float32, device=dev)
+            plan.keep += [aff]
+            plan.add(lambda st, sl=sl, aff=aff: ops.bn_seg_finalize(sl, self.seg_crops, S, co, osz * osz, g, be, None, REID_BN_EPS, aff, stream=st),
+                     "bn finalize")
+            plan.add(lambda st, raw=raw, aff=aff, y=y: ops.bn_seg_apply_f16(
+                raw.buf, co, osz, osz, nb, self.seg_of_crop, aff, None if residual is None else residual.ptr,
+                0 if residual is None else residual.pitch, act, 1 if pool else 0, y.buf, co, stream=st),
+                f"bn apply c={co}" + (" +pool" if pool else ""))
             return y
 
         stem_flops = 2.0 * nb * 2500 * 64 * 27

@@ -144,10 +144,9 @@ def bn_seg_stats_f16(x, c, hw, n, seg_of_crop, sums, stream=None) -> None:
     L.check(L.load().vcb_bn_seg_stats_f16(L.ptr(x), c, hw, n, L.ptr(seg_of_crop), L.ptr(sums), _st(stream)), "vcb_bn_seg_stats_f16")
 
 
-def bn_seg_apply_f16(x, c, h, w, n, seg_of_crop, seg_crops, sums, gamma, beta, eps, residual, res_pitch, act, pool, y, y_pitch,
-                     stream=None) -> None:
-    L.check(L.load().vcb_bn_seg_apply_f16(L.ptr(x), c, h, w, n, L.ptr(seg_of_crop), L.ptr(seg_crops), L.ptr(sums), L.ptr(gamma), L.ptr(beta),
-                                          eps, L.ptr(residual), res_pitch, act, pool, L.ptr(y), y_pitch, _st(stream)), "vcb_bn_seg_apply_f16")
+def bn_seg_apply_f16(x, c, h, w, n, seg_of_crop, affine, residual, res_pitch, act, pool, y, y_pitch, stream=None) -> None:
+    L.check(L.load().vcb_bn_seg_apply_f16(L.ptr(x), c, h, w, n, L.ptr(seg_of_crop), L.ptr(affine), L.ptr(residual), res_pitch, act, pool,
+                                          L.ptr(y), y_pitch, _st(stream)), "vcb_bn_seg_apply_f16")
 
 
 # ------------------------------------------------------------------------------------------ detect / nms
