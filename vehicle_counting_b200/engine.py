@@ -153,7 +153,7 @@ class _Plan:
         self.stream = torch.cuda.Stream(device=device)
         # consecutive convolutions walk their tiles in opposite directions, so a layer starts on the part of its input that its
         # producer wrote last (still in the 126 MB L2) instead of the part written first (evicted): +1.5-2.5 % on the whole step
-        # (profiles/r02_ab_switches.md); $VCB_TILE_REV=0 turns it off
+        # (profiles/r02_epilogue_analysis.md); $VCB_TILE_REV=0 turns it off
         self.alternate = os.environ.get("VCB_TILE_REV", "1") == "1"
         self._rev = False
 
@@ -235,7 +235,8 @@ class YoloEngine:
         self.batch, self.h, self.w = batch, h, w
         self.conf, self.iou, self.max_det, self.max_wh, self.max_nms = conf, iou, max_det, max_wh, max_nms
         self.name = model_name or infer_model_name(state_dict)
-        self.fp32_logits = fp32_logits
+        # $VCB_FP16_LOGITS=1: Detect logits stored as fp16 (what the reference's autocast path holds) instead of fp32
+        self.fp32_logits = fp32_logits and os.environ.get("VCB_FP16_LOGITS", "0") != "1"
         self.classes = None if classes is None else sorted(int(c) for c in classes)     # upstream non_max_suppression(classes=...)
         self.a_mode = a_mode
         self.fuse_c3 = os.environ.get("VCB_C3_FUSE", "1") != "0"      # C3: cv1|cv2 as one GEMM, bottlenecks in place
@@ -615,7 +616,7 @@ class ReidEngine:
 
     def stage_frame_list(self, frames: Sequence[np.ndarray]) -> torch.Tensor:
         """stage_frames for a list of equally sized HWC uint8 frames (gathered into the pinned buffer by a thread pool)"""
-        from .hostcopy import copy_frames
+        from .hostcopy import upload_frames
         key = (len(frames),) + tuple(frames[0].shape[:2])
         if key not in self._frame_bufs:
             if len(self._frame_bufs) >= 4:
@@ -624,9 +625,7 @@ class ReidEngine:
                                      torch.empty(key + (3,), dtype=torch.uint8, device=self.device))
         pinned, dev = self._frame_bufs[key]
         self.stream.synchronize()
-        copy_frames(pinned.numpy(), frames)
-        with torch.cuda.stream(self.stream):
-            dev.copy_(pinned, non_blocking=True)
+        upload_frames(pinned, dev, frames, self.stream)         # gather of chunk i+1 overlaps the H2D of chunk i
         return dev
 
     def atlas(self, nbytes: int) -> Tuple[torch.Tensor, torch.Tensor]:

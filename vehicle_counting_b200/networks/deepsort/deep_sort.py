@@ -88,19 +88,16 @@ class Extractor:
         reference rule, all crops go through ONE engine pass (train-mode BatchNorm: one statistics segment per frame = one
         reference call per frame) and the embeddings come back as one float32 [n_i, 512] array per frame."""
         h, w = frames[0].shape[:2]
-        rois, seg = [], []
-        for i, b in enumerate(boxes_xyxy):
-            b = np.asarray(b, np.float64).reshape(-1, 4)
-            bw, bh = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
-            cx, cy = b[:, 0] + bw / 2, b[:, 1] + bh / 2
-            # deep_sort.py:89-95: int() truncation (towards zero) of centre -/+ half size, clipped to the frame
-            x1 = np.maximum(np.trunc(cx - bw / 2).astype(np.int64), 0); x2 = np.minimum(np.trunc(cx + bw / 2).astype(np.int64), w - 1)
-            y1 = np.maximum(np.trunc(cy - bh / 2).astype(np.int64), 0); y2 = np.minimum(np.trunc(cy + bh / 2).astype(np.int64), h - 1)
-            if ((x2 <= x1) | (y2 <= y1)).any():
-                raise ValueError("empty crop (the reference fails inside cv2.resize here)")
-            rois.append(np.stack([np.full(len(b), i, np.int64), x1, y1, x2, y2], 1))
-            seg.append(len(b))
-        rois = np.concatenate(rois, 0).astype(np.int32)
+        seg = [len(b) for b in boxes_xyxy]
+        b = np.concatenate([np.asarray(x, np.float64).reshape(-1, 4) for x in boxes_xyxy], 0)
+        bw, bh = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+        cx, cy = b[:, 0] + bw / 2, b[:, 1] + bh / 2
+        # deep_sort.py:89-95: int() truncation (towards zero) of centre -/+ half size, clipped to the frame
+        x1 = np.maximum(np.trunc(cx - bw / 2), 0); x2 = np.minimum(np.trunc(cx + bw / 2), w - 1)
+        y1 = np.maximum(np.trunc(cy - bh / 2), 0); y2 = np.minimum(np.trunc(cy + bh / 2), h - 1)
+        if ((x2 <= x1) | (y2 <= y1)).any():
+            raise ValueError("empty crop (the reference fails inside cv2.resize here)")
+        rois = np.stack([np.repeat(np.arange(len(seg)), seg), x1, y1, x2, y2], 1).astype(np.int32)
         n = len(rois)
         eng = self.engine
         if n > eng.capacity:

@@ -20,7 +20,7 @@ from torch import nn
 
 from .. import ops
 from ..engine import YoloEngine
-from ..hostcopy import copy_frames
+from ..hostcopy import copy_frames, upload_frames
 from ..weights import load_yolov5_checkpoint, synth_yolov5_state_dict
 
 COCO_NAMES = ['person', 'bicycle', 'car', 'motorcycle', 'airplane', 'bus', 'train', 'truck', 'boat', 'traffic light',
@@ -160,11 +160,9 @@ class YoloBackbone(BaseBackbone):
                 self._pinned[key] = torch.empty(len(imgs), h0, w0, 3, dtype=torch.uint8).pin_memory()
                 self._raw_dev[key] = torch.empty(len(imgs), h0, w0, 3, dtype=torch.uint8, device=eng.frames.device)
             host, raw = self._pinned[key], self._raw_dev[key]
-            copy_frames(host.numpy(), imgs)
             dh, dw = (h1 - h0 // 2) / 2, (w1 - w0 // 2) / 2
             top, left = int(round(dh - 0.1)), int(round(dw - 0.1))
-            with torch.cuda.stream(eng.plan.stream):
-                raw.copy_(host, non_blocking=True)
+            upload_frames(host, raw, imgs, eng.plan.stream)
             ops.letterbox_half(raw, len(imgs), h0, w0, eng.frames, h1, w1, top, left, 114, stream=eng.plan.stream)
         elif all(s == shape0[0] for s in shape0) and (h0, w0) != (h1, w1) and os.environ.get("VCB_DEVICE_LETTERBOX", "1") != "0":
             # same-size frames at any other ratio: raw frames go up, cv2's fixed-point bilinear + the 114 border run on the device
@@ -183,19 +181,17 @@ class YoloBackbone(BaseBackbone):
                 self._lb_tables[tkey] = (xt, yt, geo)
             xt, yt, (top, left, nh, nw) = self._lb_tables[tkey]
             host, raw = self._pinned[key], self._raw_dev[key]
-            copy_frames(host.numpy(), imgs)
-            with torch.cuda.stream(eng.plan.stream):
-                raw.copy_(host, non_blocking=True)
+            upload_frames(host, raw, imgs, eng.plan.stream)
             ops.letterbox_bilinear(raw, len(imgs), h0, w0, eng.frames, h1, w1, top, left, nh, nw, xt, yt, 114, stream=eng.plan.stream)
         else:
             host = self._pinned[(len(imgs), h1, w1)]
             if all(im.shape[:2] == (h1, w1) for im in imgs):
-                copy_frames(host.numpy(), imgs)
+                upload_frames(host, eng.frames, imgs, eng.plan.stream)       # gather of chunk i+1 overlaps the H2D of chunk i
             else:
                 hv = host.numpy()
                 for i, im in enumerate(imgs):
                     hv[i] = im if im.shape[:2] == (h1, w1) else _letterbox(im, (h1, w1))
-            eng.upload(host)
+                eng.upload(host)
         eng.forward()
         # the optional class filter (yolo.py:64) runs inside the decode kernel, before the max_nms / max_det cuts
         return eng.download()
@@ -203,14 +199,16 @@ class YoloBackbone(BaseBackbone):
     def detect(self, batch, device=None):
         """networks/yolo.py:68-99"""
         det, cnt = self.detect_raw(batch["imgs"])
+        # the reference round-trips through DataFrame.to_json (10 decimal digits) before np.array; one vectorised pass per batch
+        nmax = int(cnt.max()) if len(cnt) else 0
+        d = np.round(det[:, :nmax].astype(np.float64), 10)
+        xywh = np.concatenate([d[..., :2], d[..., 2:4] - d[..., :2]], -1)
+        cls = det[:, :nmax, 5].astype(np.int64)
         out = []
         for b in range(len(batch["imgs"])):
             n = int(cnt[b])
             if n > 0:
-                # the reference round-trips through DataFrame.to_json (10 decimal digits) before np.array
-                d = np.round(det[b, :n].astype(np.float64), 10)
-                boxes = np.stack([d[:, 0], d[:, 1], d[:, 2] - d[:, 0], d[:, 3] - d[:, 1]], 1)
-                out.append({"bboxes": boxes, "classes": det[b, :n, 5].astype(np.int64), "scores": d[:, 4]})
+                out.append({"bboxes": xywh[b, :n].copy(), "classes": cls[b, :n].copy(), "scores": d[b, :n, 4].copy()})
             else:
                 out.append({"bboxes": np.array(()), "classes": np.array(()), "scores": np.array(())})
         return out
