@@ -196,6 +196,7 @@ typedef struct VcbRoiDesc {
   int32_t out_size;        /* 50 */
   float mean[3], inv_std[3];   /* applied to channel 0,1,2 of the stored frame order */
   int32_t out_channels;    /* channel pitch of `out`: 4 (default when 0), 8 or 16; channels >= 3 are written as zero */
+  int32_t num_frames;      /* frames behind `frames` (0 = unchecked): a ROI whose frame index is outside [0, num_frames) yields zeros */
 } VcbRoiDesc;
 /* frames: uint8 [*][fh][fw][3]; rois: int32 [num_rois][5] = frame, x1, y1, x2, y2 (already int-truncated and
  * clipped, end exclusive); out: fp16 [num_rois][out][out][out_channels] */

@@ -123,6 +123,12 @@ case("fast-big-stem", mode="tma", n=32, h=320, w=320, k=3, p=1, cin=16, cout=48,
 case("noepi-big-stem", mode="tma", n=32, h=320, w=320, k=3, p=1, cin=16, cout=48, act="silu", epi_direct=3)
 case("noepi-big-1x1-96", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, act="silu", epi_direct=3)
 case("noepi-big-1x1-192", mode="tma", n=64, h=40, w=40, k=1, cin=192, cout=192, act="silu", epi_direct=3)
+case("actprobe-big-1x1-192-none", mode="tma", n=64, h=40, w=40, k=1, cin=192, cout=192, act="none", cta_pair=1)
+case("actprobe-big-1x1-192-relu", mode="tma", n=64, h=40, w=40, k=1, cin=192, cout=192, act="relu", cta_pair=1)
+case("actprobe-big-1x1-192-tanh", mode="tma", n=64, h=40, w=40, k=1, cin=192, cout=192, act="silu_tanh", cta_pair=1)
+case("actprobe-big-1x1-96-none", mode="tma", n=32, h=160, w=160, k=1, cin=96, cout=96, act="none")
+case("actprobe-big-1x1-384-silu", mode="tma", n=64, h=40, w=40, k=1, cin=384, cout=384, act="silu")
+case("actprobe-big-1x1-384-none", mode="tma", n=64, h=40, w=40, k=1, cin=384, cout=384, act="none")
 case("fast-big-stem-tanh", mode="tma", n=32, h=320, w=320, k=3, p=1, cin=16, cout=48, act="silu_tanh")
 
 # row-window stem mode (VCB_A_ROWWIN): W-padded 16-channel input, one tiled TMA box per filter row

@@ -31,7 +31,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(L.DetectLevel) == 48
     assert C.sizeof(L.DetectDesc) == 24 + 4 * 48 + 4 + 32 + 4      # + use_class_mask, class_mask[8], tail padding to 8
     assert C.sizeof(L.NmsDesc) == 24 + 5 * 8
-    assert C.sizeof(L.RoiDesc) == 8 + 24 + 4
+    assert C.sizeof(L.RoiDesc) == 8 + 24 + 4 + 4
 
 
 def test_conv_geometry_host_functions():

@@ -66,7 +66,7 @@ class RoiDesc(C.Structure):
     _fields_ = [
         ("num_rois", C.c_int32), ("out_size", C.c_int32),
         ("mean", C.c_float * 3), ("inv_std", C.c_float * 3),
-        ("out_channels", C.c_int32),
+        ("out_channels", C.c_int32), ("num_frames", C.c_int32),
     ]
 
 

@@ -311,10 +311,24 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const CUtenso
 template <int ACT>
 __device__ __forceinline__ float act_fast(float v) {
   if (ACT == VCB_ACT_SILU) {             // v * 1/(1 + 2^(-v*log2e)); 1+e is in [1, inf] so rcp needs no scaling
+#ifdef VCB_SILU_NR
+    // A/B build (tools/ab_build.sh nr -DVCB_SILU_NR): ONE special-function operation per element.  The reciprocal of d = 1 + e runs on
+    // the FMA pipe: seed from the exponent trick (as_float(0x7EF127EA - as_int(d)), |rel err| <= 5.1e-2), two Newton steps
+    // r <- r * (2 - d * r) (2.6e-3, then 6.6e-6 -- far below the fp16 rounding of the stored result).  The exponent is clamped at
+    // 126 so that d stays finite (v < -87: the result is < 1e-36 either way).
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v * -1.4426950408889634f, 126.0f)));
+    const float d = 1.0f + e;
+    float r = __int_as_float(0x7EF127EA - __float_as_int(d));
+    r = r * fmaf(-d, r, 2.0f);
+    r = r * fmaf(-d, r, 2.0f);
+    return v * r;
+#else
     float e, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return v * r;
+#endif
   }
   if (ACT == VCB_ACT_SILU_TANH) {
     const float h = 0.5f * v;

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) roi_stem_patches_kernel(const VcbRoiDesc 
   const int f = rois[r * 5 + 0], x1 = rois[r * 5 + 1], y1 = rois[r * 5 + 2], x2 = rois[r * 5 + 3], y2 = rois[r * 5 + 4];
   const int cw = x2 - x1, chh = y2 - y1;
   uint4* o = out + (long long)r * kStemBlocks * kStemRows * (kStemK * 2 / 16);
-  if (cw <= 0 || chh <= 0 || x1 < 0 || y1 < 0 || x2 > fw || y2 > fh) {   // the reference would raise inside cv2.resize
+  if (cw <= 0 || chh <= 0 || x1 < 0 || y1 < 0 || x2 > fw || y2 > fh || f < 0 || (d.num_frames > 0 && f >= d.num_frames)) {   // the reference would raise inside cv2.resize
     for (int i = threadIdx.x; i < kStemBlocks * kStemRows * 4; i += blockDim.x) o[i] = make_uint4(0u, 0u, 0u, 0u);
     return;
   }

@@ -22,7 +22,7 @@ __global__ void roi_resize_norm_kernel(const VcbRoiDesc d, const uint8_t* __rest
   const int cw = x2 - x1, chh = y2 - y1;
   const int S = d.out_size;
   uint2* o = out + (long long)r * S * S * U;
-  if (cw <= 0 || chh <= 0 || x1 < 0 || y1 < 0 || x2 > fw || y2 > fh) {   // the reference would raise inside cv2.resize
+  if (cw <= 0 || chh <= 0 || x1 < 0 || y1 < 0 || x2 > fw || y2 > fh || f < 0 || (d.num_frames > 0 && f >= d.num_frames)) {   // the reference would raise inside cv2.resize
     for (int i = threadIdx.x; i < S * S * U; i += blockDim.x) o[i] = make_uint2(0u, 0u);
     return;
   }

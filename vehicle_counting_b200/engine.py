@@ -708,7 +708,7 @@ class ReidEngine:
         plan.add(lambda st, cur=cur: ops.avgpool_l2norm(cur.buf, 512, nb, 16, 512, feats, stream=st), "avgpool+l2norm")
         self.conv_flops_per_crop = plan.conv_flops / nb
         from collections import OrderedDict
-        return {"plan": plan, "graphs": OrderedDict()}
+        return {"plan": plan, "graphs": OrderedDict(), "rd": rd}
 
     # -- train-mode (reference-faithful) plan: conv -> segment statistics -> normalise, graph-captured per bucket ------------
     def _build_train(self, nb: int) -> dict:
@@ -810,7 +810,7 @@ class ReidEngine:
         plan.add(lambda st, cur=cur: ops.avgpool_l2norm(cur.buf, 512, nb, 16, 512, feats, stream=st), "avgpool+l2norm")
         self.conv_flops_per_crop = plan.conv_flops / nb
         from collections import OrderedDict
-        return {"plan": plan, "graphs": OrderedDict()}
+        return {"plan": plan, "graphs": OrderedDict(), "rd": rd}
 
     def _set_segments(self, n: int, nb: int, seg_sizes: Sequence[int]) -> None:
         nseg = len(seg_sizes)
@@ -856,12 +856,13 @@ class ReidEngine:
             ent = self._plans[nb] = self._build_train(nb) if self.bn_mode == "train" else self._build_eval(nb)
         plan = ent["plan"]
         self._cur[0], self._cur[1], self._cur[2] = frames.data_ptr(), int(frames.shape[1]), int(frames.shape[2])
+        ent["rd"].num_frames = int(frames.shape[0])          # bounds for the ROI kernels' frame index (part of the graph key below)
         if not use_graph:
             plan.run_eager(self.stream)
             return self.features[:n]
         # graphs bake the frames pointer and size: one per (pointer, shape), least recently used dropped beyond max_graphs.
         # Callers whose frames live in a fresh tensor every call (Extractor.__call__) pass use_graph=False instead.
-        gkey = (self._cur[0], self._cur[1], self._cur[2])
+        gkey = (self._cur[0], self._cur[1], self._cur[2], int(frames.shape[0]))
         g = ent["graphs"].get(gkey)
         if g is None:
             g = plan.capture()
