@@ -100,6 +100,13 @@ int vcb_conv_pack_weights(const VcbConvDesc* d, const float* w_oihw, const float
                           float* bias_packed, vcb_stream_t stream);
 int vcb_conv2d_fwd(const VcbConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
                    const void* residual, void* y, vcb_stream_t stream);
+/* The same convolution (act = VCB_ACT_NONE, no residual, fp16 output: the pre-BatchNorm tensor of a train-mode BN layer) that ALSO
+ * accumulates, from its epilogue, the per-(segment, channel) sum and sum of squares of the stored outputs into
+ * sums[seg_of_image[n]][cout][2] (double; the caller zeroes it): vcb_bn_seg_stats_f16's result without reading the tensor again.
+ * seg_of_image: int32 [d->n], non-decreasing.  VCB_ERR_INVALID when the geometry does not run the split epilogue (the caller then
+ * uses vcb_conv2d_fwd + vcb_bn_seg_stats_f16). */
+int vcb_conv2d_fwd_stats(const VcbConvDesc* d, const void* x, const void* w_packed, const float* bias_packed, void* y,
+                         const int32_t* seg_of_image, double* sums, vcb_stream_t stream);
 /* output spatial size for a descriptor */
 int vcb_conv_out_hw(const VcbConvDesc* d, int32_t* ho, int32_t* wo);
 
@@ -213,6 +220,20 @@ int vcb_roi_stem_patches(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh,
                          void* patches, vcb_stream_t stream);
 int vcb_reid_stem_pool(const void* patches, const void* w_packed, const float* bias, void* out, int32_t num_rois,
                        vcb_stream_t stream);
+/* The same stem fed straight from the frames (no im2col operand in HBM): crop + resize + normalise (the arithmetic of
+ * vcb_roi_resize_norm, out_size must be 50) happen in shared memory inside the tcgen05 kernel, every CTA owning a contiguous range
+ * of ROIs.  w_packed: fp16 [64][32], k = (r*3+s)*3+c for k < 27, k = 27 / 28 hold the conv bias split into an fp16 head and tail
+ * (the kernel feeds 1.0 there), k >= 29 zero.  out fp16 [num_rois][25][25][64].
+ *   vcb_reid_stem_direct        maxpool3x3s2p1(relu(conv + bias))                                 (BatchNorm folded into w / bias)
+ *   vcb_reid_stem_direct_stats  sums[seg][64][2] += sum / sum of squares of conv + bias           (train-mode BN, pass 1)
+ *   vcb_reid_stem_direct_bn     maxpool3x3s2p1(relu((conv + bias) * scale[seg] + shift[seg]))     (pass 2; affine from
+ *                               vcb_bn_seg_finalize with bias = NULL: the bias is already inside the statistics) */
+int vcb_reid_stem_direct(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, int32_t fw, const int32_t* rois, const void* w_packed,
+                         void* out, vcb_stream_t stream);
+int vcb_reid_stem_direct_stats(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, int32_t fw, const int32_t* rois, const void* w_packed,
+                               const int32_t* seg_of_crop, double* sums, vcb_stream_t stream);
+int vcb_reid_stem_direct_bn(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, int32_t fw, const int32_t* rois, const void* w_packed,
+                            const float* affine, const int32_t* seg_of_crop, void* out, vcb_stream_t stream);
 /* float64 xyxy boxes -> the reference's integer crop rectangle (deep_sort.py:78-95), on device.
  * boxes: double [num][4]; frame_of: int32 [num]; rois out: int32 [num][5] */
 int vcb_boxes_to_rois(const double* boxes_xyxy, const int32_t* frame_of, int32_t num, int32_t fw, int32_t fh,

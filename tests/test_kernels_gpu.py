@@ -385,6 +385,105 @@ def test_reid_fused_stem_train_mode_bn_matches_torch(lib):
         off += k
 
 
+def _stem_case(seed, n, fh=240, fw=320, frames_n=2):
+    from oracle import reid as R
+    from vehicle_counting_b200 import ops, _lib as L
+    rng = np.random.default_rng(seed)
+    frames = torch.from_numpy(rng.integers(0, 256, (frames_n, fh, fw, 3), dtype=np.uint8)).to(DEV)
+    wh = rng.uniform(8, 200, (n, 2)); tl = rng.uniform(0, 1, (n, 2)) * (np.array([fw, fh]) - wh)
+    rois_np = np.concatenate([rng.integers(0, frames_n, (n, 1)), tl, tl + wh], 1).astype(np.int32)
+    rd = L.RoiDesc()
+    rd.num_rois, rd.out_size, rd.out_channels, rd.num_frames = n, 50, 4, frames_n
+    for c in range(3):
+        rd.mean[c] = R.NORM_MEAN[c]; rd.inv_std[c] = 1.0 / R.NORM_STD[c]
+    return rng, frames, rois_np, rd
+
+
+@pytest.mark.parametrize("n", [1, 37, 700])
+def test_reid_direct_stem_matches_torch_on_the_resized_crop(lib, n):
+    """vcb_reid_stem_direct (frames + ROIs -> crop -> conv3x3 3->64 + bias -> ReLU -> maxpool 3/2/1 in ONE kernel, the im2col rows
+    built in shared memory) against torch on the fp16 crop vcb_roi_resize_norm produces, and against the two-kernel form that
+    stages patches in HBM (/root/reference/networks/deepsort/deep/model.py:52-60).  n = 1 (one CTA), 37 (one crop per CTA, a
+    degenerate ROI, a ROI of another frame index out of range) and 700 (several crops per CTA: the double-buffered crop)."""
+    import torch.nn.functional as F
+    from vehicle_counting_b200 import ops
+    rng, frames, rois_np, rd = _stem_case(50 + n, n)
+    fh, fw = 240, 320
+    if n >= 37:
+        rois_np[5] = (0, 10, 10, 10, 30)                         # zero-width crop -> zeros in, bias out
+        rois_np[9, 0] = 7                                        # frame index out of range -> zeros in
+    rois = torch.from_numpy(rois_np).to(DEV)
+    x = torch.zeros(n, 50, 50, 4, dtype=torch.float16, device=DEV)
+    ops.roi_resize_norm(rd, frames, fh, fw, rois, x)
+    g = torch.Generator().manual_seed(3)
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.3)
+    b = torch.randn(64, generator=g) * 0.2
+    wpd = ops.pack_reid_stem_weights_direct(w.to(DEV), b.to(DEV))
+    out = torch.full((n, 25, 25, 64), -5.0, dtype=torch.float16, device=DEV)
+    ops.reid_stem_direct(rd, frames, fh, fw, rois, wpd, out)
+    # the round-2 pair of kernels on the same inputs
+    wp, bp = ops.pack_reid_stem_weights(w.to(DEV), b.to(DEV))
+    patches = torch.zeros(n, 25, 128, 32, dtype=torch.float16, device=DEV)
+    out2 = torch.full((n, 25, 25, 64), -5.0, dtype=torch.float16, device=DEV)
+    ops.roi_stem_patches(rd, frames, fh, fw, rois, patches)
+    ops.reid_stem_pool(patches, wp, bp, out2, n)
+    torch.cuda.synchronize()
+    assert tuple(lib_fault()) == (0, 0, 0, 0)
+    conv = F.conv2d(x[..., :3].float().cpu().permute(0, 3, 1, 2), wp[:, :27].float().cpu().view(64, 3, 3, 3).permute(0, 3, 1, 2), b, 1, 1)
+    ref = F.max_pool2d(F.relu(conv).half().float(), 3, 2, 1).permute(0, 2, 3, 1)
+    got = out.float().cpu()
+    assert (got - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+    # same operands, same products; only the position of the bias in the fp32 sum differs
+    assert (got - out2.float().cpu()).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_reid_direct_stem_train_mode_bn_matches_torch(lib):
+    """vcb_reid_stem_direct_stats + vcb_bn_seg_finalize (bias = NULL: it is inside the statistics) + vcb_reid_stem_direct_bn against
+    F.batch_norm(training=True) per segment on the same fp16 crop; 300 crops so that CTAs own several crops and segment boundaries
+    fall inside a CTA's range."""
+    import torch.nn.functional as F
+    from vehicle_counting_b200 import ops
+    n, nb = 300, 320
+    seg_sizes = [5, 1, 120, 64, 110]
+    rng, frames, rois_np, rd = _stem_case(61, nb)
+    fh, fw = 240, 320
+    rois_np[n:] = 0
+    rois = torch.from_numpy(rois_np).to(DEV)
+    x = torch.zeros(nb, 50, 50, 4, dtype=torch.float16, device=DEV)
+    ops.roi_resize_norm(rd, frames, fh, fw, rois, x)
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(64, 3, 3, 3, generator=g) * 0.3
+    b = torch.randn(64, generator=g) * 0.2
+    gamma = torch.rand(64, generator=g) + 0.5
+    beta = torch.randn(64, generator=g) * 0.1
+    wpd = ops.pack_reid_stem_weights_direct(w.to(DEV), b.to(DEV))
+    nseg = len(seg_sizes)
+    soc = np.full(nb, nseg, np.int32); soc[:n] = np.repeat(np.arange(nseg), seg_sizes)
+    cnt = np.zeros(nseg + 1, np.int32); cnt[:nseg] = seg_sizes; cnt[nseg] = nb - n
+    soc_d, cnt_d = torch.from_numpy(soc).to(DEV), torch.from_numpy(cnt).to(DEV)
+    sums = torch.zeros(nseg + 1, 64, 2, dtype=torch.float64, device=DEV)
+    affine = torch.zeros(nseg + 1, 64, 2, dtype=torch.float32, device=DEV)
+    out = torch.full((nb, 25, 25, 64), -5.0, dtype=torch.float16, device=DEV)
+    ops.reid_stem_direct_stats(rd, frames, fh, fw, rois, wpd, soc_d, sums)
+    ops.bn_seg_finalize(sums, cnt_d, nseg + 1, 64, 2500, gamma.to(DEV), beta.to(DEV), None, 1e-5, affine)
+    ops.reid_stem_direct_bn(rd, frames, fh, fw, rois, wpd, affine, soc_d, out)
+    torch.cuda.synchronize()
+    assert tuple(lib_fault()) == (0, 0, 0, 0)
+    wk = wpd[:, :27].float().cpu().view(64, 3, 3, 3).permute(0, 3, 1, 2)
+    conv = F.conv2d(x[:n, ..., :3].float().cpu().permute(0, 3, 1, 2), wk, b, 1, 1)
+    got_sums = sums.cpu()
+    off = 0
+    for si, k in enumerate(seg_sizes):
+        c_ = conv[off:off + k].double()
+        np.testing.assert_allclose(got_sums[si, :, 0].numpy(), c_.sum((0, 2, 3)).numpy(), rtol=2e-4, atol=5e-2)
+        np.testing.assert_allclose(got_sums[si, :, 1].numpy(), (c_ * c_).sum((0, 2, 3)).numpy(), rtol=2e-4, atol=5e-2)
+        y = F.relu(F.batch_norm(conv[off:off + k], None, None, gamma, beta, True, 0.0, 1e-5))
+        ref = F.max_pool2d(y.half().float(), 3, 2, 1).permute(0, 2, 3, 1)
+        err = (out[off:off + k].float().cpu() - ref).abs().max().item()
+        assert err <= 4e-3 * max(1.0, ref.abs().max().item()), (si, k, err)
+        off += k
+
+
 @pytest.mark.parametrize("c,h,n,seg_sizes,res,pool", [(64, 25, 70, [5, 1, 40, 24], True, False), (512, 4, 300, [64, 64, 64, 64, 44], True, False),
                                                      (256, 7, 130, [130], False, False), (64, 50, 9, [4, 5], False, True)])
 def test_bn_seg_stats_finalize_apply_match_torch(lib, c, h, n, seg_sizes, res, pool):
@@ -497,3 +596,39 @@ def test_letterbox_bilinear_is_bit_identical_to_cv2(lib):
     eng = net._engine(2, 384, 640)
     want = np.stack([NY._letterbox(im, (384, 640)) for im in imgs])
     np.testing.assert_array_equal(eng.frames.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("n,h,cin,cout,k,s,seg_sizes", [(37, 25, 64, 64, 3, 1, [5, 1, 20, 11]), (40, 13, 128, 128, 3, 1, [40]),
+                                                        (300, 4, 256, 512, 3, 1, [64, 64, 64, 64, 44]), (23, 13, 64, 40, 1, 2, [3, 20]),
+                                                        (130, 7, 128, 256, 3, 2, [1] * 130)])
+def test_conv_epilogue_bn_statistics_match_the_statistics_kernel(lib, n, h, cin, cout, k, s, seg_sizes):
+    """vcb_conv2d_fwd_stats: the convolution's epilogue accumulates the train-mode BatchNorm statistics of the fp16 tensor it stores;
+    they must equal what vcb_bn_seg_stats_f16 computes from that tensor (128-row and CTA-pair kernels, tiles that straddle segments,
+    one-crop segments, a cout that is not a multiple of 64, the M tail)."""
+    from vehicle_counting_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(n + cout)
+    x = torch.randn(n, h, h, cin, generator=g).half().to(DEV)
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    b = (torch.randn(cout, generator=g) * 0.3).to(DEV)
+    p = k // 2
+    cp = (cout + 7) // 8 * 8
+    d = ops.make_conv_desc(n, h, h, cin, cout, k, s, p, cout_pitch=cp, act=L.ACT_NONE)
+    ho, wo = ops.conv_out_hw(d)
+    wp, bp = ops.pack_conv_weights(d, w, b)
+    nseg = len(seg_sizes)
+    soc = torch.from_numpy(np.repeat(np.arange(nseg), seg_sizes).astype(np.int32)).to(DEV)
+    y1 = torch.zeros(n, ho, wo, cp, dtype=torch.float16, device=DEV)
+    y2 = torch.zeros_like(y1)
+    sums = torch.zeros(nseg + 1, cout, 2, dtype=torch.float64, device=DEV)
+    ops.conv2d(d, x, wp, bp, y1)
+    ops.conv2d_stats(d, x, wp, bp, y2, soc, sums)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    yf = y1[..., :cout].double().cpu()
+    off = 0
+    for si, kk in enumerate(seg_sizes):
+        blk = yf[off:off + kk]
+        np.testing.assert_allclose(sums[si, :, 0].cpu().numpy(), blk.sum((0, 1, 2)).numpy(), rtol=1e-5, atol=5e-3)
+        np.testing.assert_allclose(sums[si, :, 1].cpu().numpy(), (blk * blk).sum((0, 1, 2)).numpy(), rtol=1e-5, atol=5e-3)
+        off += kk
+    assert (sums[nseg] == 0).all()

@@ -86,6 +86,7 @@ _SIGNATURES = {
     "vcb_conv_packed_sizes": ([C.POINTER(ConvDesc), C.POINTER(_I64), C.POINTER(_I64)], _I32),
     "vcb_conv_pack_weights": ([C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP], _I32),
     "vcb_conv2d_fwd": ([C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP], _I32),
+    "vcb_conv2d_fwd_stats": ([C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP, _VP], _I32),
     "vcb_conv_out_hw": ([C.POINTER(ConvDesc), C.POINTER(_I32), C.POINTER(_I32)], _I32),
     "vcb_frames_to_f16c4": ([_VP, _VP, _I32, _I32, _I32, _VP], _I32),
     "vcb_frames_to_f16_s2d": ([_VP, _VP, _I32, _I32, _I32, _VP], _I32),
@@ -102,6 +103,9 @@ _SIGNATURES = {
     "vcb_boxes_to_rois": ([_VP, _VP, _I32, _I32, _I32, _VP, _VP], _I32),
     "vcb_roi_stem_patches": ([C.POINTER(RoiDesc), _VP, _I32, _I32, _VP, _VP, _VP], _I32),
     "vcb_reid_stem_pool": ([_VP, _VP, _VP, _VP, _I32, _VP], _I32),
+    "vcb_reid_stem_direct": ([C.POINTER(RoiDesc), _VP, _I32, _I32, _VP, _VP, _VP, _VP], _I32),
+    "vcb_reid_stem_direct_stats": ([C.POINTER(RoiDesc), _VP, _I32, _I32, _VP, _VP, _VP, _VP, _VP], _I32),
+    "vcb_reid_stem_direct_bn": ([C.POINTER(RoiDesc), _VP, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP], _I32),
     "vcb_avgpool_l2norm": ([_VP, _I32, _I32, _I32, _I32, _VP, _VP], _I32),
     "vcb_bn_train_stats": ([_VP, _I32, _VP, _I32, _VP, _VP, _F, _VP, _VP, _VP], _I32),
     "vcb_bn_apply": ([_VP, _I32, _I32, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _I32, _VP], _I32),

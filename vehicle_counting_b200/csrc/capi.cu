@@ -33,6 +33,9 @@ int roi_stem_patches(const VcbRoiDesc&, const uint8_t*, int, int, const int*, vo
 int reid_stem_pool(const void*, const void*, const float*, void*, int, cudaStream_t);
 int reid_stem_stats(const void*, const void*, const float*, int, const int*, double*, cudaStream_t);
 int reid_stem_pool_bn(const void*, const void*, const float*, const int*, void*, int, cudaStream_t);
+int reid_stem_direct(const VcbRoiDesc&, const uint8_t*, int, int, const int*, const void*, void*, cudaStream_t);
+int reid_stem_direct_stats(const VcbRoiDesc&, const uint8_t*, int, int, const int*, const void*, const int*, double*, cudaStream_t);
+int reid_stem_direct_bn(const VcbRoiDesc&, const uint8_t*, int, int, const int*, const void*, const float*, const int*, void*, cudaStream_t);
 int bn_seg_finalize(const double*, const int*, int, int, int, const float*, const float*, const float*, float, float*, cudaStream_t);
 
 static thread_local char g_err[512] = "";
@@ -171,6 +174,12 @@ int vcb_conv2d_fwd(const VcbConvDesc* d, const void* x, const void* wp, const fl
   VCB_GUARD(d);
   return conv2d_fwd(*d, x, wp, bp, res, y, (cudaStream_t)st);
 }
+int vcb_conv2d_fwd_stats(const VcbConvDesc* d, const void* x, const void* wp, const float* bp, void* y, const int32_t* seg_of_image,
+                         double* sums, vcb_stream_t st) {
+  VCB_GUARD(d);
+  if (!seg_of_image || !sums) return set_error(VCB_ERR_INVALID, "conv2d_fwd_stats: null segment table / sums");
+  return conv2d_fwd(*d, x, wp, bp, nullptr, y, (cudaStream_t)st, seg_of_image, sums);
+}
 int vcb_frames_to_f16c4(const uint8_t* frames, void* out, int32_t n, int32_t h, int32_t w, vcb_stream_t st) {
   const int rc = require_init(); if (rc) return rc;
   return frames_to_f16c4(frames, out, n, h, w, (cudaStream_t)st);
@@ -229,6 +238,21 @@ int vcb_roi_stem_patches(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh,
 }
 int vcb_reid_stem_pool(const void* patches, const void* w_packed, const float* bias, void* out, int32_t num_rois, vcb_stream_t st) {
   return reid_stem_pool(patches, w_packed, bias, out, num_rois, (cudaStream_t)st);
+}
+int vcb_reid_stem_direct(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, int32_t fw, const int32_t* rois, const void* w_packed,
+                         void* out, vcb_stream_t st) {
+  VCB_GUARD(d);
+  return reid_stem_direct(*d, frames, fh, fw, rois, w_packed, out, (cudaStream_t)st);
+}
+int vcb_reid_stem_direct_stats(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, int32_t fw, const int32_t* rois, const void* w_packed,
+                               const int32_t* seg_of_crop, double* sums, vcb_stream_t st) {
+  VCB_GUARD(d);
+  return reid_stem_direct_stats(*d, frames, fh, fw, rois, w_packed, seg_of_crop, sums, (cudaStream_t)st);
+}
+int vcb_reid_stem_direct_bn(const VcbRoiDesc* d, const uint8_t* frames, int32_t fh, int32_t fw, const int32_t* rois, const void* w_packed,
+                            const float* affine, const int32_t* seg_of_crop, void* out, vcb_stream_t st) {
+  VCB_GUARD(d);
+  return reid_stem_direct_bn(*d, frames, fh, fw, rois, w_packed, affine, seg_of_crop, out, (cudaStream_t)st);
 }
 int vcb_boxes_to_rois(const double* boxes, const int32_t* frame_of, int32_t num, int32_t fw, int32_t fh, int32_t* rois, vcb_stream_t st) {
   const int rc = require_init(); if (rc) return rc;

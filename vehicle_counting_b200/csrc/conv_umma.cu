@@ -100,6 +100,10 @@ struct ConvParams {
   int tile_rev;        // walk the tiles from the last to the first: a layer that starts where its producer stopped finds the
                        // most recently written part of its input still in L2 (the engine alternates the direction per layer)
   unsigned long long a_policy, b_policy;   // L2 cache policies of the activation / weight TMA loads (kL2Evict*)
+  // train-mode BatchNorm statistics from the epilogue (vcb_conv2d_fwd_stats): per-(segment, channel) sum / sum of squares of the
+  // STORED (fp16-rounded) outputs, accumulated into stat_sums[seg][Cout][2]; image n of the batch belongs to segment stat_seg[n]
+  const int* stat_seg;
+  double* stat_sums;
   const __half* x;
   const float* bias;
   const __half* residual;
@@ -621,7 +625,8 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, const CU
 template <int ACT, int RES, bool F32OUT, bool TWO_CTA>
 __device__ __forceinline__ void conv_epilogue_split(const ConvParams& p, const CUtensorMap* tmap_out_ptr, const CUtensorMap* tmap_res_ptr,
                                                     uint32_t tmem_base, uint32_t out_stage, uint32_t bias_smem, uint32_t res_bar0,
-                                                    uint32_t tmem_full0, uint32_t tmem_empty0, int first_tile, int tile_step, int cta_rank) {
+                                                    uint32_t tmem_full0, uint32_t tmem_empty0, int first_tile, int tile_step, int cta_rank,
+                                                    float* stat_scratch) {
   const int total_tiles = TWO_CTA ? p.num_pair_tiles : p.num_tiles;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -641,6 +646,7 @@ __device__ __forceinline__ void conv_epilogue_split(const ConvParams& p, const C
   const bool two_acc = p.acc_stages == 2;
   const int n_tiles = p.n_tiles;
   const int per_img = p.patch_ytiles * p.patch_xsegs;      // row-window mode only
+  if (p.stat_sums != nullptr) stat_scratch[threadIdx.x] = 0.f;      // 256 floats: two groups x 64 columns x 2 statistics
 
   // (tile ordinal, sub-tile) of this group's current item; items alternate between the groups
   int t_idx = (num_sub == 1) ? grp : 0;
@@ -784,6 +790,55 @@ __device__ __forceinline__ void conv_epilogue_split(const ConvParams& p, const C
       if (RES != VCB_RES_NONE && first_tile + nt * tile_step < total_tiles) {
         tma_store_wait_read<0>();                            // same buffer: the store just issued must have read it
         issue_res_load(nt, ns);
+      }
+    }
+    if (ACT == VCB_ACT_NONE && RES == VCB_RES_NONE && !F32OUT && p.stat_sums != nullptr) {
+      // BatchNorm statistics of this 128 x 64 sub-tile, read back from the staged fp16 tile (the values the normalisation pass will
+      // see): thread (column pair cp, row quarter rq) sums 32 rows, the four row quarters meet in shared memory, then ONE fp64 atomic
+      // per (column, statistic).  Tiles that straddle two segments (rare: segment boundaries only) take the per-row path.
+      const int t = threadIdx.x & 127;
+      const int cp = t & 31, rq = t >> 5;
+      const int m0 = m_tile * kBlockM;
+      const int rows_valid = min(kBlockM, p.M - m0);
+      const bool col_ok = 2 * cp < ncols && n_base + col0 + 2 * cp < p.Cout;
+      const uint32_t cbase = stage_buf + (uint32_t)(cp & 3) * 4u;
+      const uint32_t chunk = (uint32_t)(cp >> 2);
+      int seg_a = 0, seg_b = 0;
+      if (rows_valid > 0) {
+        seg_a = __ldg(p.stat_seg + m0 / p.PQ);
+        seg_b = __ldg(p.stat_seg + (m0 + rows_valid - 1) / p.PQ);
+      }
+      const int r_lo = rq * 32, r_hi = min(r_lo + 32, rows_valid);
+      float* scratch = stat_scratch + grp * 128;
+      if (seg_a == seg_b) {
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        if (col_ok) {
+          for (int r = r_lo; r < r_hi; ++r) {
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(cbase + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+            s0 += f.x; s1 += f.y;
+            q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+          }
+          atomicAdd(scratch + 4 * cp + 0, s0); atomicAdd(scratch + 4 * cp + 1, q0);
+          atomicAdd(scratch + 4 * cp + 2, s1); atomicAdd(scratch + 4 * cp + 3, q1);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        {
+          const int c_ = t >> 1, ch = n_base + col0 + c_;          // slot t = column t / 2, statistic t % 2
+          if (rows_valid > 0 && c_ < ncols && ch < p.Cout) atomicAdd(p.stat_sums + ((long long)seg_a * p.Cout + ch) * 2 + (t & 1), (double)scratch[t]);
+          scratch[t] = 0.f;
+        }
+      } else if (col_ok) {
+        const int ch = n_base + col0 + 2 * cp;
+        for (int r = r_lo; r < r_hi; ++r) {
+          uint32_t w;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(cbase + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+          double* dst = p.stat_sums + ((long long)__ldg(p.stat_seg + (m0 + r) / p.PQ) * p.Cout + ch) * 2;
+          atomicAdd(dst + 0, (double)f.x); atomicAdd(dst + 1, (double)f.x * (double)f.x);
+          atomicAdd(dst + 2, (double)f.y); atomicAdd(dst + 3, (double)f.y * (double)f.y);
+        }
       }
     }
     t_idx = nt; sub = ns;
@@ -1019,7 +1074,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp < kEpilogueWarps) {
 #define VCB_EPI_CASE(K, ACT, RES, F32) \
     case K: \
-      if (!M256 && p.epi_split) conv_epilogue_split<ACT, RES, F32, false>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), tmem_empty_bar(0), blockIdx.x, gridDim.x, 0); \
+      if (!M256 && p.epi_split) conv_epilogue_split<ACT, RES, F32, false>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), tmem_empty_bar(0), blockIdx.x, gridDim.x, 0, bias_gen + p.cout_pad); \
       else conv_epilogue_fast<ACT, RES, F32, M256>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), tmem_empty_bar(0)); \
       break;
     if (A_MODE == A_TMA && !M256 && p.a_rowwin && !p.epi_split) {   // 2-D pixel blocks: the patch-mode staging / 4-D store with a dense lattice (Lp = Xs)
@@ -1309,7 +1364,7 @@ conv_umma_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #define VCB_EPI_CASE(K, ACT, RES, F32) \
     case K: \
       if (p.epi_split) conv_epilogue_split<ACT, RES, F32, true>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), \
-                                                                tmem_empty_bar(0), cluster_id, num_clusters, rank); \
+                                                                tmem_empty_bar(0), cluster_id, num_clusters, rank, bias_gen + p.cout_pad); \
       else conv_epilogue_fast<ACT, RES, F32, false, true>(p, &tmap_out, &tmap_res, tmem_base, out_stage, bias_smem, res_bar0, tmem_full_bar(0), \
                                                           tmem_empty_bar(0), cluster_id, num_clusters, rank); \
       break;
@@ -1593,7 +1648,8 @@ struct ConvGeom {
 
 static int conv_geometry(const VcbConvDesc& d_in, ConvGeom& g) {
   VcbConvDesc d = d_in;
-  d.reserved[1] &= 0xff;      // bits 8.. are per-launch flags that do not change the geometry (conv2d_fwd)
+  const bool want_stats = (d_in.reserved[1] & 0x200) != 0;     // internal (vcb_conv2d_fwd_stats): keep to the kernels with the split epilogue
+  d.reserved[1] &= 0xff;      // bit 8 is a per-launch flag that does not change the geometry (conv2d_fwd)
   if (d.n <= 0 || d.h <= 0 || d.w <= 0 || d.cin <= 0 || d.cout <= 0 || d.kh <= 0 || d.kw <= 0 || d.stride <= 0 ||
       d.pad < 0)
     return set_error(VCB_ERR_INVALID, "conv: non-positive dimension");
@@ -1686,12 +1742,12 @@ static int conv_geometry(const VcbConvDesc& d_in, ConvGeom& g) {
   // specialised epilogue: single-CTA TMA kernel with the staged TMA store (any debug value in reserved[0] forces the generic one)
   g.epi_kind = (g.a_mode == A_TMA && d.reserved[0] == 0) ? epi_kind_of(d.act, d.res_mode, d.out_dtype == VCB_F32 ? 1 : 0) : 0;
   const size_t b_total = (size_t)g.total_chunks * g.block_n * g.bk * 2;
-  const size_t tail0 = 1024 /*align slack*/ + 8 * (2 * kMaxStages + 4) + 16 + kBlockM * sizeof(RowInfo) + (size_t)g.cout_pad * 4 + 64;
+  const size_t tail0 = 1024 /*align slack*/ + 8 * (2 * kMaxStages + 4) + 16 + kBlockM * sizeof(RowInfo) + (size_t)g.cout_pad * 4 + 1024 /*BN-statistics scratch*/ + 64;
   g.m256 = 0; g.tile_m = kBlockM; g.b_resident = 0; g.b_res_bytes = 0; g.kchains = 1; g.patch = 0;
   int chosen = 0;
   // ---- patch mode: 3x3/s1/p1 with 64-channel chunks; reserved[3] == 5 forces it, == 1 (or any other forced mode) forbids it
   {
-    const bool can = g.a_mode == A_TMA && !g.rowwin && !g.two_cta && g.epi_kind != 0 && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.pad == 1 && g.bk == 64;
+    const bool can = g.a_mode == A_TMA && !g.rowwin && !want_stats && !g.two_cta && g.epi_kind != 0 && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.pad == 1 && g.bk == 64;
     // automatic for narrow layers (N <= 64) with at least two waves of tiles: measured 4-14 % faster than the 128-row im2col mode
     // (ReID layer 1, YOLOv5m 48->48, YOLOv5s 64->64; profiles/r01_layer_modes.md); wider layers lose (single CTA per SM)
     bool want = can && (d.reserved[3] == 5);
@@ -1921,10 +1977,15 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 }
 
 int conv2d_fwd(const VcbConvDesc& d_in, const void* x, const void* w_packed, const float* bias_packed, const void* residual,
-               void* y, cudaStream_t st) {
+               void* y, cudaStream_t st, const int* stat_seg, double* stat_sums) {
   VcbConvDesc d = d_in;
   const int launch_flags = d.reserved[1] >> 8;      // bit 0: walk the tiles in reverse order
   d.reserved[1] &= 0xff;
+  if (stat_sums != nullptr) {
+    if (stat_seg == nullptr || d.act != VCB_ACT_NONE || d.res_mode != VCB_RES_NONE || d.out_dtype != VCB_F16 || d.reserved[0] != 0)
+      return set_error(VCB_ERR_INVALID, "conv (BN statistics): needs act = none, no residual, fp16 output and a segment table");
+    d.reserved[1] |= 0x200;                         // geometry: stay on the kernels that run the split epilogue
+  }
   int rc = require_init();
   if (rc != VCB_OK) return rc;
   ConvGeom g;
@@ -1972,6 +2033,10 @@ int conv2d_fwd(const VcbConvDesc& d_in, const void* x, const void* w_packed, con
                    (num_sub >= 2 || g.acc_stages == 2)) ? 1 : 0;
     p.epi_empty_count = (p.epi_split && num_sub == 1 ? kNumEpilogueThreads / 2 : kNumEpilogueThreads) * (g.two_cta ? 2 : 1);
   }
+  if (stat_sums != nullptr && (!p.epi_split || g.rowwin))
+    return set_error(VCB_ERR_INVALID, "conv (BN statistics): this geometry does not run the split epilogue");
+  p.stat_seg = stat_seg;
+  p.stat_sums = stat_sums;
   p.a_policy = state().l2_hint ? kL2EvictFirst : kL2EvictNormal;
   p.b_policy = state().l2_hint ? kL2EvictLast : kL2EvictNormal;
   p.kchains = g.kchains;

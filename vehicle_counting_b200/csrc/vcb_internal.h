@@ -43,6 +43,6 @@ int conv_packed_sizes(const VcbConvDesc& d, int64_t* weight_halfs, int64_t* bias
 int conv_out_hw(const VcbConvDesc& d, int32_t* ho, int32_t* wo);
 int conv_pack_weights(const VcbConvDesc& d, const float* w, const float* bias, void* wp, float* bp, cudaStream_t st);
 int conv2d_fwd(const VcbConvDesc& d, const void* x, const void* w_packed, const float* bias_packed, const void* residual,
-               void* y, cudaStream_t st);
+               void* y, cudaStream_t st, const int* stat_seg = nullptr, double* stat_sums = nullptr);
 
 }  // namespace vcb

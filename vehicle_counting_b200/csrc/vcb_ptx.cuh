@@ -311,6 +311,19 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 256 bit, four times along the columns: 16 rows x 32 fp32 columns starting at the lane / column of `taddr` (the lane
+// must be the warp's quarter base or that + 16).  mma-accumulator fragment: thread t holds, for j = 0..3,
+//   v[4j], v[4j+1] = row t/4,     columns 8j + 2(t%4), + 1        v[4j+2], v[4j+3] = row t/4 + 8, same columns
+// so a thread sees only 8 distinct columns: column statistics accumulate in registers without any shuffle.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile in shared memory, 128-byte swizzle: rows of 64 fp16 (128 B), 8-row

@@ -164,9 +164,12 @@ class _Plan:
 
     def conv(self, x: TRef, n: int, w: torch.Tensor, b: Optional[torch.Tensor], y: TRef, k: int, s: int, p: int, act: int,
              residual: Optional[TRef] = None, res_mode: int = L.RES_NONE, out_dtype: int = L.F16, a_mode: int = L.A_AUTO,
-             flops: Optional[float] = None, wcache: Optional[dict] = None, wkey=None):
+             flops: Optional[float] = None, wcache: Optional[dict] = None, wkey=None, stats=None) -> bool:
         """`flops`: algorithmic FLOPs of the layer when the launched geometry is a re-expression of it (stems).
-        `wcache` / `wkey`: packed weights are a function of the layer, not of the batch: plans of different batch sizes share them."""
+        `wcache` / `wkey`: packed weights are a function of the layer, not of the batch: plans of different batch sizes share them.
+        `stats` = (seg_of_image tensor, sums tensor): the launch also accumulates train-mode BatchNorm statistics from its epilogue
+        (vcb_conv2d_fwd_stats); returns False when the geometry cannot do that (the plain launch is queued, the caller adds the
+        separate statistics kernel)."""
         cout, cin = int(w.shape[0]), int(w.shape[1])
         d = ops.make_conv_desc(n, x.h, x.w, cin, cout, k, s, p, cin_pitch=x.pitch, cout_pitch=y.pitch, act=act,
                                res_mode=res_mode if residual is not None else L.RES_NONE,
@@ -188,8 +191,19 @@ class _Plan:
         fl = 2.0 * n * ho * wo * cout * cin * k * k if flops is None else flops
         self.conv_flops += fl
         self.num_convs += 1
-        self.add(lambda st, d=d, xp=xp, wp=wp, bp=bp, yp=yp, rp=rp: ops.conv2d(d, xp, wp, bp, yp, residual=rp, stream=st),
-                 f"conv{k}x{k}s{s} {cin}->{cout} M={n * ho * wo}" + (" +res" if residual is not None else ""), fl)
+        label = f"conv{k}x{k}s{s} {cin}->{cout} M={n * ho * wo}" + (" +res" if residual is not None else "")
+        if stats is not None:
+            seg_t, sums_t = stats
+            try:                    # one eager launch decides: geometries without the split epilogue answer VCB_ERR_INVALID
+                ops.conv2d_stats(d, xp, wp, bp, yp, seg_t, sums_t, stream=self.stream)
+                torch.cuda.synchronize(self.device)
+                self.add(lambda st, d=d, xp=xp, wp=wp, bp=bp, yp=yp: ops.conv2d_stats(d, xp, wp, bp, yp, seg_t, sums_t, stream=st),
+                         label + " +BN stats", fl)
+                return True
+            except L.VcbError:
+                pass
+        self.add(lambda st, d=d, xp=xp, wp=wp, bp=bp, yp=yp, rp=rp: ops.conv2d(d, xp, wp, bp, yp, residual=rp, stream=st), label, fl)
+        return stats is None
 
     def run_eager(self, stream=None) -> None:
         st = stream if stream is not None else self.stream
@@ -560,6 +574,10 @@ class ReidEngine:
         assert bn_mode in ("eval", "train")
         # folded-BN path: fused crop -> stem conv -> ReLU -> max-pool ($VCB_REID_FUSED_STEM=0 keeps the three separate kernels)
         self.fused_stem = os.environ.get("VCB_REID_FUSED_STEM", "1") != "0"
+        # ... fed straight from the frames (csrc/reid_stem_direct.cu); $VCB_REID_STEM=patches keeps the round-2 pair of kernels that
+        # stage the im2col operand in HBM
+        self.stem_direct = os.environ.get("VCB_REID_STEM", "direct") != "patches"
+        self.epi_stats = os.environ.get("VCB_EPI_STATS", "0") != "0"      # train-mode BN statistics from the conv epilogue (measured: no gain, off)
         self.device = torch.device(device)
         L.init(self.device.index or 0)
         self.sd = {k: v for k, v in state_dict.items() if not k.startswith("classifier")}
@@ -659,7 +677,17 @@ class ReidEngine:
         w_, b_ = wc["stem"]
         cur = TRef(buf(25, 64), 0, 64)
         stem_flops = 2.0 * nb * 2500 * 64 * 27
-        if self.fused_stem:
+        if self.fused_stem and self.stem_direct:
+            # frames + ROIs -> crop / resize / normalise -> conv + bias -> ReLU -> 3x3/s2 max-pool in ONE tcgen05 kernel; neither the
+            # crop, nor the im2col operand, nor the 50x50x64 stem map reaches HBM (csrc/reid_stem_direct.cu)
+            if "stem_packed_direct" not in wc:
+                wc["stem_packed_direct"] = ops.pack_reid_stem_weights_direct(w_, b_)
+            wpd = wc["stem_packed_direct"]
+            plan.conv_flops += stem_flops
+            plan.num_convs += 1
+            plan.add(lambda st, cur=cur: ops.reid_stem_direct(rd, cur_[0], cur_[1], cur_[2], self.rois, wpd, cur.buf, stream=st),
+                     f"crop+resize+norm + stem conv3x3 3->64 + maxpool3x3s2 (one kernel) M={nb * 2500}", stem_flops)
+        elif self.fused_stem:
             # crop -> im2col patches of the stem (K = 27 -> 32), then ONE kernel: tcgen05 GEMM + bias + ReLU + 3x3/s2 max-pool
             # (csrc/reid_stem.cu): the 50x50x64 stem map never reaches HBM
             patches = torch.zeros(nb, 25, 128, 32, dtype=torch.float16, device=dev)
@@ -754,11 +782,13 @@ class ReidEngine:
             b = None if bias_name is None else sd[bias_name].to(device=dev, dtype=torch.float32)
             osz = (x.h + 2 * p - k) // s + 1
             raw = TRef(buf(osz, co), 0, co)
-            plan.conv(x, nb, w, b, raw, k, s, p, L.ACT_NONE, a_mode=self.a_mode, wcache=wc, wkey="t:" + wname, flops=flops)
             sl = sums[bn_i[0]]
             bn_i[0] += 1
             g, be = f32(bnp + ".weight"), f32(bnp + ".bias")
-            plan.add(lambda st, raw=raw, sl=sl: ops.bn_seg_stats_f16(raw.buf, co, osz * osz, nb, self.seg_of_crop, sl, stream=st), f"bn stats c={co}")
+            fused = plan.conv(x, nb, w, b, raw, k, s, p, L.ACT_NONE, a_mode=self.a_mode, wcache=wc, wkey="t:" + wname, flops=flops,
+                              stats=(self.seg_of_crop, sl) if self.epi_stats else None)
+            if not (self.epi_stats and fused):          # statistics from the convolution's epilogue, else one more pass over the tensor
+                plan.add(lambda st, raw=raw, sl=sl: ops.bn_seg_stats_f16(raw.buf, co, osz * osz, nb, self.seg_of_crop, sl, stream=st), f"bn stats c={co}")
             out_sz = (osz + 1) // 2 if pool else osz
             y = TRef(buf(out_sz, co), 0, co)
             aff = torch.zeros(S, co, 2, dtype=torch.float32, device=dev)
@@ -772,7 +802,28 @@ class ReidEngine:
             return y
 
         stem_flops = 2.0 * nb * 2500 * 64 * 27
-        if self.fused_stem:
+        if self.fused_stem and self.stem_direct:
+            # the direct stem kernel twice (csrc/reid_stem_direct.cu MODE 1 / MODE 2): statistics of conv + bias per segment, then
+            # conv -> per-segment scale / shift -> ReLU -> max-pool; both passes resize the crop in shared memory from the frames
+            if "t:stem_packed_direct" not in wc:
+                wc["t:stem_packed_direct"] = ops.pack_reid_stem_weights_direct(sd["conv.0.weight"].to(device=dev, dtype=torch.float32),
+                                                                               sd["conv.0.bias"].to(device=dev, dtype=torch.float32))
+            wpd = wc["t:stem_packed_direct"]
+            affine = torch.zeros(S, 64, 2, dtype=torch.float32, device=dev)
+            g0, b0 = f32("conv.1.weight"), f32("conv.1.bias")
+            cur = TRef(buf(25, 64), 0, 64)
+            sl0 = sums[bn_i[0]]
+            bn_i[0] += 1
+            plan.keep += [affine]
+            plan.add(lambda st: ops.reid_stem_direct_stats(rd, cur_[0], cur_[1], cur_[2], self.rois, wpd, self.seg_of_crop, sl0, stream=st),
+                     "crop+resize+norm + stem conv: BN statistics only")
+            plan.add(lambda st: ops.bn_seg_finalize(sl0, self.seg_crops, S, 64, 2500, g0, b0, None, REID_BN_EPS, affine, stream=st), "bn finalize")
+            plan.conv_flops += stem_flops
+            plan.num_convs += 1
+            plan.add(lambda st, cur=cur: ops.reid_stem_direct_bn(rd, cur_[0], cur_[1], cur_[2], self.rois, wpd, affine, self.seg_of_crop, cur.buf,
+                                                                 stream=st),
+                     f"crop+resize+norm + stem conv3x3 3->64 + BN(train) + ReLU + maxpool3x3s2 (one kernel) M={nb * 2500}", stem_flops)
+        elif self.fused_stem:
             # the fused stem kernel twice over the same im2col patches (csrc/reid_stem.cu MODE 1 / MODE 2): statistics of conv + bias
             # per segment, then conv -> per-segment scale / shift -> ReLU -> max-pool.  The 50x50x64 pre-BN map (1.3 GB per 4096
             # crops, written once and read twice by the three-launch form below) never exists.

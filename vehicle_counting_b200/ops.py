@@ -76,6 +76,12 @@ def conv2d(d: L.ConvDesc, x, wp, bp, y, residual=None, stream=None) -> None:
             "vcb_conv2d_fwd")
 
 
+def conv2d_stats(d: L.ConvDesc, x, wp, bp, y, seg_of_image, sums, stream=None) -> None:
+    """conv2d (no activation, fp16 out) + per-(segment, channel) sum / sum of squares of its outputs from the epilogue"""
+    L.check(L.load().vcb_conv2d_fwd_stats(C.byref(d), L.ptr(x), L.ptr(wp), L.ptr(bp), L.ptr(y), L.ptr(seg_of_image), L.ptr(sums), _st(stream)),
+            "vcb_conv2d_fwd_stats")
+
+
 # ------------------------------------------------------------------------------------------ data movement
 def frames_to_f16c4(frames_u8: torch.Tensor, out: torch.Tensor, stream=None) -> None:
     n, h, w, c = frames_u8.shape
@@ -201,6 +207,35 @@ def pack_reid_stem_weights(w_oihw: torch.Tensor, bias: torch.Tensor):
     wp = torch.zeros(64, 32, dtype=torch.float16, device=w_oihw.device)
     wp[:, :27] = wk.to(torch.float16)
     return wp.contiguous(), bias.to(torch.float32).contiguous()
+
+
+def pack_reid_stem_weights_direct(w_oihw: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """[64, 3, 3, 3] fp32 + bias -> fp16 [64][32] for the vcb_reid_stem_direct* kernels: k = (r*3+s)*3 + c, then the bias as an fp16
+    head (k = 27) and tail (k = 28; head + tail reproduces the fp32 bias to ~2^-22), zeros"""
+    assert tuple(w_oihw.shape) == (64, 3, 3, 3)
+    wp = torch.zeros(64, 32, dtype=torch.float16, device=w_oihw.device)
+    wp[:, :27] = w_oihw.permute(0, 2, 3, 1).reshape(64, 27).to(torch.float16)
+    b32 = bias.to(device=w_oihw.device, dtype=torch.float32)
+    hi = b32.to(torch.float16)
+    wp[:, 27] = hi
+    wp[:, 28] = (b32 - hi.float()).to(torch.float16)
+    return wp.contiguous()
+
+
+def reid_stem_direct(desc: L.RoiDesc, frames_u8, fh, fw, rois, w_packed, out, stream=None) -> None:
+    """frames + ROIs -> crop/resize/normalise -> conv3x3(3->64) + bias -> ReLU -> maxpool 3/2/1, one kernel, nothing staged in HBM"""
+    L.check(L.load().vcb_reid_stem_direct(C.byref(desc), L.ptr(frames_u8), fh, fw, L.ptr(rois), L.ptr(w_packed), L.ptr(out), _st(stream)),
+            "vcb_reid_stem_direct")
+
+
+def reid_stem_direct_stats(desc: L.RoiDesc, frames_u8, fh, fw, rois, w_packed, seg_of_crop, sums, stream=None) -> None:
+    L.check(L.load().vcb_reid_stem_direct_stats(C.byref(desc), L.ptr(frames_u8), fh, fw, L.ptr(rois), L.ptr(w_packed), L.ptr(seg_of_crop),
+                                                L.ptr(sums), _st(stream)), "vcb_reid_stem_direct_stats")
+
+
+def reid_stem_direct_bn(desc: L.RoiDesc, frames_u8, fh, fw, rois, w_packed, affine, seg_of_crop, out, stream=None) -> None:
+    L.check(L.load().vcb_reid_stem_direct_bn(C.byref(desc), L.ptr(frames_u8), fh, fw, L.ptr(rois), L.ptr(w_packed), L.ptr(affine),
+                                             L.ptr(seg_of_crop), L.ptr(out), _st(stream)), "vcb_reid_stem_direct_bn")
 
 
 def boxes_to_rois(boxes_f64, frame_of, num, fw, fh, rois, stream=None) -> None:
