@@ -32,8 +32,8 @@ constexpr int kTileBytes = kRows * kK * 2;    // 8 KiB
 constexpr int kStages = 4;
 constexpr int kAccs = 4;
 constexpr int kEpiThreads = 256;              // warps 0-7
-constexpr int kProdThreads = 128;             // warps 8-11
-constexpr int kThreads = kEpiThreads + kProdThreads + 32;   // + warp 12: weights load, MMA issue
+constexpr int kProdThreads = 256;             // warps 8-15: two groups of 128, group g builds (and issues the MMAs of) tiles it % 2 == g
+constexpr int kThreads = kEpiThreads + kProdThreads;
 
 // shared-memory map (offsets from the 1024-byte aligned base)
 constexpr uint32_t kOffW = kStages * kTileBytes;                 // 32768: weights [64][32] fp16, 64-byte swizzle
@@ -44,8 +44,7 @@ constexpr uint32_t kOffImg = kOffTab + 2 * 100 * 16;             // 2 x {const u
 constexpr uint32_t kOffBars = kOffImg + 2 * 16;                  // full[4], empty[4], tfull[4], tempty[4], w_bar
 constexpr uint32_t kOffTmemSlot = kOffBars + 8 * (2 * kStages + 2 * kAccs + 1);
 constexpr uint32_t kOffAff = (kOffTmemSlot + 16 + 15) & ~15u;    // MODE 2: [64][2] scale, shift of the current segment
-constexpr uint32_t kOffLut = kOffAff + kN * 8;                   // float [256]: i / 255.0f (cv2: im.astype(float32) / 255.)
-constexpr uint32_t kSmemBytes = 1024 + kOffLut + 1024 + 64;
+constexpr uint32_t kSmemBytes = 1024 + kOffAff + kN * 8 + 64;
 
 struct TabEntry { int off0, off1; float frac; int unused; };
 struct ImgEntry { const uint8_t* frame; int valid; int unused; };
@@ -78,12 +77,12 @@ reid_stem_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const VcbRoi
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), kProdThreads); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < kAccs; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiThreads); }
     mbar_init(w_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 12) {
+  if (warp == 8) {
     if (lane == 0) tma_prefetch_desc(&tmap_w);
     tmem_alloc(smem_base + kOffTmemSlot, 256u);
     tmem_relinquish();
@@ -93,39 +92,39 @@ reid_stem_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const VcbRoi
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 12) {
-    if (lane == 0) {       // ---- weights once, then two tcgen05.mma (M = 128, N = 64, K = 16) per tile
+  if (warp >= 8) {
+    // ---- producers (256 threads = two groups): thread r of group g builds GEMM row r of the tiles it % 2 == g; thread 0 of a group
+    // also issues that tile's two tcgen05.mma (M = 128, N = 64, K = 16) once its group has arrived
+    const int pt = (int)threadIdx.x - kEpiThreads;
+    const int grp = pt >> 7, r_ = pt & 127;
+    if (pt == 0) {
       mbar_arrive_expect_tx(w_bar, 4096u);
       tma_load_2d(&tmap_w, w_bar, smem_base + kOffW, 0, 0);
-      const uint32_t idesc = umma_idesc_f16((uint32_t)kN);
-      const uint64_t desc_hi = umma_desc_kmajor(0, 8u * kK * 2u, 4u);      // SWIZZLE_64B, 8-row groups 512 B apart
-      const uint64_t w_desc = desc_hi | (uint64_t)(((smem_base + kOffW) & 0x3FFFF) >> 4);
-      mbar_wait(w_bar, 0u, fault, FAULT_FULL_WAIT, 610);
-      for (uint32_t it = 0; it < (uint32_t)my_tiles; ++it) {
-        const int st = it % kStages;
-        const uint32_t acc = it % kAccs;
-        mbar_wait(tempty_bar(acc), ((it / kAccs) & 1u) ^ 1u, fault, FAULT_TMEM_EMPTY_WAIT, 620 + (int)acc);
-        mbar_wait(full_bar(st), (it / kStages) & 1u, fault, FAULT_FULL_WAIT, 630 + st);
-        tcgen05_fence_after();
-        const uint64_t a_desc = desc_hi | (uint64_t)(((smem_base + (uint32_t)st * kTileBytes) & 0x3FFFF) >> 4);
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)kN;
-        umma_f16(d_tmem, a_desc, w_desc, idesc, 0u);
-        umma_f16(d_tmem, a_desc + 2u, w_desc + 2u, idesc, 1u);
-        umma_commit(empty_bar(st));
-        umma_commit(tfull_bar(acc));
-      }
     }
-  } else if (warp >= 8) {
-    // ---- producers (128 threads): thread pt builds GEMM row pt of every tile
-    const int pt = (int)threadIdx.x - kEpiThreads;
-    const int rr = min(pt, 120);                          // rows 121..127 are never read by the epilogue: any finite content
+    const uint32_t idesc = umma_idesc_f16((uint32_t)kN);
+    const uint64_t desc_hi = umma_desc_kmajor(0, 8u * kK * 2u, 4u);      // SWIZZLE_64B, 8-row groups 512 B apart
+    const uint64_t w_desc = desc_hi | (uint64_t)(((smem_base + kOffW) & 0x3FFFF) >> 4);
+    auto issue_tile = [&](uint32_t it) {
+      const int st = it % kStages;
+      const uint32_t acc = it % kAccs;
+      mbar_wait_parked(full_bar(st), (it / kStages) & 1u, fault, FAULT_FULL_WAIT, 630 + st, 500u);
+      mbar_wait_parked(tempty_bar(acc), ((it / kAccs) & 1u) ^ 1u, fault, FAULT_TMEM_EMPTY_WAIT, 620 + (int)acc);
+      tcgen05_fence_after();
+      const uint64_t a_desc = desc_hi | (uint64_t)(((smem_base + (uint32_t)st * kTileBytes) & 0x3FFFF) >> 4);
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t)kN;
+      umma_f16(d_tmem, a_desc, w_desc, idesc, 0u);
+      umma_f16(d_tmem, a_desc + 2u, w_desc + 2u, idesc, 1u);
+      umma_commit(empty_bar(st));
+      umma_commit(tfull_bar(acc));
+    };
+    const int rr = min(r_, 120);                          // rows 121..127 are never read by the epilogue: any finite content
     const int ti = rr / 11, tj = rr - ti * 11;
-    const uint32_t row_smem = (uint32_t)pt * 64u;
-    const uint32_t swz = (uint32_t)((pt >> 1) & 3);
+    const uint32_t row_smem = (uint32_t)r_ * 64u;
+    const uint32_t swz = (uint32_t)((r_ >> 1) & 3);
     const uint32_t crop_smem = smem_base + kOffCrop;
     TabEntry* tabs = reinterpret_cast<TabEntry*>(smem_gen + kOffTab);
     ImgEntry* imgs = reinterpret_cast<ImgEntry*>(smem_gen + kOffImg);
-    auto prod_sync = [&]() { asm volatile("bar.sync 3, 128;" ::: "memory"); };
+    auto prod_sync = [&]() { asm volatile("bar.sync 3, 256;" ::: "memory"); };
 
     // resize tables of crop c into table set b: entries 0..49 = columns, 50..99 = rows (the arithmetic of roi_resize_norm_kernel)
     auto build_tables = [&](int c, int b) {
@@ -155,29 +154,53 @@ reid_stem_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const VcbRoi
         }
       }
     };
-    // one resized, normalised pixel (oy, ox) of the crop described by table set b -> crop buffer b.  Split in two so that the twelve
-    // byte loads are in flight while the caller builds its im2col row.  u8 -> float / 255 is a 256-entry table (same values).
-    const float* lut = reinterpret_cast<const float*>(smem_gen + kOffLut);
-    struct PixLoad { uint32_t v[12]; float fx, fy; };
+    // one resized, normalised pixel (oy, ox) of the crop described by table set b -> crop buffer b.  Split in two so that the global
+    // loads are in flight while the caller builds its im2col row.  The two taps of a source row are 6 contiguous bytes (3 when the
+    // column is clamped): they arrive as up to three ALIGNED 32-bit words (a word is loaded only if it holds a needed byte, so every
+    // load stays inside the frame) instead of six byte gathers -- the byte loads' sector lookups were saturating L1.
+    // u8 -> float / 255 exactly as cv2 (im.astype(float32) / 255.): q0 = i * r, q = fma(fma(-q0, 255, i), r, q0) with r = RN(1 / 255)
+    // is the correctly rounded quotient for every i in 0..255 (checked exhaustively).
+    struct PixLoad { uint32_t t0, t1, t2, b0, b1, b2, sft; float fx, fy; bool same_x; };
+    auto row_load = [&](const uint8_t* pa, bool same_x, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+      const uintptr_t u = reinterpret_cast<uintptr_t>(pa);
+      const uint32_t o = (uint32_t)(u & 3u), nb = same_x ? 3u : 6u;
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(u & ~(uintptr_t)3);
+      w0 = __ldg(wp);
+      w1 = (o + nb > 4u) ? __ldg(wp + 1) : 0u;
+      w2 = (o + nb > 8u) ? __ldg(wp + 2) : 0u;
+    };
     auto pixel_load = [&](int oy, int ox, int b, const uint8_t* frame, PixLoad& L_) {
       const TabEntry ex = tabs[b * 100 + ox], ey = tabs[b * 100 + 50 + oy];
-      L_.fx = ex.frac; L_.fy = ey.frac;
-      const uint8_t* p00 = frame + ey.off0 + ex.off0;
-      const uint8_t* p01 = frame + ey.off0 + ex.off1;
-      const uint8_t* p10 = frame + ey.off1 + ex.off0;
-      const uint8_t* p11 = frame + ey.off1 + ex.off1;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        L_.v[c] = __ldg(p00 + c); L_.v[3 + c] = __ldg(p01 + c); L_.v[6 + c] = __ldg(p10 + c); L_.v[9 + c] = __ldg(p11 + c);
-      }
+      L_.fx = ex.frac; L_.fy = ey.frac; L_.same_x = ex.off1 == ex.off0;
+      const uint8_t* pt_ = frame + ey.off0 + ex.off0;
+      const uint8_t* pb_ = frame + ey.off1 + ex.off0;
+      // both rows start at the same offset modulo 4 only if the row pitch is a multiple of 4: keep the shift per row
+      L_.sft = (uint32_t)(reinterpret_cast<uintptr_t>(pt_) & 3u) | ((uint32_t)(reinterpret_cast<uintptr_t>(pb_) & 3u) << 8);
+      row_load(pt_, L_.same_x, L_.t0, L_.t1, L_.t2);
+      row_load(pb_, L_.same_x, L_.b0, L_.b1, L_.b2);
+    };
+    auto unpack_row = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t o, bool same_x, uint32_t& A, uint32_t& B) {
+      const uint32_t s_ = o * 8u;
+      const uint32_t x0 = __funnelshift_r(w0, w1, s_), x1 = __funnelshift_r(w1, w2, s_);
+      A = x0;                                                  // bytes 0..2 = the left tap
+      B = same_x ? x0 : ((x0 >> 24) | (x1 << 8));              // bytes 0..2 = the right tap
+    };
+    auto u8_over_255 = [&](uint32_t packed, int c) {
+      const float i = __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650u | (uint32_t)c)) - 8388608.0f;
+      const float r = __uint_as_float(0x3b808081u);
+      const float q0 = i * r;
+      return fmaf(fmaf(-q0, 255.0f, i), r, q0);
     };
     auto pixel_store = [&](int oy, int ox, int b, bool ok, const PixLoad& L_) {
       __half* dst = reinterpret_cast<__half*>(smem_gen + kOffCrop + b * kCropBytes) + ((oy + 1) * kPad + (ox + 1)) * 3;
       const float fx = L_.fx, fy = L_.fy;
+      uint32_t p00, p01, p10, p11;
+      unpack_row(L_.t0, L_.t1, L_.t2, L_.sft & 3u, L_.same_x, p00, p01);
+      unpack_row(L_.b0, L_.b1, L_.b2, (L_.sft >> 8) & 3u, L_.same_x, p10, p11);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float a = lut[L_.v[c]], b2 = lut[L_.v[3 + c]];
-        const float e = lut[L_.v[6 + c]], g = lut[L_.v[9 + c]];
+        const float a = u8_over_255(p00, c), b2 = u8_over_255(p01, c);
+        const float e = u8_over_255(p10, c), g = u8_over_255(p11, c);
         const float top = a * (1.0f - fx) + b2 * fx;
         const float bot = e * (1.0f - fx) + g * fx;
         const float val = top * (1.0f - fy) + bot * fy;
@@ -189,7 +212,6 @@ reid_stem_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const VcbRoi
       // both crop buffers start as zeros: the one-pixel border is never written again
       for (int i = pt; i < 2 * kCropBytes / 16; i += kProdThreads)
         asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(crop_smem + (uint32_t)i * 16u), "r"(0u) : "memory");
-      for (int i = pt; i < 256; i += kProdThreads) reinterpret_cast<float*>(smem_gen + kOffLut)[i] = (float)i / 255.0f;
       build_tables(c_begin, 0);
       prod_sync();
       {
@@ -202,9 +224,10 @@ reid_stem_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const VcbRoi
         }
       }
       prod_sync();
+      if (r_ == 0) mbar_wait(w_bar, 0u, fault, FAULT_FULL_WAIT, 610);
       // pixels of the NEXT crop this thread resizes while the tiles of the current one are built: tile blk -> rows 2*blk, 2*blk+1
-      const bool px_thread = pt < 100;
-      const int ox_n = pt < 50 ? pt : pt - 50, oy_n = pt < 50 ? 0 : 1;
+      const bool px_thread = r_ < 100;
+      const int ox_n = r_ < 50 ? r_ : r_ - 50, oy_n = r_ < 50 ? 0 : 1;
       uint32_t it = 0;
       for (int c = c_begin; c < c_end; ++c) {
         const int cur = (c - c_begin) & 1;
@@ -216,6 +239,10 @@ reid_stem_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const VcbRoi
         const uint32_t crop_cur = crop_smem + (uint32_t)cur * kCropBytes;
         int by = 0, bx = 0;
         for (int blk = 0; blk < kBlocks; ++blk, ++it) {
+          if ((int)(it & 1u) != grp) {                        // the other group's tile
+            if (++bx == 5) { bx = 0; ++by; }
+            continue;
+          }
           PixLoad pl;
           if (do_px) pixel_load(2 * blk + oy_n, ox_n, cur ^ 1, ie.frame, pl);
           // ---- im2col row: conv output (cy, cx) = (10*by - 1 + ti, 10*bx - 1 + tj); output row / column -1 is pool padding (never
@@ -247,7 +274,7 @@ reid_stem_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const VcbRoi
           o[13] = (t[2][4] & 0xffffu) | 0x3C000000u;
           o[14] = 0x00003C00u; o[15] = 0u;
           const int st = it % kStages;
-          mbar_wait(empty_bar(st), ((it / kStages) & 1u) ^ 1u, fault, FAULT_EMPTY_WAIT, 600 + st);
+          mbar_wait_parked(empty_bar(st), ((it / kStages) & 1u) ^ 1u, fault, FAULT_EMPTY_WAIT, 600 + st, 500u);
           const uint32_t dst = smem_base + (uint32_t)st * kTileBytes + row_smem;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -256,6 +283,7 @@ reid_stem_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const VcbRoi
           fence_proxy_async_smem();
           mbar_arrive(full_bar(st));
           if (do_px) pixel_store(2 * blk + oy_n, ox_n, cur ^ 1, ie.valid != 0, pl);
+          if (r_ == 0) issue_tile(it);
           if (++bx == 5) { bx = 0; ++by; }
         }
         prod_sync();        // the next crop is complete and nobody reads this one any more
@@ -308,7 +336,8 @@ reid_stem_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const VcbRoi
           cur_seg = seg;
         }
       }
-      mbar_wait(tfull_bar(acc), (it / kAccs) & 1u, fault, FAULT_TMEM_FULL_WAIT, 640 + (int)acc);
+      if (lane == 0) mbar_wait_parked(tfull_bar(acc), (it / kAccs) & 1u, fault, FAULT_TMEM_FULL_WAIT, 640 + (int)acc);   // one poller per warp: 256 spinning
+      __syncwarp();                                                                                                // threads saturate the shared-memory pipe
       tcgen05_fence_after();
       const uint32_t t_addr = tmem_base + acc * (uint32_t)kN + (uint32_t)(half * 32) + ((uint32_t)(q * 32) << 16);
       uint32_t v0[16], v1[16];
@@ -353,7 +382,8 @@ reid_stem_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const VcbRoi
           cur_seg = seg;
         }
       }
-      mbar_wait(tfull_bar(acc), (it / kAccs) & 1u, fault, FAULT_TMEM_FULL_WAIT, 640 + (int)acc);
+      if (lane == 0) mbar_wait_parked(tfull_bar(acc), (it / kAccs) & 1u, fault, FAULT_TMEM_FULL_WAIT, 640 + (int)acc);   // one poller per warp: 256 spinning
+      __syncwarp();                                                                                                // threads saturate the shared-memory pipe
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + acc * (uint32_t)kN + (uint32_t)(half * 32) + ((uint32_t)(q * 32) << 16);
       uint32_t v0[16], v1[16];
@@ -402,8 +432,8 @@ reid_stem_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const VcbRoi
 #pragma unroll
           for (int dj = 0; dj < 3; ++dj) {
             if (di == 1 && dj == 1) continue;
-            if ((di == 0 && skip_r) || (dj == 0 && skip_c)) continue;
-            const int r9 = (2 * pi + di) * 11 + (2 * pj + dj);
+            // a skipped tap re-reads the window centre's row / column instead (branch-free; a duplicate cannot change a max)
+            const int r9 = (2 * pi + ((di == 0 && skip_r) ? 1 : di)) * 11 + (2 * pj + ((dj == 0 && skip_c) ? 1 : dj));
             const uint4 x = *reinterpret_cast<const uint4*>(bg + r9 * 128 + ((ch ^ (r9 & 7)) << 4));
             const __half2* xh = reinterpret_cast<const __half2*>(&x);
             m[0] = __hmax2(m[0], xh[0]); m[1] = __hmax2(m[1], xh[1]); m[2] = __hmax2(m[2], xh[2]); m[3] = __hmax2(m[3], xh[3]);
@@ -419,7 +449,7 @@ reid_stem_direct_kernel(const __grid_constant__ CUtensorMap tmap_w, const VcbRoi
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem_base, 256u);
+  if (warp == 8) tmem_dealloc(tmem_base, 256u);
 }
 
 template <int MODE>

@@ -109,6 +109,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, KernelF
     if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > 2000000000ull) mbar_fault(f, code, info, (int)parity);
   }
 }
+// Wait for a barrier that is normally SEVERAL HUNDRED cycles away (an epilogue waiting for its producers): the try_wait carries a
+// suspend-time hint, so the hardware parks the thread instead of letting it spin.  A spinning warp issues ~17 instructions per
+// poll; sixteen of them per SM took a third of all issue slots of the fused ReID stem (ncu, profiles/r02_stem_direct.md).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, KernelFault* f, int code, int info, uint32_t hint_ns = 2000u) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, hint_ns)) {
+    if ((++spins & 0xff) == 0 && global_timer_ns() - t0 > 2000000000ull) mbar_fault(f, code, info, (int)parity);
+  }
+}
 // tight polling variant (A/B experiments)
 __device__ __forceinline__ void mbar_wait_tight(uint32_t bar, uint32_t parity, KernelFault* f, int code, int info) {
   uint32_t spins = 0;
