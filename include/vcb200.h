@@ -59,6 +59,13 @@ int vcb_version(void);
  * accesses with griddepcontrol.wait); default from $VCB_PDL at vcb_init(), else 0.  "l2_hint" = 1: activation TMA loads carry the
  * evict-first L2 policy and weight loads evict-last ($VCB_L2_HINT).  Unknown names: VCB_ERR_INVALID / -1. */
 int vcb_set_option(const char* name, int32_t value);
+/* Frames that already live in page-locked host memory go to the device IN PLACE (no gather into a staging buffer): n sources of
+ * bytes_each bytes -> dst[i * bytes_each], asynchronous on `stream`; neighbouring sources that are contiguous in host memory are
+ * merged into one copy.  Returns 1 when every source is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) and the
+ * copies were queued, 0 when at least one is pageable (nothing is queued: the caller gathers into its own pinned buffer, as
+ * the reference's lists of cv2 frames need, modules/datasets.py:72-76), negative on error.  The sources must stay untouched until
+ * the stream has passed the copies. */
+int vcb_h2d_frames_inplace(void* dst, const void* const* srcs, int32_t n, int64_t bytes_each, vcb_stream_t stream);
 int vcb_get_option(const char* name);
 /* development aid: "prof" = 1 zeroes and enables per-role cycle counters inside the conv kernel (summed over CTAs: CTA
  * lifetime, set-up, producer / MMA / epilogue waits and totals, CTAs, tiles); vcb_read_prof synchronises and copies them

@@ -632,3 +632,36 @@ def test_conv_epilogue_bn_statistics_match_the_statistics_kernel(lib, n, h, cin,
         np.testing.assert_allclose(sums[si, :, 1].cpu().numpy(), (blk * blk).sum((0, 1, 2)).numpy(), rtol=1e-5, atol=5e-3)
         off += kk
     assert (sums[nseg] == 0).all()
+
+
+def test_h2d_frames_inplace_takes_pinned_frames_and_declines_pageable_ones(lib):
+    """vcb_h2d_frames_inplace / hostcopy.upload_frames: frames that live in page-locked memory (views of one pinned tensor: merged
+    into one copy; separately pinned tensors: one copy each) reach the device without the gather; a pageable frame in the list makes
+    the call decline (0) and upload_frames falls back to its pinned staging buffer.  Same bytes on the device either way."""
+    from vehicle_counting_b200 import hostcopy
+    rng = np.random.default_rng(11)
+    n, h, w = 6, 48, 80
+    stream = torch.cuda.current_stream()
+    block = torch.from_numpy(rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)).pin_memory()
+    views = [block.numpy()[i] for i in range(n)]
+    dev = torch.zeros(n, h, w, 3, dtype=torch.uint8, device=DEV)
+    assert hostcopy.upload_inplace(dev, views, stream) is True
+    torch.cuda.synchronize()
+    assert torch.equal(dev.cpu(), block)
+    singles_t = [torch.from_numpy(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).pin_memory() for _ in range(n)]
+    singles = [t.numpy() for t in singles_t]
+    dev.zero_()
+    assert hostcopy.upload_inplace(dev, singles, stream) is True
+    torch.cuda.synchronize()
+    assert torch.equal(dev.cpu(), torch.stack(singles_t))
+    mixed = list(singles)
+    mixed[3] = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)             # pageable
+    dev.zero_()
+    assert hostcopy.upload_inplace(dev, mixed, stream) is False
+    torch.cuda.synchronize()
+    assert int(dev.sum()) == 0                                             # nothing was queued
+    staging = torch.empty(n, h, w, 3, dtype=torch.uint8).pin_memory()
+    hostcopy.upload_frames(staging, dev, mixed, stream)
+    torch.cuda.synchronize()
+    assert torch.equal(dev.cpu(), torch.from_numpy(np.stack(mixed)))
+    assert hostcopy.upload_inplace(dev, [v[:, :, ::-1] for v in views], stream) is False      # BGR views are not contiguous

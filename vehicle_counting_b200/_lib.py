@@ -83,6 +83,7 @@ _SIGNATURES = {
     "vcb_set_option": ([C.c_char_p, _I32], _I32),
     "vcb_get_option": ([C.c_char_p], _I32),
     "vcb_read_prof": ([C.POINTER(C.c_uint64)], _I32),
+    "vcb_h2d_frames_inplace": ([_VP, _VP, _I32, _I64, _VP], _I32),
     "vcb_conv_packed_sizes": ([C.POINTER(ConvDesc), C.POINTER(_I64), C.POINTER(_I64)], _I32),
     "vcb_conv_pack_weights": ([C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP], _I32),
     "vcb_conv2d_fwd": ([C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP], _I32),

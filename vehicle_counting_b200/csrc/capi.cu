@@ -117,6 +117,27 @@ int vcb_init(int device) {
   return VCB_OK;
 }
 
+int vcb_h2d_frames_inplace(void* dst, const void* const* srcs, int32_t n, int64_t bytes_each, vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  if (!dst || !srcs || n < 0 || bytes_each <= 0) return set_error(VCB_ERR_INVALID, "h2d_frames_inplace: bad argument");
+  for (int i = 0; i < n; ++i) {
+    if (!srcs[i]) return set_error(VCB_ERR_INVALID, "h2d_frames_inplace: null source");
+    cudaPointerAttributes a;
+    const cudaError_t e = cudaPointerGetAttributes(&a, srcs[i]);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (a.type != cudaMemoryTypeHost) return 0;                 // pageable (cudaMemoryTypeUnregistered) or not host memory at all
+  }
+  for (int i = 0; i < n;) {
+    int j = i + 1;                                               // [i, j): one contiguous run of sources
+    while (j < n && static_cast<const char*>(srcs[j]) == static_cast<const char*>(srcs[j - 1]) + bytes_each) ++j;
+    const cudaError_t e = cudaMemcpyAsync(static_cast<char*>(dst) + (size_t)i * bytes_each, srcs[i], (size_t)(j - i) * bytes_each,
+                                          cudaMemcpyHostToDevice, (cudaStream_t)st);
+    if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyAsync(h2d_frames_inplace)");
+    i = j;
+  }
+  return 1;
+}
+
 int vcb_set_option(const char* name, int32_t value) {
   if (!name) return set_error(VCB_ERR_INVALID, "null option name");
   if (strcmp(name, "pdl") == 0) { state().pdl = value != 0 ? 1 : 0; return VCB_OK; }

@@ -502,16 +502,24 @@ class YoloEngine:
         self.scale.copy_(self.scale_host)
 
     def set_scale(self, shapes0: Sequence[Tuple[int, int]]) -> None:
-        """scale_coords parameters for original shapes (h0, w0) letterboxed into (self.h, self.w)."""
-        for i, (h0, w0) in enumerate(shapes0):
-            gain = min(self.h / h0, self.w / w0)
-            self.scale_host[0, i] = gain
-            self.scale_host[1, i] = (self.w - w0 * gain) / 2
-            self.scale_host[2, i] = (self.h - h0 * gain) / 2
-            self.scale_host[3, i] = float(w0)
-            self.scale_host[4, i] = float(h0)
+        """scale_coords parameters for original shapes (h0, w0) letterboxed into (self.h, self.w); a repeated list of shapes (every
+        batch of a video) costs one tuple comparison."""
+        key = tuple(shapes0)
+        if key == getattr(self, "_scale_key", None):
+            return
+        hw = np.asarray(shapes0, np.float64).reshape(-1, 2)
+        gain = np.minimum(self.h / hw[:, 0], self.w / hw[:, 1])
+        sh = self.scale_host.numpy()
+        n = len(hw)
+        self.plan.stream.synchronize()                  # the previous copy out of scale_host has completed
+        sh[0, :n] = gain
+        sh[1, :n] = (self.w - hw[:, 1] * gain) / 2
+        sh[2, :n] = (self.h - hw[:, 0] * gain) / 2
+        sh[3, :n] = hw[:, 1]
+        sh[4, :n] = hw[:, 0]
         with torch.cuda.stream(self.plan.stream):
             self.scale.copy_(self.scale_host, non_blocking=True)
+        self._scale_key = key
 
     def upload(self, frames_host: torch.Tensor) -> None:
         """H2D of a pinned uint8 [batch, h, w, 3] tensor on the plan's stream."""
