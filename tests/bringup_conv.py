@@ -239,6 +239,27 @@ for _nm, _kw in (("reid-l1", dict(n=1024, h=25, w=25, k=3, p=1, cin=64, cout=64)
     case(f"xq-m128-noepi-{_nm}", mode="tma", act="relu", cta_pair=1, epi_direct=3, **_kw)
 
 
+# round 2, session 3: N-tile width of the wide 1x1 layers (one 192 / 256-column tile leaves room for ONE accumulator stage in the 256
+# TMEM columns of a two-per-SM CTA, so MMA and epilogue serialise; two narrower tiles keep two stages)
+for _tag, _kw in (("192-192-m409k", dict(n=64, h=80, w=80, cin=192, cout=192)), ("192-192-m102k", dict(n=64, h=40, w=40, cin=192, cout=192)),
+                  ("384-384-m102k", dict(n=64, h=40, w=40, cin=384, cout=384)), ("384-384-m25k", dict(n=64, h=20, w=20, cin=384, cout=384)),
+                  ("768-768-m25k", dict(n=64, h=20, w=20, cin=768, cout=768)), ("768-384-m102k", dict(n=64, h=40, w=40, cin=768, cout=384)),
+                  ("1536-768-m25k", dict(n=64, h=20, w=20, cin=1536, cout=768)), ("384-192-m409k", dict(n=64, h=80, w=80, cin=384, cout=192)),
+                  ("96-96-m1638k", dict(n=64, h=160, w=160, cin=96, cout=96))):
+    for _bn in (0, 64, 96, 128):
+        if _bn and (_kw["cout"] % _bn or _bn >= _kw["cout"] or (_kw["cout"] // _bn > 1 and _bn % 64)):
+            continue
+        case(f"bnsweep-1x1-{_tag}-bn{_bn}", mode="tma", k=1, act="silu", block_n=_bn, **_kw)
+for _bn in (0, 128):
+    case(f"bnsweep-head-192-255-bn{_bn}", mode="tma", n=64, h=80, w=80, k=1, cin=192, cout=255, cout_pitch=256, out="f32", block_n=_bn)
+for _tag, _kw in (("48-96-s2", dict(n=64, h=320, w=320, cin=48, cout=96)), ("96-192-s2", dict(n=64, h=160, w=160, cin=96, cout=192)),
+                  ("192-384-s2", dict(n=64, h=80, w=80, cin=192, cout=384)), ("384-768-s2", dict(n=64, h=40, w=40, cin=384, cout=768))):
+    for _bn in (0, 64, 128):
+        if _bn and (_bn >= _kw["cout"] or _kw["cout"] % _bn):
+            continue
+        case(f"bnsweep-3x3-{_tag}-bn{_bn}", mode="tma", k=3, s=2, p=1, act="silu", block_n=_bn, **_kw)
+
+
 def run_case(idx: int) -> dict:
     import torch
     import torch.nn.functional as F

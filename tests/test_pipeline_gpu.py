@@ -111,3 +111,29 @@ def test_pipeline_csv_agreement_full_gpu_path(lib, tmp_path, monkeypatch):
         json.dump(rec, fh)
     assert len(got) > 0
     assert near >= 0.6 * len(want), rec
+
+
+def test_video_loader_pinned_ring_yields_the_same_frames_and_uploads_in_place(lib, tmp_path, monkeypatch):
+    """$VCB_PINNED_FRAMES: the frame source decodes into a ring of page-locked buffers (modules/datasets.py mirror); the batches are
+    the same bytes as without it and the stage upload takes the in-place path (no gather)."""
+    _need_inputs()
+    from oracle import make_goldens as M
+    from vehicle_counting_b200 import hostcopy
+    from vehicle_counting_b200.modules.datasets import VideoLoader
+    z = np.load(os.path.join(GOLD, "pipeline_golden.npz"))
+    clip = M.write_pipeline_inputs(str(tmp_path), z["base"], int(z["T"]), int(z["step"]))
+    cfg = types.SimpleNamespace(image_size=[640, 640], keep_ratio=True)
+    plain = [(b["imgs"][0].copy(), b["ori_imgs"][0].copy()) for b in VideoLoader(cfg, clip)]
+    monkeypatch.setenv("VCB_PINNED_FRAMES", "4")
+    stream = torch.cuda.current_stream()
+    n = 0
+    for b in VideoLoader(cfg, clip, batch_size=2):
+        for k in range(len(b["imgs"])):
+            np.testing.assert_array_equal(b["imgs"][k], plain[n][0])
+            np.testing.assert_array_equal(b["ori_imgs"][k], plain[n][1])
+            n += 1
+        dev = torch.zeros((len(b["imgs"]),) + b["imgs"][0].shape, dtype=torch.uint8, device="cuda:0")
+        assert hostcopy.upload_inplace(dev, b["imgs"], stream) is True
+        torch.cuda.synchronize()
+        assert torch.equal(dev.cpu(), torch.from_numpy(np.stack(b["imgs"])))
+    assert n == len(plain)

@@ -174,7 +174,8 @@ class _Plan:
         d = ops.make_conv_desc(n, x.h, x.w, cin, cout, k, s, p, cin_pitch=x.pitch, cout_pitch=y.pitch, act=act,
                                res_mode=res_mode if residual is not None else L.RES_NONE,
                                res_pitch=residual.pitch if residual is not None else 0, out_dtype=out_dtype, a_mode=a_mode,
-                               tile_rev=self.alternate and self._rev)
+                               tile_rev=self.alternate and self._rev,
+                               block_n=TUNED_BLOCK_N.get((k, s, cin, cout), 0) if a_mode == L.A_AUTO and out_dtype == L.F16 else 0)
         self._rev = not self._rev
         ho, wo = ops.conv_out_hw(d)
         assert (ho, wo) == (y.h, y.w), ((ho, wo), (y.h, y.w))
@@ -231,6 +232,12 @@ class _Plan:
 
 
 _ROWWIN_OK: Optional[bool] = None
+
+# N-tile widths that beat the library's choice (one tile as wide as fits 256 columns), measured per layer shape on B200
+# (tests/bringup_conv.py --only bnsweep, profiles/r02_bnsweep.jsonl): a 192- or 256-wide tile leaves room for ONE accumulator stage in
+# the 256 TMEM columns of a two-per-SM CTA, so MMA and epilogue serialise; narrower tiles keep two stages at the price of fetching
+# the activation tile once per N tile -- a win only while K is small.  (k, stride, cin, cout) -> block_n
+TUNED_BLOCK_N = {(1, 1, 192, 192): 64, (1, 1, 384, 384): 128, (3, 2, 384, 768): 128}
 
 
 def SILU_DEFAULT() -> bool:

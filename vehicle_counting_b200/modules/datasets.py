@@ -27,13 +27,43 @@ class VideoSet:
         self.video_info = {"name": os.path.basename(self.input_path), "width": self.WIDTH, "height": self.HEIGHT, "fps": self.FPS,
                            "num_frames": self.NUM_FRAMES}
 
+    def _pinned_slot(self):
+        """$VCB_PINNED_FRAMES=N (N >= 2): frames are decoded into a ring of N page-locked (BGR, RGB) buffer pairs, so the stages copy
+        them to the device in place (vcb_h2d_frames_inplace: no gather through a staging buffer).  A frame handed out stays valid
+        for the next N - 1 reads: N must exceed the number of frames the consumer holds at once (batch size x batches in flight).
+        Off by default: the reference hands out fresh arrays that stay valid for ever."""
+        n = int(os.environ.get("VCB_PINNED_FRAMES", "0") or 0)
+        if n < 2:
+            return None
+        ring = getattr(self, "_ring", None)
+        if ring is None or ring[0].shape[0] != n:
+            import torch
+            if not torch.cuda.is_available():
+                return None
+            ring = self._ring = tuple(torch.empty(n, self.HEIGHT, self.WIDTH, 3, dtype=torch.uint8).pin_memory() for _ in range(2))
+            self._ring_np = tuple(t.numpy() for t in ring)
+        k = self.current_frame_id % n
+        return self._ring_np[0][k], self._ring_np[1][k]
+
     def read(self) -> Optional[Dict]:
         import cv2
-        ok, ori = self.stream.read()
+        slot = self._pinned_slot()
+        if slot is None:
+            ok, ori = self.stream.read()
+        else:
+            ok, got = self.stream.read(slot[0])
+            ori = slot[0]
+            if ok and got is not ori:                   # the decoder allocated its own array (size / type mismatch): copy once
+                if got.shape != ori.shape:
+                    slot = None
+                    ori = got
+                else:
+                    ori[...] = got
         self.current_frame_id += 1
         if not ok:
             return None
-        return {"img": cv2.cvtColor(ori, cv2.COLOR_BGR2RGB), "frame": self.current_frame_id, "ori_img": ori}
+        rgb = cv2.cvtColor(ori, cv2.COLOR_BGR2RGB) if slot is None else cv2.cvtColor(ori, cv2.COLOR_BGR2RGB, dst=slot[1])
+        return {"img": rgb, "frame": self.current_frame_id, "ori_img": ori}
 
     def __len__(self) -> int:
         return self.NUM_FRAMES
