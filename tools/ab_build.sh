@@ -6,7 +6,7 @@ set -e
 tag=$1; shift
 cd "$(dirname "$0")/../vehicle_counting_b200/csrc"
 tmp=$(mktemp -d)
-for f in conv_umma pointwise detect_nms roi reid_stem capi; do
+for f in conv_umma pointwise detect_nms roi reid_stem reid_stem_direct capi; do
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -c $f.cu -o $tmp/$f.o &
 done
 wait
