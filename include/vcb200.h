@@ -283,6 +283,14 @@ int vcb_bn_seg_finalize(const double* sums, const int32_t* seg_crops, int32_t nu
 int vcb_reid_stem_pool_bn(const void* patches, const void* w_packed, const float* affine, const int32_t* seg_of_crop, void* out,
                           int32_t num_rois, vcb_stream_t stream);
 int vcb_bn_seg_stats_f16(const void* x, int32_t c, int32_t hw, int32_t n, const int32_t* seg_of_crop, double* sums, vcb_stream_t stream);
+/* vcb_bn_seg_finalize + vcb_bn_seg_apply_f16 in one launch: scale / shift are derived in the kernel from `sums` (same arithmetic), and
+ * the residual may itself be a pre-BN tensor -- the downsample branch of a BasicBlock (model.py:19-25, :33-37) -- normalised on the
+ * fly with its own statistics / gamma / beta (res_sums != NULL), which removes that branch's apply pass:
+ *   y = act(BN(x) + (res_sums ? BN_r(residual) : residual));  x: fp16 [n][hw][c], c = 8 * power of two <= 512; no pooling form. */
+int vcb_bn_seg_apply_fused_f16(const void* x, int32_t c, int32_t hw, int32_t n, const int32_t* seg_of_crop, const int32_t* seg_crops,
+                               const double* sums, const float* gamma, const float* beta, float eps, const void* residual, int32_t res_pitch,
+                               const double* res_sums, const float* res_gamma, const float* res_beta, int32_t act, void* y, int32_t y_pitch,
+                               vcb_stream_t stream);
 int vcb_bn_seg_apply_f16(const void* x, int32_t c, int32_t h, int32_t w, int32_t n, const int32_t* seg_of_crop, const float* affine,
                          const void* residual, int32_t res_pitch, int32_t act, int32_t pool, void* y, int32_t y_pitch, vcb_stream_t stream);
 

@@ -665,3 +665,48 @@ def test_h2d_frames_inplace_takes_pinned_frames_and_declines_pageable_ones(lib):
     torch.cuda.synchronize()
     assert torch.equal(dev.cpu(), torch.from_numpy(np.stack(mixed)))
     assert hostcopy.upload_inplace(dev, [v[:, :, ::-1] for v in views], stream) is False      # BGR views are not contiguous
+
+
+@pytest.mark.parametrize("c,h,n,seg_sizes,res", [(64, 25, 70, [5, 1, 40, 24], "plain"), (128, 13, 130, [64, 64, 2], "bn"), (512, 4, 300, [64, 64, 64, 64, 44], "bn"),
+                                                 (256, 7, 40, [40], "none")])
+def test_bn_fused_apply_equals_finalize_plus_apply(lib, c, h, n, seg_sizes, res):
+    """vcb_bn_seg_apply_fused_f16 (scale / shift derived in the kernel; the residual optionally a pre-BN tensor normalised on the fly --
+    the downsample branch of a BasicBlock, model.py:33-37) against the two-step form it replaces: bit-identical without a BN'd
+    residual, and against F.batch_norm(training=True) per segment with one."""
+    import torch.nn.functional as F
+    from vehicle_counting_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(c + n)
+    nseg = len(seg_sizes)
+    x = (torch.randn(n, h, h, c, generator=g) * 1.7 + 0.3).half().to(DEV)
+    r = (torch.randn(n, h, h, c, generator=g) * 0.9 - 0.2).half().to(DEV)
+    gamma, beta = (torch.rand(c, generator=g) + 0.5).to(DEV), (torch.randn(c, generator=g) * 0.1).to(DEV)
+    gr, br = (torch.rand(c, generator=g) + 0.5).to(DEV), (torch.randn(c, generator=g) * 0.1).to(DEV)
+    soc = torch.from_numpy(np.repeat(np.arange(nseg), seg_sizes).astype(np.int32)).to(DEV)
+    cnt = torch.tensor(seg_sizes + [0], dtype=torch.int32, device=DEV)
+    sums = torch.zeros(nseg + 1, c, 2, dtype=torch.float64, device=DEV)
+    rsums = torch.zeros_like(sums)
+    ops.bn_seg_stats_f16(x, c, h * h, n, soc, sums)
+    ops.bn_seg_stats_f16(r, c, h * h, n, soc, rsums)
+    y = torch.zeros(n, h, h, c, dtype=torch.float16, device=DEV)
+    ops.bn_seg_apply_fused_f16(x, c, h * h, n, soc, cnt, sums, gamma, beta, 1e-5, None if res == "none" else r, c, L.ACT_RELU, y, c,
+                               res_sums=rsums if res == "bn" else None, res_gamma=gr if res == "bn" else None, res_beta=br if res == "bn" else None)
+    torch.cuda.synchronize()
+    if res != "bn":
+        aff = torch.zeros(nseg + 1, c, 2, dtype=torch.float32, device=DEV)
+        y2 = torch.zeros_like(y)
+        ops.bn_seg_finalize(sums, cnt, nseg + 1, c, h * h, gamma, beta, None, 1e-5, aff)
+        ops.bn_seg_apply_f16(x, c, h, h, n, soc, aff, None if res == "none" else r, c, L.ACT_RELU, 0, y2, c)
+        torch.cuda.synchronize()
+        assert torch.equal(y, y2)
+    off = 0
+    for k in seg_sizes:
+        xs = x[off:off + k].float().cpu().permute(0, 3, 1, 2)
+        want = F.batch_norm(xs, None, None, gamma.cpu(), beta.cpu(), True, 0.0, 1e-5)
+        if res == "plain":
+            want = want + r[off:off + k].float().cpu().permute(0, 3, 1, 2)
+        elif res == "bn":
+            want = want + F.batch_norm(r[off:off + k].float().cpu().permute(0, 3, 1, 2), None, None, gr.cpu(), br.cpu(), True, 0.0, 1e-5)
+        want = F.relu(want).permute(0, 2, 3, 1)
+        err = (y[off:off + k].float().cpu() - want).abs().max().item()
+        assert err <= 4e-3 * max(1.0, want.abs().max().item()), (k, err)
+        off += k

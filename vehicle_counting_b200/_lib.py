@@ -114,6 +114,7 @@ _SIGNATURES = {
     "vcb_bn_seg_finalize": ([_VP, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _F, _VP, _VP], _I32),
     "vcb_reid_stem_pool_bn": ([_VP, _VP, _VP, _VP, _VP, _I32, _VP], _I32),
     "vcb_bn_seg_stats_f16": ([_VP, _I32, _I32, _I32, _VP, _VP, _VP], _I32),
+    "vcb_bn_seg_apply_fused_f16": ([_VP, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _F, _VP, _I32, _VP, _VP, _VP, _I32, _VP, _I32, _VP], _I32),
     "vcb_bn_seg_apply_f16": ([_VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _I32, _VP], _I32),
     "vcb_graph_begin": ([_VP], _I32),
     "vcb_graph_end": ([_VP, C.POINTER(_VP)], _I32),

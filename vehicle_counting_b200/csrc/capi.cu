@@ -23,6 +23,8 @@ int bn_train_stats(const float*, int, const int*, int, const float*, const float
 int bn_apply(const float*, int, int, const int*, const float*, const float*, const void*, int, int, void*, int, cudaStream_t);
 int bn_seg_stats_f16(const void*, int, int, int, const int*, double*, cudaStream_t);
 int bn_seg_apply_f16(const void*, int, int, int, int, const int*, const float*, const void*, int, int, int, void*, int, cudaStream_t);
+int bn_seg_apply_fused_f16(const void*, int, int, int, const int*, const int*, const double*, const float*, const float*, float, const void*, int,
+                           const double*, const float*, const float*, int, void*, int, cudaStream_t);
 int detect_decode(const VcbDetectDesc&, float*, float*, int*, int*, int*, cudaStream_t);
 int nms(const VcbNmsDesc&, const float*, const float*, const int*, const int*, const int*, unsigned long long*, float*, int*,
         cudaStream_t);
@@ -301,6 +303,14 @@ int vcb_reid_stem_stats(const void* patches, const void* w_packed, const float* 
 int vcb_reid_stem_pool_bn(const void* patches, const void* w_packed, const float* affine, const int32_t* seg_of_crop, void* out,
                           int32_t num_rois, vcb_stream_t st) {
   return reid_stem_pool_bn(patches, w_packed, affine, seg_of_crop, out, num_rois, (cudaStream_t)st);
+}
+int vcb_bn_seg_apply_fused_f16(const void* x, int32_t c, int32_t hw, int32_t n, const int32_t* seg_of_crop, const int32_t* seg_crops,
+                               const double* sums, const float* gamma, const float* beta, float eps, const void* residual, int32_t res_pitch,
+                               const double* res_sums, const float* res_gamma, const float* res_beta, int32_t act, void* y, int32_t y_pitch,
+                               vcb_stream_t st) {
+  const int rc = require_init(); if (rc) return rc;
+  return bn_seg_apply_fused_f16(x, c, hw, n, seg_of_crop, seg_crops, sums, gamma, beta, eps, residual, res_pitch, res_sums, res_gamma, res_beta,
+                                act, y, y_pitch, (cudaStream_t)st);
 }
 int vcb_bn_seg_finalize(const double* sums, const int32_t* seg_crops, int32_t num_seg_plus1, int32_t c, int32_t hw, const float* gamma,
                         const float* beta, const float* bias, float eps, float* affine, vcb_stream_t st) {

@@ -640,6 +640,96 @@ __global__ void __launch_bounds__(256) bn_seg_apply_f16_kernel(const uint4* __re
   }
 }
 
+// Train-mode BatchNorm apply with the scale / shift derived IN the kernel from the statistics (no vcb_bn_seg_finalize launch, no affine
+// table) and, optionally, a residual that is itself a pre-BN tensor (the downsample branch of a BasicBlock, model.py:19-25,33-37):
+//   y = act( x * k + (beta - mean * k)  +  [ r * kr + (beta_r - mean_r * kr)  |  r ] ),   k = gamma / sqrt(var + eps)
+// mean / var per (segment, channel) from sums[seg][c][2] over seg_crops[seg] * hw values, computed once per block and segment in
+// shared memory with the arithmetic of bn_seg_finalize_kernel; a thread then keeps the 8 channels it always meets in registers.
+__global__ void __launch_bounds__(256) bn_seg_apply_fused_f16_kernel(const uint4* __restrict__ x, int c8, int hw, int n, int cpb,
+                                                                      const int* __restrict__ seg_of_crop, const int* __restrict__ seg_crops,
+                                                                      const double* __restrict__ sums, const float* __restrict__ gamma,
+                                                                      const float* __restrict__ beta, float eps,
+                                                                      const uint4* __restrict__ residual, int res_pitch8,
+                                                                      const double* __restrict__ res_sums, const float* __restrict__ res_gamma,
+                                                                      const float* __restrict__ res_beta, int act, uint4* __restrict__ y, int y_pitch8) {
+  __shared__ float sc[512], sh[512], rc[512];
+  const int c = c8 * 8;
+  const int crop0 = blockIdx.x * cpb, crop1 = min(n, crop0 + cpb);
+  const int cv = threadIdx.x & (c8 - 1), rl = threadIdx.x / c8, lanes = 256 / c8;
+  int cur = -1;
+  float rs[8], rh[8], rq[8];
+  for (int crop = crop0; crop < crop1; ++crop) {
+    const int seg = seg_of_crop[crop];
+    if (seg != cur) {                                     // block-uniform
+      __syncthreads();
+      const double cnt = (double)seg_crops[seg] * (double)hw;
+      for (int ch = threadIdx.x; ch < c; ch += 256) {
+        const long long i = (long long)seg * c + ch;
+        const double mean = cnt > 0 ? sums[i * 2] / cnt : 0.0;
+        double var = cnt > 0 ? sums[i * 2 + 1] / cnt - mean * mean : 0.0;
+        if (var < 0) var = 0;
+        const float k = gamma[ch] * (float)(1.0 / sqrt(var + (double)eps));
+        float shift = beta[ch] + (0.0f - (float)mean) * k;
+        float kr = 1.0f;
+        if (res_sums != nullptr) {
+          const double mr = cnt > 0 ? res_sums[i * 2] / cnt : 0.0;
+          double vr = cnt > 0 ? res_sums[i * 2 + 1] / cnt - mr * mr : 0.0;
+          if (vr < 0) vr = 0;
+          kr = res_gamma[ch] * (float)(1.0 / sqrt(vr + (double)eps));
+          shift += res_beta[ch] + (0.0f - (float)mr) * kr;
+        }
+        sc[ch] = k; sh[ch] = shift; rc[ch] = kr;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { rs[k] = sc[cv * 8 + k]; rh[k] = sh[cv * 8 + k]; rq[k] = rc[cv * 8 + k]; }
+      cur = seg;
+    }
+    const uint4* xb = x + (long long)crop * hw * c8;
+    const long long row0 = (long long)crop * hw;
+    for (int r0 = rl; r0 < hw; r0 += 4 * lanes) {
+      uint4 v[4], rv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * lanes;
+        v[u] = r < hw ? __ldg(xb + (long long)r * c8 + cv) : make_uint4(0u, 0u, 0u, 0u);
+        if (residual != nullptr) rv[u] = r < hw ? __ldg(residual + (row0 + r) * res_pitch8 + cv) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * lanes;
+        if (r >= hw) break;
+        const __half2* hh = reinterpret_cast<const __half2*>(&v[u]);
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 t = __half22float2(hh[k]);
+          f[2 * k] = fmaf(t.x, rs[2 * k], rh[2 * k]);
+          f[2 * k + 1] = fmaf(t.y, rs[2 * k + 1], rh[2 * k + 1]);
+        }
+        if (residual != nullptr) {
+          const __half2* rr = reinterpret_cast<const __half2*>(&rv[u]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 t = __half22float2(rr[k]);
+            f[2 * k] = fmaf(t.x, rq[2 * k], f[2 * k]);
+            f[2 * k + 1] = fmaf(t.y, rq[2 * k + 1], f[2 * k + 1]);
+          }
+        }
+        if (act == VCB_ACT_RELU) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+        y[(row0 + r) * y_pitch8 + cv] = o;
+      }
+    }
+  }
+}
+
 static int crops_per_block(int n, int hw, int c, int target_bytes) {
   long long per_crop = (long long)hw * c * 2;
   int cpb = (int)(target_bytes / (per_crop > 0 ? per_crop : 1));
@@ -671,6 +761,20 @@ int bn_seg_apply_f16(const void* x, int c, int h, int w, int n, const int* seg_o
                                                               reinterpret_cast<const float2*>(affine), reinterpret_cast<const uint4*>(residual),
                                                               res_pitch / 8, act, pool, reinterpret_cast<uint4*>(y), y_pitch / 8);
   return check_cuda(cudaGetLastError(), "bn_seg_apply_f16 launch");
+}
+
+int bn_seg_apply_fused_f16(const void* x, int c, int hw, int n, const int* seg_of_crop, const int* seg_crops, const double* sums,
+                           const float* gamma, const float* beta, float eps, const void* residual, int res_pitch, const double* res_sums,
+                           const float* res_gamma, const float* res_beta, int act, void* y, int y_pitch, cudaStream_t st) {
+  if (!x || !seg_of_crop || !seg_crops || !sums || !gamma || !beta || !y || n <= 0 || hw <= 0 || c <= 0 || (c & 7) || c > 512 ||
+      ((c / 8) & (c / 8 - 1)) || (y_pitch & 7) || (residual && (res_pitch & 7)) || ((uintptr_t)x & 15) || ((uintptr_t)y & 15) ||
+      ((uintptr_t)residual & 15) || (res_sums && (!residual || !res_gamma || !res_beta)) || (act != VCB_ACT_NONE && act != VCB_ACT_RELU))
+    return set_error(VCB_ERR_INVALID, "bn_seg_apply_fused_f16: bad argument (c must be 8 * a power of two, <= 512)");
+  const int cpb = crops_per_block(n, hw, c, 131072);
+  bn_seg_apply_fused_f16_kernel<<<(n + cpb - 1) / cpb, 256, 0, st>>>(
+      reinterpret_cast<const uint4*>(x), c / 8, hw, n, cpb, seg_of_crop, seg_crops, sums, gamma, beta, eps, reinterpret_cast<const uint4*>(residual),
+      res_pitch / 8, res_sums, res_gamma, res_beta, act, reinterpret_cast<uint4*>(y), y_pitch / 8);
+  return check_cuda(cudaGetLastError(), "bn_seg_apply_fused_f16 launch");
 }
 
 }  // namespace vcb

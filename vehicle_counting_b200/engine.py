@@ -790,7 +790,13 @@ class ReidEngine:
         plan.add(zero_sums, "zero BN sums")
         bn_i = [0]
 
-        def conv_bn(x: TRef, wname, bias_name, bnp, co, k, s, p, act, residual: Optional[TRef], pool=False, flops=None) -> TRef:
+        fuse_apply = os.environ.get("VCB_BN_FUSED_APPLY", "1") != "0"
+
+        def conv_bn(x: TRef, wname, bias_name, bnp, co, k, s, p, act, residual: Optional[TRef], pool=False, flops=None, raw_only=False,
+                    res_bn=None):
+            """conv -> statistics -> normalise (+ residual) -> act.  `raw_only`: stop after the statistics and return (raw, sums, gamma,
+            beta) -- the caller's next conv_bn normalises this tensor as its residual (`res_bn`), so the downsample branch of a block
+            costs no apply pass of its own.  $VCB_BN_FUSED_APPLY=0: finalize table + vcb_bn_seg_apply_f16 per BatchNorm (round-2 form)."""
             w = sd[wname].to(device=dev, dtype=torch.float32)
             if w.shape[1] != x.c:
                 w = _pad_cin(w, x.c)
@@ -804,8 +810,21 @@ class ReidEngine:
                               stats=(self.seg_of_crop, sl) if self.epi_stats else None)
             if not (self.epi_stats and fused):          # statistics from the convolution's epilogue, else one more pass over the tensor
                 plan.add(lambda st, raw=raw, sl=sl: ops.bn_seg_stats_f16(raw.buf, co, osz * osz, nb, self.seg_of_crop, sl, stream=st), f"bn stats c={co}")
+            if raw_only:
+                return raw, sl, g, be
             out_sz = (osz + 1) // 2 if pool else osz
             y = TRef(buf(out_sz, co), 0, co)
+            if fuse_apply and not pool:
+                rs, rg, rb = (res_bn[1], res_bn[2], res_bn[3]) if res_bn is not None else (None, None, None)
+                res = res_bn[0] if res_bn is not None else residual
+                plan.keep += [t for t in (rs, rg, rb) if t is not None]
+                plan.add(lambda st, raw=raw, sl=sl, y=y, res=res, rs=rs, rg=rg, rb=rb: ops.bn_seg_apply_fused_f16(
+                    raw.buf, co, osz * osz, nb, self.seg_of_crop, self.seg_crops, sl, g, be, REID_BN_EPS,
+                    None if res is None else res.ptr, 0 if res is None else res.pitch, act, y.buf, co,
+                    res_sums=rs, res_gamma=rg, res_beta=rb, stream=st),
+                    f"bn apply c={co}" + (" (+BN of the residual)" if res_bn is not None else ""))
+                return y
+            assert res_bn is None
             aff = torch.zeros(S, co, 2, dtype=torch.float32, device=dev)
             plan.keep += [aff]
             plan.add(lambda st, sl=sl, aff=aff: ops.bn_seg_finalize(sl, self.seg_crops, S, co, osz * osz, g, be, None, REID_BN_EPS, aff, stream=st),
@@ -869,6 +888,10 @@ class ReidEngine:
         for prefix, ci, co, down in REID_BLOCKS:
             s_ = 2 if down else 1
             t = conv_bn(cur, prefix + ".conv1.weight", None, prefix + ".bn1", co, 3, s_, 1, L.ACT_RELU, None)
+            if down and fuse_apply:       # the downsample branch stays pre-BN; the block's last apply normalises it as its residual
+                rb = conv_bn(cur, prefix + ".downsample.0.weight", None, prefix + ".downsample.1", co, 1, 2, 0, L.ACT_NONE, None, raw_only=True)
+                cur = conv_bn(t, prefix + ".conv2.weight", None, prefix + ".bn2", co, 3, 1, 1, L.ACT_RELU, None, res_bn=rb)
+                continue
             sc = conv_bn(cur, prefix + ".downsample.0.weight", None, prefix + ".downsample.1", co, 1, 2, 0, L.ACT_NONE, None) if down else cur
             cur = conv_bn(t, prefix + ".conv2.weight", None, prefix + ".bn2", co, 3, 1, 1, L.ACT_RELU, sc)
         assert cur.h == 4

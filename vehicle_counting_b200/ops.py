@@ -141,6 +141,14 @@ def bn_seg_finalize(sums, seg_crops, num_seg_plus1, c, hw, gamma, beta, bias, ep
                                          L.ptr(affine), _st(stream)), "vcb_bn_seg_finalize")
 
 
+def bn_seg_apply_fused_f16(x, c, hw, n, seg_of_crop, seg_crops, sums, gamma, beta, eps, residual, res_pitch, act, y, y_pitch, res_sums=None,
+                           res_gamma=None, res_beta=None, stream=None) -> None:
+    """finalize + apply in one launch; `res_sums` / `res_gamma` / `res_beta`: the residual is a pre-BN tensor normalised on the fly"""
+    L.check(L.load().vcb_bn_seg_apply_fused_f16(L.ptr(x), c, hw, n, L.ptr(seg_of_crop), L.ptr(seg_crops), L.ptr(sums), L.ptr(gamma), L.ptr(beta),
+                                                eps, L.ptr(residual), res_pitch, L.ptr(res_sums), L.ptr(res_gamma), L.ptr(res_beta), act,
+                                                L.ptr(y), y_pitch, _st(stream)), "vcb_bn_seg_apply_fused_f16")
+
+
 def reid_stem_pool_bn(patches, w_packed, affine, seg_of_crop, out, num_rois, stream=None) -> None:
     L.check(L.load().vcb_reid_stem_pool_bn(L.ptr(patches), L.ptr(w_packed), L.ptr(affine), L.ptr(seg_of_crop), L.ptr(out), num_rois,
                                            _st(stream)), "vcb_reid_stem_pool_bn")
