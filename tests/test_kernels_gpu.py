@@ -412,6 +412,11 @@ def test_reid_direct_stem_matches_torch_on_the_resized_crop(lib, n):
     if n >= 37:
         rois_np[5] = (0, 10, 10, 10, 30)                         # zero-width crop -> zeros in, bias out
         rois_np[9, 0] = 7                                        # frame index out of range -> zeros in
+        rois_np[11] = (1, 0, 0, 1, 1)                            # one pixel in the first corner (every tap clamps)
+        rois_np[12] = (1, fw - 1, fh - 1, fw, fh)                # one pixel in the last corner: the last bytes of the last frame
+        rois_np[13] = (0, 0, 0, fw, fh)                          # the whole frame (6.4x / 4.8x reduction)
+        rois_np[14] = (1, 3, 5, 5, 6)                            # 2 x 1 pixels
+        rois_np[15] = (0, fw - 2, 0, fw, fh)                     # two columns, full height
     rois = torch.from_numpy(rois_np).to(DEV)
     x = torch.zeros(n, 50, 50, 4, dtype=torch.float16, device=DEV)
     ops.roi_resize_norm(rd, frames, fh, fw, rois, x)
