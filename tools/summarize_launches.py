@@ -25,7 +25,7 @@ for k, a in sorted(agg.items(), key=lambda x: -x[1]["us"]):
     out["by_kernel"].append({"kernel": k, "launches": a["launches"], "total_us": round(a["us"], 1), "share": round(a["us"] / tot, 4),
                              "dram_read_MB_per_step": round(a["dram_read_MB"] / steps, 1), "dram_write_MB_per_step": round(a["dram_write_MB"] / steps, 1),
                              "tensor_pipe_active_pct_time_weighted": round(a["tensor_pct_x_us"] / max(a["us"], 1e-9), 1)})
-conv = [b for b in out["by_kernel"] if "conv_umma" in b["kernel"] or "conv_patch" in b["kernel"] or "reid_stem_pool" in b["kernel"]]
+conv = [b for b in out["by_kernel"] if "conv_umma" in b["kernel"] or "conv_patch" in b["kernel"] or "reid_stem_pool" in b["kernel"] or "reid_stem_direct" in b["kernel"]]
 out["conv_kernels"] = {"launches_per_step": sum(b["launches"] for b in conv) / steps, "us_per_step": round(sum(b["total_us"] for b in conv) / steps, 1),
                        "dram_bytes_per_step": int(sum(b["dram_read_MB_per_step"] + b["dram_write_MB_per_step"] for b in conv) * 1e6),
                        "share_of_step": round(sum(b["total_us"] for b in conv) / tot, 4),
