@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(256) bn_seg_apply_f16_kernel(const uint4* __re
 //   y = act( x * k + (beta - mean * k)  +  [ r * kr + (beta_r - mean_r * kr)  |  r ] ),   k = gamma / sqrt(var + eps)
 // mean / var per (segment, channel) from sums[seg][c][2] over seg_crops[seg] * hw values, computed once per block and segment in
 // shared memory with the arithmetic of bn_seg_finalize_kernel; a thread then keeps the 8 channels it always meets in registers.
-__global__ void __launch_bounds__(256) bn_seg_apply_fused_f16_kernel(const uint4* __restrict__ x, int c8, int hw, int n, int cpb,
+__global__ void __launch_bounds__(256, 3) bn_seg_apply_fused_f16_kernel(const uint4* __restrict__ x, int c8, int hw, int n, int cpb,
                                                                       const int* __restrict__ seg_of_crop, const int* __restrict__ seg_crops,
                                                                       const double* __restrict__ sums, const float* __restrict__ gamma,
                                                                       const float* __restrict__ beta, float eps,
