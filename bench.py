@@ -171,7 +171,7 @@ def workload_config(a, batch):
             "frames_per_step_per_gpu": batch, "rois_per_frame": a.rois,
             "reid_bn": "batch statistics per frame's call (reference: Extractor never calls .eval())" if a.reid_bn == "train" else "folded (eval)",
             "conf": 0.25, "iou": 0.45, "max_det": 300,
-            "sharding": "frames round-robin over ranks; one NCCL all-gather of int64[3] counters at the end",
+            "sharding": "frames round-robin over ranks; one NCCL all-gather of int64[5] counters (frames, detections, crops, H2D probe, bound cores) at the end",
             "l2": "inputs rotate through a pool of distinct batches larger than L2; per-step activations (GBs) exceed L2"}
 
 
@@ -205,6 +205,47 @@ def per_launch_times(plans, reps=3):
     return out
 
 
+def pin_to_gpu_local_cores(gpu_index: int, local_rank: int, local_world: int) -> list:
+    """Multi-rank runs: bind this process to its share of the cores NVML reports as local to its GPU (ranks whose GPUs report the
+    same core set -- one NUMA domain for all eight GPUs on the round-1 box -- split it evenly), so that the host side of the numpy
+    surface (gathers, result conversion) and the H2D staging of a rank stay on memory next to its PCIe root.  Returns the cores."""
+    try:
+        all_cpus = sorted(os.sched_getaffinity(0))
+        cpus = all_cpus
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            n = (max(all_cpus) + 64) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+            near = [c for c in all_cpus if (mask[c // 64] >> (c % 64)) & 1]
+            if near:
+                cpus = near
+        except Exception:
+            pass
+        k = max(1, len(cpus) // max(local_world, 1))
+        mine = cpus[(local_rank % max(len(cpus) // k, 1)) * k:][:k] or cpus
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return []
+
+
+def h2d_probe_gbps(dev, nbytes: int = 80 << 20, reps: int = 5) -> float:
+    """pinned -> device copy bandwidth of this rank (all ranks copy at the same time when the caller puts a barrier in front)"""
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return nbytes * reps / (e0.elapsed_time(e1) / 1e3) / 1e9
+
+
 def run_ours(a) -> dict:
     import torch.distributed as dist
     from vehicle_counting_b200 import _lib as L
@@ -219,6 +260,7 @@ def run_ours(a) -> dict:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = pin_to_gpu_local_cores(local, local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))) if world > 1 else []
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
@@ -392,7 +434,9 @@ def run_ours(a) -> dict:
     launches = sum(p.graph.num_kernels for p in plans if p.graph is not None)
 
     ms_dev, ms_e2e = max_over_ranks([ms_dev, ms_e2e], device=dev)
-    per_rank = gather_counters([a.steps * B, n_det, n_feat], device=dev)
+    barrier()
+    h2d_gbps = h2d_probe_gbps(dev)                      # every rank copies at the same time: the host-side ceiling of the e2e arm
+    per_rank = gather_counters([a.steps * B, n_det, n_feat, int(h2d_gbps * 1000), len(cores)], device=dev)
     totals = [sum(c[i] for c in per_rank) for i in range(3)]
 
     peaks = _peaks()
@@ -427,6 +471,8 @@ def run_ours(a) -> dict:
                             "yolo_frac": yolo_tf / peaks["tflops_sustained"], "yolo_tflops": yolo_tf, "yolo_conv_ms_per_step": times[0][0],
                             "whole_step_tensor_frac": conv_flops / (ms_dev / 1e3) / 1e12 / peaks["tflops_sustained"]},
                "counters": {"frames": totals[0], "detections": totals[1], "crops": totals[2], "detections_last_step_rank0": det_total},
+               "host": {"h2d_probe_GBps_per_rank": [round(c[3] / 1000.0, 1) for c in per_rank], "pinned_cores_per_rank": [int(c[4]) for c in per_rank],
+                        "note": "pinned->device copy rate with all ranks copying at once; ranks > 1 are bound to their share of the GPU-local cores"},
                "kernels_per_step": int(launches)}
         if with_reid:
             out["roofline"]["reid_tflops"] = plans[1].conv_flops / (times[1][0] / 1e3) / 1e12

@@ -260,6 +260,13 @@ for _tag, _kw in (("48-96-s2", dict(n=64, h=320, w=320, cin=48, cout=96)), ("96-
         case(f"bnsweep-3x3-{_tag}-bn{_bn}", mode="tma", k=3, s=2, p=1, act="silu", block_n=_bn, **_kw)
 
 
+# cin = 48 (YOLOv5m stage 1): 64-channel K chunks carry 25 % zeros; 16-channel chunks fit exactly (27 instead of 36 MMAs per 3x3 tile)
+for _bk in (0, 16):
+    case(f"bksweep-3x3s2-48-96-bk{_bk}", mode="tma", n=64, h=320, w=320, k=3, s=2, p=1, cin=48, cout=96, act="silu", bk=_bk)
+    case(f"bksweep-1x1-48-48-bk{_bk}", mode="tma", n=64, h=160, w=160, k=1, cin=48, cout=48, cin_pitch=96, cout_pitch=48, act="silu", bk=_bk)
+    case(f"bksweep-3x3-48-48-res-bk{_bk}", mode="tma", n=64, h=160, w=160, k=3, p=1, cin=48, cout=48, cout_pitch=96, act="silu", res="after", bk=_bk)
+
+
 def run_case(idx: int) -> dict:
     import torch
     import torch.nn.functional as F
