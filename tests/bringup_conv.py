@@ -267,6 +267,16 @@ for _bk in (0, 16):
     case(f"bksweep-3x3-48-48-res-bk{_bk}", mode="tma", n=64, h=160, w=160, k=3, p=1, cin=48, cout=48, cout_pitch=96, act="silu", res="after", bk=_bk)
 
 
+# N-tile width / kernel choice of the deep 3x3 stride-1 layers (wave quantisation: 400 pair tiles on 148 clusters, 400 tiles on 296 CTAs)
+for _tag, _kw in (("192-192-m102k", dict(n=64, h=40, w=40, cin=192, cout=192)), ("384-384-m25k", dict(n=64, h=20, w=20, cin=384, cout=384)),
+                  ("96-96-m409k", dict(n=64, h=80, w=80, cin=96, cout=96))):
+    for _bn in (0, 64, 128):
+        for _pair in (0, 1, 2):
+            if _bn and (_bn >= _kw["cout"] or _kw["cout"] % _bn):
+                continue
+            case(f"bn3sweep-3x3-{_tag}-bn{_bn}-pair{_pair}", mode="tma", k=3, p=1, act="silu", res="after", block_n=_bn, cta_pair=_pair, **_kw)
+
+
 def run_case(idx: int) -> dict:
     import torch
     import torch.nn.functional as F

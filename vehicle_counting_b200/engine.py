@@ -175,7 +175,9 @@ class _Plan:
                                res_mode=res_mode if residual is not None else L.RES_NONE,
                                res_pitch=residual.pitch if residual is not None else 0, out_dtype=out_dtype, a_mode=a_mode,
                                tile_rev=self.alternate and self._rev,
-                               block_n=TUNED_BLOCK_N.get((k, s, cin, cout), 0) if a_mode == L.A_AUTO and out_dtype == L.F16 else 0)
+                               block_n=TUNED_BLOCK_N.get((k, s, cin, cout), 0) if a_mode == L.A_AUTO and out_dtype == L.F16 else 0,
+                               cta_pair=TUNED_CTA_PAIR.get((k, s, cin, cout), 0) if a_mode == L.A_AUTO and out_dtype == L.F16 and stats is None
+                               and n * ((x.h + 2 * p - k) // s + 1) * ((x.w + 2 * p - k) // s + 1) >= 16384 else 0)
         self._rev = not self._rev
         ho, wo = ops.conv_out_hw(d)
         assert (ho, wo) == (y.h, y.w), ((ho, wo), (y.h, y.w))
@@ -238,6 +240,10 @@ _ROWWIN_OK: Optional[bool] = None
 # the 256 TMEM columns of a two-per-SM CTA, so MMA and epilogue serialise; narrower tiles keep two stages at the price of fetching
 # the activation tile once per N tile -- a win only while K is small.  (k, stride, cin, cout) -> block_n
 TUNED_BLOCK_N = {(1, 1, 192, 192): 64, (1, 1, 384, 384): 128, (3, 2, 384, 768): 128}
+# ... and where the CTA-pair kernel wins although the library's rule (two waves of pair tiles) does not pick it: 3x3 384->384 at
+# M = 25 600 (one wave and a third of 256-row tiles): 83.0 -> 74.9 us (profiles/r02_bnsweep.jsonl).  (k, stride, cin, cout) -> cta_pair,
+# applied from 16 384 output pixels up
+TUNED_CTA_PAIR = {(3, 1, 384, 384): 2}
 
 
 def SILU_DEFAULT() -> bool:
