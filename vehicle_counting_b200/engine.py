@@ -171,13 +171,15 @@ class _Plan:
         (vcb_conv2d_fwd_stats); returns False when the geometry cannot do that (the plain launch is queued, the caller adds the
         separate statistics kernel)."""
         cout, cin = int(w.shape[0]), int(w.shape[1])
+        m_out = n * ((x.h + 2 * p - k) // s + 1) * ((x.w + 2 * p - k) // s + 1)
+        tb, tp = tuned_choice(k, s, cin, cout, residual is not None, m_out) if (a_mode == L.A_AUTO and out_dtype == L.F16 and stats is None) else (0, 0)
+        if CONV_SHAPE_LOG is not None:
+            CONV_SHAPE_LOG.append(dict(n=n, h=x.h, w=x.w, cin=cin, cin_pitch=x.pitch, cout=cout, cout_pitch=y.pitch, k=k, s=s, p=p, act=act,
+                                       res=(res_mode if residual is not None else L.RES_NONE), out_dtype=out_dtype, a_mode=a_mode))
         d = ops.make_conv_desc(n, x.h, x.w, cin, cout, k, s, p, cin_pitch=x.pitch, cout_pitch=y.pitch, act=act,
                                res_mode=res_mode if residual is not None else L.RES_NONE,
                                res_pitch=residual.pitch if residual is not None else 0, out_dtype=out_dtype, a_mode=a_mode,
-                               tile_rev=self.alternate and self._rev,
-                               block_n=TUNED_BLOCK_N.get((k, s, cin, cout), 0) if a_mode == L.A_AUTO and out_dtype == L.F16 else 0,
-                               cta_pair=TUNED_CTA_PAIR.get((k, s, cin, cout), 0) if a_mode == L.A_AUTO and out_dtype == L.F16 and stats is None
-                               and n * ((x.h + 2 * p - k) // s + 1) * ((x.w + 2 * p - k) // s + 1) >= 16384 else 0)
+                               tile_rev=self.alternate and self._rev, block_n=tb, cta_pair=tp)
         self._rev = not self._rev
         ho, wo = ops.conv_out_hw(d)
         assert (ho, wo) == (y.h, y.w), ((ho, wo), (y.h, y.w))
@@ -244,6 +246,31 @@ TUNED_BLOCK_N = {(1, 1, 192, 192): 64, (1, 1, 384, 384): 128, (3, 2, 384, 768): 
 # M = 25 600 (one wave and a third of 256-row tiles): 83.0 -> 74.9 us (profiles/r02_bnsweep.jsonl).  (k, stride, cin, cout) -> cta_pair,
 # applied from 16 384 output pixels up
 TUNED_CTA_PAIR = {(3, 1, 384, 384): 2}
+
+# The complete per-layer table: data/tuned_layers.json, written by tools/autotune_layers.py on a B200 (every convolution shape of the
+# BASELINE configurations x {N-tile width, single / pair / patch kernel}, each timed with CUDA events and checked against the
+# library's own choice; an entry exists only where a variant was >= 3 % faster).  Key "k,s,cin,cout,res,log2(M)" -> [block_n, cta_pair].
+# $VCB_TUNED=0 ignores it (and the two small tables above remain).
+_TUNED_TABLE: Optional[dict] = None
+CONV_SHAPE_LOG: Optional[list] = [] if os.environ.get("VCB_LOG_CONV_SHAPES") == "1" else None
+
+
+def tuned_choice(k: int, s: int, cin: int, cout: int, has_res: bool, m: int) -> Tuple[int, int]:
+    """(block_n, cta_pair) for a convolution of this shape; (0, 0) = the library's own choice"""
+    global _TUNED_TABLE
+    if _TUNED_TABLE is None:
+        _TUNED_TABLE = {}
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "tuned_layers.json")
+        if os.environ.get("VCB_TUNED", "1") != "0" and os.path.isfile(path):
+            import json
+            with open(path) as f:
+                _TUNED_TABLE = {kk: tuple(v[:2]) for kk, v in json.load(f).get("layers", {}).items()}
+    key = f"{k},{s},{cin},{cout},{int(has_res)},{int(round(math.log2(max(m, 1))))}"
+    if key in _TUNED_TABLE:
+        return _TUNED_TABLE[key]
+    if os.environ.get("VCB_TUNED", "1") == "0":
+        return 0, 0
+    return TUNED_BLOCK_N.get((k, s, cin, cout), 0), (TUNED_CTA_PAIR.get((k, s, cin, cout), 0) if m >= 16384 else 0)
 
 
 def SILU_DEFAULT() -> bool:
