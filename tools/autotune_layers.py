@@ -25,17 +25,18 @@ DEV = torch.device("cuda:0")
 
 def collect():
     L.init(0)
-    for name, b, h, w in (("yolov5m", 64, 640, 640), ("yolov5s", 32, 640, 640), ("yolov5m", 32, 1024, 1024), ("yolov5l", 64, 384, 640),
-                          ("yolov5l", 16, 736, 1280)):
+    for name, b, h, w in (("yolov5m", 64, 640, 640), ("yolov5m", 128, 640, 640), ("yolov5s", 32, 640, 640), ("yolov5s", 8, 640, 640),
+                          ("yolov5m", 32, 1024, 1024), ("yolov5l", 64, 384, 640), ("yolov5l", 32, 384, 640), ("yolov5l", 16, 736, 1280)):
         eng = E.YoloEngine(synth_yolov5_state_dict(name, seed=0), b, h, w, model_name=name)
         del eng
         torch.cuda.empty_cache()
     rsd = synth_reid_state_dict(0)
     for mode in ("eval", "train"):
         r = E.ReidEngine(rsd, capacity=4096, bn_mode=mode, max_segments=64)
-        rois = np.zeros((4096, 5), np.int32); rois[:, 0] = np.repeat(np.arange(64), 64); rois[:, 3:] = 100
-        r.run(torch.zeros(64, 640, 640, 3, dtype=torch.uint8, device=DEV), rois, seg_sizes=[64] * 64)
-        torch.cuda.synchronize()
+        for nc in (64, 1024, 2048, 4096):            # one frame per call, configs[4] at 16 frames, configs[2], the default step
+            rois = np.zeros((nc, 5), np.int32); rois[:, 0] = np.repeat(np.arange(nc // 64), 64); rois[:, 3:] = 100
+            r.run(torch.zeros(64, 640, 640, 3, dtype=torch.uint8, device=DEV), rois, seg_sizes=[64] * (nc // 64))
+            torch.cuda.synchronize()
         del r
         torch.cuda.empty_cache()
     uniq = {}
@@ -86,7 +87,7 @@ def main():
         ho = (c["h"] + 2 * c["p"] - c["k"]) // c["s"] + 1
         wo = (c["w"] + 2 * c["p"] - c["k"]) // c["s"] + 1
         m = c["n"] * ho * wo
-        key = f'{c["k"]},{c["s"]},{c["cin"]},{c["cout"]},{int(c["res"] != 0)},{int(round(math.log2(max(m, 1))))}'
+        key = f'{c["k"]},{c["s"]},{c["cin"]},{c["cout"]},{int(c["res"] != 0)},{c["h"]}x{c["w"]},{int(round(math.log2(max(c["n"], 1))))}'
         try:
             base, ref = time_variant(c, 0, 0)
         except Exception as e:
@@ -116,7 +117,7 @@ def main():
             if prev is None or prev[3] > best[0]:
                 table[key] = [best[1], best[2], round(base, 1), round(best[0], 1)]
         print(f'{key:28s} M={m:8d} default {base:7.1f} us  best {best[0]:7.1f} us (block_n={best[1]}, cta_pair={best[2]})  {"*" if key in table else ""}', flush=True)
-    out = {"device": torch.cuda.get_device_name(0), "note": "key = k,s,cin,cout,res,round(log2(M)); value = [block_n, cta_pair, default us, tuned us]",
+    out = {"device": torch.cuda.get_device_name(0), "note": "key = k,s,cin,cout,res,HxW of the input,round(log2(n)); value = [block_n, cta_pair, default us, tuned us]",
            "layers": table}
     path = os.path.join(ROOT, "vehicle_counting_b200", "data", "tuned_layers.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)

@@ -172,7 +172,7 @@ class _Plan:
         separate statistics kernel)."""
         cout, cin = int(w.shape[0]), int(w.shape[1])
         m_out = n * ((x.h + 2 * p - k) // s + 1) * ((x.w + 2 * p - k) // s + 1)
-        tb, tp = tuned_choice(k, s, cin, cout, residual is not None, m_out) if (a_mode == L.A_AUTO and out_dtype == L.F16 and stats is None) else (0, 0)
+        tb, tp = tuned_choice(k, s, cin, cout, residual is not None, m_out, n, x.h, x.w) if (a_mode == L.A_AUTO and out_dtype == L.F16 and stats is None) else (0, 0)
         if CONV_SHAPE_LOG is not None:
             CONV_SHAPE_LOG.append(dict(n=n, h=x.h, w=x.w, cin=cin, cin_pitch=x.pitch, cout=cout, cout_pitch=y.pitch, k=k, s=s, p=p, act=act,
                                        res=(res_mode if residual is not None else L.RES_NONE), out_dtype=out_dtype, a_mode=a_mode))
@@ -249,13 +249,14 @@ TUNED_CTA_PAIR = {(3, 1, 384, 384): 2}
 
 # The complete per-layer table: data/tuned_layers.json, written by tools/autotune_layers.py on a B200 (every convolution shape of the
 # BASELINE configurations x {N-tile width, single / pair / patch kernel}, each timed with CUDA events and checked against the
-# library's own choice; an entry exists only where a variant was >= 3 % faster).  Key "k,s,cin,cout,res,log2(M)" -> [block_n, cta_pair].
+# library's own choice; an entry exists only where a variant was >= 3 % faster).  Key "k,s,cin,cout,res,HxW,round(log2(n))" (input
+# image size and batch bucket: the same GEMM shape behaves differently on 7x7 crops and on 46x80 frames) -> [block_n, cta_pair].
 # $VCB_TUNED=0 ignores it (and the two small tables above remain).
 _TUNED_TABLE: Optional[dict] = None
 CONV_SHAPE_LOG: Optional[list] = [] if os.environ.get("VCB_LOG_CONV_SHAPES") == "1" else None
 
 
-def tuned_choice(k: int, s: int, cin: int, cout: int, has_res: bool, m: int) -> Tuple[int, int]:
+def tuned_choice(k: int, s: int, cin: int, cout: int, has_res: bool, m: int, n: int = 0, h: int = 0, w: int = 0) -> Tuple[int, int]:
     """(block_n, cta_pair) for a convolution of this shape; (0, 0) = the library's own choice"""
     global _TUNED_TABLE
     if _TUNED_TABLE is None:
@@ -265,7 +266,7 @@ def tuned_choice(k: int, s: int, cin: int, cout: int, has_res: bool, m: int) -> 
             import json
             with open(path) as f:
                 _TUNED_TABLE = {kk: tuple(v[:2]) for kk, v in json.load(f).get("layers", {}).items()}
-    key = f"{k},{s},{cin},{cout},{int(has_res)},{int(round(math.log2(max(m, 1))))}"
+    key = f"{k},{s},{cin},{cout},{int(has_res)},{h}x{w},{int(round(math.log2(max(n, 1))))}"      # input image size + batch bucket
     if key in _TUNED_TABLE:
         return _TUNED_TABLE[key]
     if os.environ.get("VCB_TUNED", "1") == "0":
