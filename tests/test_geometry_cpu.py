@@ -2,8 +2,12 @@
 runs the same conv_geometry() the launch uses (tile mode, stages, shared-memory / TMEM budget), so a shape that would be
 rejected at launch ("not enough shared memory", bad N tile, ...) fails here.  Shapes come from a meta-device pass over the
 oracle's YOLOv5 graph (n/s/m/l/x) and from the ReID network's layer table."""
+import os
+
 import pytest
 import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 from torch import nn
 
 
@@ -95,3 +99,34 @@ def test_cv2_linear_table_reproduces_cv2_resize():
         out = (((yt[:, 2, None, None] * (H[yt[:, 0]] >> 4)) >> 16) + ((yt[:, 3, None, None] * (H[yt[:, 1]] >> 4)) >> 16) + 2) >> 2
         np.testing.assert_array_equal(np.clip(out, 0, 255).astype(np.uint8), cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR),
                                       err_msg=str((sh, sw, dh, dw)))
+
+
+def test_tuned_layer_table_is_well_formed_and_only_applies_to_measured_shapes(monkeypatch):
+    """data/tuned_layers.json (tools/autotune_layers.py on a B200): keys 'k,s,cin,cout,res,HxW,round(log2 n)', values
+    [block_n, cta_pair, default us, tuned us] with a >= 3 % gain; the engine applies an entry to exactly that shape and falls back to
+    the library's own choice (plus the two small built-in tables) elsewhere; VCB_TUNED=0 switches everything off."""
+    import json
+    from vehicle_counting_b200 import engine as E
+    path = os.path.join(ROOT, "vehicle_counting_b200", "data", "tuned_layers.json")
+    layers = json.load(open(path))["layers"]
+    assert len(layers) > 50
+    for key, v in layers.items():
+        k, s, cin, cout, res, hw, lg = key.split(",")
+        h, w = hw.split("x")
+        assert int(k) in (1, 3) and int(s) in (1, 2) and int(res) in (0, 1) and int(h) > 0 and int(w) > 0 and 0 <= int(lg) <= 13
+        bn, cp, us0, us1 = v
+        assert bn in (0, 64, 128) and cp in (0, 1, 2, 4, 5) and (bn, cp) != (0, 0)
+        assert bn == 0 or (int(cout) % bn == 0 and bn < int(cout))
+        assert us1 <= 0.97 * us0 + 1e-9
+    monkeypatch.setattr(E, "_TUNED_TABLE", None)
+    key = next(iter(layers))
+    k, s, cin, cout, res, hw, lg = key.split(",")
+    h, w = (int(v) for v in hw.split("x"))
+    n = 2 ** int(lg)
+    assert E.tuned_choice(int(k), int(s), int(cin), int(cout), bool(int(res)), n * h * w, n, h, w) == tuple(layers[key][:2])
+    assert E.tuned_choice(3, 1, 40, 40, False, 1000, 1, 25, 40) == (0, 0)                     # unknown shape: the library decides
+    assert E.tuned_choice(1, 1, 192, 192, False, 5000, 3, 33, 50) == (64, 0)                  # built-in table, small M: no pair override
+    monkeypatch.setattr(E, "_TUNED_TABLE", None)
+    monkeypatch.setenv("VCB_TUNED", "0")
+    assert E.tuned_choice(int(k), int(s), int(cin), int(cout), bool(int(res)), n * h * w, n, h, w) == (0, 0)
+    monkeypatch.setattr(E, "_TUNED_TABLE", None)
