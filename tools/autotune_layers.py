@@ -41,7 +41,7 @@ def collect():
         torch.cuda.empty_cache()
     uniq = {}
     for c in E.CONV_SHAPE_LOG:
-        if c["a_mode"] != L.A_AUTO or c["out_dtype"] != L.F16:
+        if c["a_mode"] != L.A_AUTO:
             continue
         uniq[tuple(sorted(c.items()))] = c
     return list(uniq.values())
@@ -54,10 +54,10 @@ def time_variant(c, block_n, cta_pair, ref=None):
     wt = (torch.randn(c["cout"], c["cin"], c["k"], c["k"], generator=g) / (c["cin"] * c["k"] ** 2) ** 0.5).to(DEV)
     bias = (torch.randn(c["cout"], generator=g) * 0.3).to(DEV)
     d = ops.make_conv_desc(n, h, w, c["cin"], c["cout"], c["k"], c["s"], c["p"], cin_pitch=c["cin_pitch"], cout_pitch=c["cout_pitch"], act=c["act"],
-                           res_mode=c["res"], res_pitch=c["cout_pitch"] if c["res"] else 0, block_n=block_n, cta_pair=cta_pair)
+                           res_mode=c["res"], res_pitch=c["cout_pitch"] if c["res"] else 0, out_dtype=c["out_dtype"], block_n=block_n, cta_pair=cta_pair)
     ho, wo = ops.conv_out_hw(d)
     wp, bp = ops.pack_conv_weights(d, wt, bias)
-    y = torch.zeros(n, ho, wo, c["cout_pitch"], dtype=torch.float16, device=DEV)
+    y = torch.zeros(n, ho, wo, c["cout_pitch"], dtype=torch.float32 if c["out_dtype"] == L.F32 else torch.float16, device=DEV)
     res = (torch.randn(n, ho, wo, c["cout_pitch"], generator=g)).half().to(DEV) if c["res"] else None
     for _ in range(3):
         ops.conv2d(d, x, wp, bp, y, residual=res)
@@ -84,10 +84,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only-k", type=int, default=0, help="1 or 3: tune only layers with this filter size and MERGE into the existing table")
     ap.add_argument("--pairs-1x1", default="1", help="cta_pair candidates for 1x1 layers (comma separated)")
+    ap.add_argument("--only-f32", action="store_true", help="only the fp32-output layers (Detect heads); merges into the existing table")
     a = ap.parse_args()
     shapes = collect()
     if a.only_k:
         shapes = [c for c in shapes if c["k"] == a.only_k]
+    if a.only_f32:
+        shapes = [c for c in shapes if c["out_dtype"] == L.F32]
+        a.only_k = a.only_k or 1
     print(len(shapes), "distinct convolution shapes", flush=True)
     table, rows = {}, []
     path0 = os.path.join(ROOT, "vehicle_counting_b200", "data", "tuned_layers.json")

@@ -172,7 +172,7 @@ class _Plan:
         separate statistics kernel)."""
         cout, cin = int(w.shape[0]), int(w.shape[1])
         m_out = n * ((x.h + 2 * p - k) // s + 1) * ((x.w + 2 * p - k) // s + 1)
-        tb, tp = tuned_choice(k, s, cin, cout, residual is not None, m_out, n, x.h, x.w) if (a_mode == L.A_AUTO and out_dtype == L.F16 and stats is None) else (0, 0)
+        tb, tp = tuned_choice(k, s, cin, cout, residual is not None, m_out, n, x.h, x.w) if (a_mode == L.A_AUTO and stats is None) else (0, 0)
         if CONV_SHAPE_LOG is not None:
             CONV_SHAPE_LOG.append(dict(n=n, h=x.h, w=x.w, cin=cin, cin_pitch=x.pitch, cout=cout, cout_pitch=y.pitch, k=k, s=s, p=p, act=act,
                                        res=(res_mode if residual is not None else L.RES_NONE), out_dtype=out_dtype, a_mode=a_mode))
