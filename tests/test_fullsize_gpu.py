@@ -12,6 +12,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _iou(a, b):
@@ -144,3 +145,45 @@ def test_conv_full_layer_linearity_and_variant_equality(lib):
     assert lin <= 2e-5 * y12.abs().max().item(), lin
     for mode in (4, 3):                 # CTA pairs with two clusters per SM pair; 256-row tiles
         assert torch.equal(run(x1, mode), y1), mode
+
+
+def test_every_tuned_layer_variant_computes_what_the_default_kernel_computes(lib):
+    """data/tuned_layers.json picks a kernel variant (N-tile width, CTA pair, patch kernel) per convolution shape of the BASELINE
+    configurations at their FULL sizes.  Every entry: the variant's output equals the library's own choice on the same seeded
+    operands up to the accumulation order (2e-3 of the output range; a wrong tiling would be off by O(1))."""
+    import json
+    from vehicle_counting_b200 import ops, _lib as L
+    layers = json.load(open(os.path.join(ROOT, "vehicle_counting_b200", "data", "tuned_layers.json")))["layers"]
+    checked = 0
+    for key, v in sorted(layers.items()):
+        k, s, cin, cout, res, hw, lg = key.split(",")
+        k, s, cin, cout, res, n = int(k), int(s), int(cin), int(cout), int(res), 2 ** int(lg)
+        h, w = (int(t) for t in hw.split("x"))
+        f32 = cout == 255                                            # the Detect heads write fp32 logits
+        cp = (cout + 7) // 8 * 8
+        if n * h * w * max(cin, cp) * (4 if f32 else 2) > 3 << 30:
+            continue
+        g = torch.Generator().manual_seed(checked)
+        x = torch.randn(n, h, w, cin, generator=g).half().to(DEV)
+        wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+        b = (torch.randn(cout, generator=g) * 0.3).to(DEV)
+        p = k // 2
+        outs = []
+        for bn, pair in ((0, 0), (v[0], v[1])):
+            d = ops.make_conv_desc(n, h, w, cin, cout, k, s, p, cout_pitch=cp, act=L.ACT_NONE if f32 else L.ACT_SILU,
+                                   res_mode=L.RES_AFTER_ACT if res else L.RES_NONE, res_pitch=cp if res else 0,
+                                   out_dtype=L.F32 if f32 else L.F16, block_n=bn, cta_pair=pair)
+            ho, wo = ops.conv_out_hw(d)
+            wp, bp = ops.pack_conv_weights(d, wt, b)
+            y = torch.zeros(n, ho, wo, cp, dtype=torch.float32 if f32 else torch.float16, device=DEV)
+            r = (torch.randn(n, ho, wo, cp, generator=torch.Generator().manual_seed(7)).half().to(DEV)) if res else None
+            ops.conv2d(d, x, wp, bp, y, residual=r)
+            outs.append(y[..., :cout].float())
+            del y, wp, bp, r
+        torch.cuda.synchronize()
+        assert tuple(L.last_fault()) == (0, 0, 0, 0), key
+        err = (outs[0] - outs[1]).abs().max().item()
+        assert err <= 2e-3 * max(1.0, outs[0].abs().max().item()), (key, v, err)
+        checked += 1
+        del outs, x
+    assert checked >= 150
