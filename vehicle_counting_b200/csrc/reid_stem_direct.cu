@@ -5,15 +5,18 @@
 // crops and read them back (twice under train-mode BatchNorm) for 450 MB of algorithmic traffic.  Same reference lines:
 //   /root/reference/networks/deepsort/deep/feature_extractor.py:26-39  (crop preprocessing)
 //   /root/reference/networks/deepsort/deep/model.py:52-60             (stem conv + BN + ReLU + MaxPool2d(3, 2, padding=1))
-// Every CTA owns a contiguous range of crops.  Four producer warps keep the current crop, resized exactly like roi_resize_norm
-// (cv2 INTER_LINEAR semantics, fp16 rounding of the normalised pixel), in shared memory as a zero-bordered [52][52][3] fp16 image
-// and build, per block of 5x5 pooled pixels, the 128 x 32 im2col tile (one GEMM row per thread: three runs of nine consecutive
-// halves of the staged crop) directly in the 64-byte-swizzled layout the tensor core reads; the NEXT crop is resized into the
-// other buffer one hundred pixels per tile, so its global loads hide behind the row building.  The conv bias rides in the GEMM:
-// K slots 27 / 28 of every row hold 1.0 and the packed weights hold the bias split into an fp16 head and tail there, so the
-// accumulator is conv + bias and the epilogue keeps no per-channel registers.  MMA issue, TMEM accumulators, epilogue and the
-// shared-memory max-pool are those of reid_stem_pool_kernel; MODE 0 / 1 / 2 as there (folded BN / statistics only / per-segment
-// affine).
+// Every CTA owns a contiguous range of crops.  Eight producer warps (two groups of four; group g builds the tiles it % 2 == g) keep
+// the current crop, resized exactly like roi_resize_norm (cv2 INTER_LINEAR semantics, fp16 rounding of the normalised pixel), in
+// shared memory as a zero-bordered [52][52][3] fp16 image and build, per block of 5x5 pooled pixels, the 128 x 32 im2col tile (one
+// GEMM row per thread: three runs of nine consecutive halves of the staged crop) directly in the 64-byte-swizzled layout the tensor
+// core reads; the NEXT crop is resized into the other buffer one hundred pixels per tile, so its global loads hide behind the row
+// building (the two taps of a source row arrive as <= 3 aligned 32-bit words; u8 / 255 is an exact FMA sequence).  Thread 0 of a
+// producer group issues the two tcgen05.mma of its tile once its group has arrived.  The conv bias rides in the GEMM: K slots
+// 27 / 28 of every row hold 1.0 and the packed weights hold the bias split into an fp16 head and tail there, so the accumulator is
+// conv + bias and the epilogue keeps no per-channel registers.  Epilogue (warps 0-7): TMEM -> fp16 -> staged 11x11x64 tile ->
+// 3x3/s2 max (pool padding = the window centre re-read) -> ReLU -> 16-byte stores.  MODE 0: BatchNorm folded; MODE 1: statistics
+// only, read through the 16x256b accumulator fragment (a thread owns fixed columns: sums stay in registers across tiles); MODE 2:
+// per-segment scale / shift before the pool.  Measurements and the ncu findings that shaped it: profiles/r02_stem_direct.md.
 #include "vcb_internal.h"
 #include "vcb_ptx.cuh"
 
