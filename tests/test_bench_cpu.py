@@ -29,3 +29,27 @@ def test_cuda_arm_fails_loudly_without_a_device():
         pytest.skip("a CUDA device is present")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_rank_core_binding_partitions_the_allowed_cores():
+    """bench.pin_to_gpu_local_cores: ranks that share a core set split it into disjoint, equally sized shares (NVML is absent here,
+    so the process' own affinity mask is the set); the binding is undone afterwards."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    before = os.sched_getaffinity(0)
+    try:
+        if len(before) < 2:
+            import pytest
+            pytest.skip("one core")
+        world = 2
+        shares = []
+        for r in range(world):
+            os.sched_setaffinity(0, before)
+            shares.append(set(bench.pin_to_gpu_local_cores(0, r, world)))
+            assert os.sched_getaffinity(0) == shares[-1]
+        assert shares[0] and shares[1] and not (shares[0] & shares[1])
+        assert len(shares[0]) == len(shares[1]) == len(before) // world
+        assert (shares[0] | shares[1]) <= set(before)
+    finally:
+        os.sched_setaffinity(0, before)
