@@ -22,7 +22,8 @@ struct State {
   int device = -1;
   int num_sms = 0;
   int driver_version = 0;
-  int pdl = 0;                         // conv launches carry the programmatic-dependent-launch attribute ($VCB_PDL / vcb_set_option)
+  int pdl = 1;                         // conv launches carry the programmatic-dependent-launch attribute ($VCB_PDL=0 / vcb_set_option turn it
+                                       // off): +6-7 % at B = 1 ... 8 (grids smaller than the GPU: the next kernel's prologue overlaps), neutral at B = 64
   EncodeTiledFn encode_tiled = nullptr;
   EncodeIm2colFn encode_im2col = nullptr;
   KernelFault* fault_host = nullptr;   // pinned + mapped: still readable after a trapped kernel
