@@ -23,15 +23,18 @@ from vehicle_counting_b200.weights import synth_reid_state_dict, synth_yolov5_st
 DEV = torch.device("cuda:0")
 
 
-def collect():
+DEFAULT_YOLO = (("yolov5m", 64, 640, 640), ("yolov5m", 128, 640, 640), ("yolov5s", 32, 640, 640), ("yolov5s", 8, 640, 640),
+                ("yolov5m", 32, 1024, 1024), ("yolov5l", 64, 384, 640), ("yolov5l", 32, 384, 640), ("yolov5l", 16, 736, 1280))
+
+
+def collect(yolo=DEFAULT_YOLO, reid=True):
     L.init(0)
-    for name, b, h, w in (("yolov5m", 64, 640, 640), ("yolov5m", 128, 640, 640), ("yolov5s", 32, 640, 640), ("yolov5s", 8, 640, 640),
-                          ("yolov5m", 32, 1024, 1024), ("yolov5l", 64, 384, 640), ("yolov5l", 32, 384, 640), ("yolov5l", 16, 736, 1280)):
+    for name, b, h, w in yolo:
         eng = E.YoloEngine(synth_yolov5_state_dict(name, seed=0), b, h, w, model_name=name)
         del eng
         torch.cuda.empty_cache()
     rsd = synth_reid_state_dict(0)
-    for mode in ("eval", "train"):
+    for mode in (("eval", "train") if reid else ()):
         r = E.ReidEngine(rsd, capacity=4096, bn_mode=mode, max_segments=64)
         for nc in (64, 1024, 2048, 4096):            # one frame per call, configs[4] at 16 frames, configs[2], the default step
             rois = np.zeros((nc, 5), np.int32); rois[:, 0] = np.repeat(np.arange(nc // 64), 64); rois[:, 3:] = 100
@@ -85,8 +88,14 @@ def main():
     ap.add_argument("--only-k", type=int, default=0, help="1 or 3: tune only layers with this filter size and MERGE into the existing table")
     ap.add_argument("--pairs-1x1", default="1", help="cta_pair candidates for 1x1 layers (comma separated)")
     ap.add_argument("--only-f32", action="store_true", help="only the fp32-output layers (Detect heads); merges into the existing table")
+    ap.add_argument("--yolo", default="", help="name:batch:h:w,... instead of the BASELINE list (implies merging, no ReID shapes)")
     a = ap.parse_args()
-    shapes = collect()
+    if a.yolo:
+        shapes = collect(tuple((t.split(":")[0],) + tuple(int(v) for v in t.split(":")[1:]) for t in a.yolo.split(",")), reid=False)
+        a.merge_all = True
+    else:
+        shapes = collect()
+        a.merge_all = False
     if a.only_k:
         shapes = [c for c in shapes if c["k"] == a.only_k]
     if a.only_f32:
@@ -95,7 +104,7 @@ def main():
     print(len(shapes), "distinct convolution shapes", flush=True)
     table, rows = {}, []
     path0 = os.path.join(ROOT, "vehicle_counting_b200", "data", "tuned_layers.json")
-    if a.only_k and os.path.isfile(path0):
+    if (a.only_k or a.merge_all) and os.path.isfile(path0):
         table = json.load(open(path0))["layers"]
     for c in sorted(shapes, key=lambda c: (c["k"], c["cin"], c["cout"], -c["n"] * c["h"] * c["w"])):
         ho = (c["h"] + 2 * c["p"] - c["k"]) // c["s"] + 1
@@ -135,7 +144,7 @@ def main():
                      "tried": sorted(tried)[:4]})
         if gain >= 0.03 and (best[1], best[2]) != (0, 0):
             prev = table.get(key)
-            if prev is None or prev[3] > best[0] or a.only_k:
+            if prev is None or prev[3] > best[0] or a.only_k or a.merge_all:
                 table[key] = [best[1], best[2], round(base, 1), round(best[0], 1)]
         print(f'{key:28s} M={m:8d} default {base:7.1f} us  best {best[0]:7.1f} us (block_n={best[1]}, cta_pair={best[2]})  {"*" if key in table else ""}', flush=True)
     out = {"device": torch.cuda.get_device_name(0), "note": "key = k,s,cin,cout,res,HxW of the input,round(log2(n)); value = [block_n, cta_pair, default us, tuned us]",
