@@ -27,7 +27,7 @@ DEFAULT_YOLO = (("yolov5m", 64, 640, 640), ("yolov5m", 128, 640, 640), ("yolov5s
                 ("yolov5m", 32, 1024, 1024), ("yolov5l", 64, 384, 640), ("yolov5l", 32, 384, 640), ("yolov5l", 16, 736, 1280))
 
 
-def collect(yolo=DEFAULT_YOLO, reid=True):
+def collect(yolo=DEFAULT_YOLO, reid=True, reid_ns=(64, 1024, 2048, 4096)):
     L.init(0)
     for name, b, h, w in yolo:
         eng = E.YoloEngine(synth_yolov5_state_dict(name, seed=0), b, h, w, model_name=name)
@@ -36,9 +36,10 @@ def collect(yolo=DEFAULT_YOLO, reid=True):
     rsd = synth_reid_state_dict(0)
     for mode in (("eval", "train") if reid else ()):
         r = E.ReidEngine(rsd, capacity=4096, bn_mode=mode, max_segments=64)
-        for nc in (64, 1024, 2048, 4096):            # one frame per call, configs[4] at 16 frames, configs[2], the default step
-            rois = np.zeros((nc, 5), np.int32); rois[:, 0] = np.repeat(np.arange(nc // 64), 64); rois[:, 3:] = 100
-            r.run(torch.zeros(64, 640, 640, 3, dtype=torch.uint8, device=DEV), rois, seg_sizes=[64] * (nc // 64))
+        for nc in reid_ns:                           # one frame per call, configs[4] at 16 frames, configs[2], the default step
+            per = min(nc, 64)
+            rois = np.zeros((nc, 5), np.int32); rois[:, 0] = np.repeat(np.arange(nc // per), per); rois[:, 3:] = 100
+            r.run(torch.zeros(64, 640, 640, 3, dtype=torch.uint8, device=DEV), rois, seg_sizes=[per] * (nc // per))
             torch.cuda.synchronize()
         del r
         torch.cuda.empty_cache()
@@ -88,10 +89,12 @@ def main():
     ap.add_argument("--only-k", type=int, default=0, help="1 or 3: tune only layers with this filter size and MERGE into the existing table")
     ap.add_argument("--pairs-1x1", default="1", help="cta_pair candidates for 1x1 layers (comma separated)")
     ap.add_argument("--only-f32", action="store_true", help="only the fp32-output layers (Detect heads); merges into the existing table")
+    ap.add_argument("--reid-n", default="", help="crop counts for the ReID plans, e.g. 8,16,32 (implies merging)")
     ap.add_argument("--yolo", default="", help="name:batch:h:w,... instead of the BASELINE list (implies merging, no ReID shapes)")
     a = ap.parse_args()
-    if a.yolo:
-        shapes = collect(tuple((t.split(":")[0],) + tuple(int(v) for v in t.split(":")[1:]) for t in a.yolo.split(",")), reid=False)
+    if a.yolo or a.reid_n:
+        ys = tuple((t.split(":")[0],) + tuple(int(v) for v in t.split(":")[1:]) for t in a.yolo.split(",")) if a.yolo else ()
+        shapes = collect(ys, reid=bool(a.reid_n), reid_ns=tuple(int(v) for v in a.reid_n.split(",")) if a.reid_n else ())
         a.merge_all = True
     else:
         shapes = collect()
