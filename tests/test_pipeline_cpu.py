@@ -46,3 +46,21 @@ def test_pipeline_golden_csv_shape():
     df = pd.read_csv(os.path.join(GOLD, "pipeline_golden.csv"))
     assert list(df.columns) == ["track_id", "frame_id", "box", "color", "label", "direction", "fpoint", "lpoint", "fframe", "lframe"]
     assert len(df) > 50 and df.frame_id.between(1, 8).all() and (df.fframe <= df.frame_id).all() and (df.frame_id <= df.lframe).all()
+
+
+def test_video_loader_pinned_ring_request_without_a_gpu_falls_back_to_plain_frames(tmp_path, monkeypatch):
+    """$VCB_PINNED_FRAMES asks the frame source for page-locked buffers; without a CUDA device there is nothing to pin, and the
+    loader must hand out the same frames as always."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present (the pinned path is covered by tests/test_pipeline_gpu.py)")
+    from vehicle_counting_b200.modules.datasets import VideoLoader
+    M, z, path = _clip(tmp_path)
+    cfg = types.SimpleNamespace(image_size=[640, 640], keep_ratio=True)
+    frames = M.pipeline_clip_frames(z["base"], int(z["T"]), int(z["step"]))
+    monkeypatch.setenv("VCB_PINNED_FRAMES", "4")
+    got = list(VideoLoader(cfg, path))
+    assert len(got) == len(frames)
+    for t, b in enumerate(got):
+        np.testing.assert_array_equal(b["ori_imgs"][0], frames[t])
+        np.testing.assert_array_equal(b["imgs"][0], frames[t][:, :, ::-1])
